@@ -1,0 +1,88 @@
+"""tcgen05 GEMM mainloop vs a plain fp32 torch reference (all operand major-ness combinations,
+ragged shapes, split-K, bias/ReLU, bf16/fp32 outputs)."""
+import ctypes
+
+import pytest
+import torch
+
+from vae_captioning_b200 import lib as L
+
+pytestmark = pytest.mark.gpu
+
+
+def run_gemm(M, N, K, a_mn, b_mn, bn, splits=1, relu=0, out_bf16=0, bias=True, seed=0):
+    lib = L.load()
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    # pitches padded to 8 elements so rows are 16-byte aligned
+    def pad8(x):
+        return (x + 7) // 8 * 8
+    A_log = torch.randn(M, K, generator=g)
+    B_log = torch.randn(N, K, generator=g)
+    if a_mn:
+        A_buf = torch.zeros(K, pad8(M)); A_buf[:, :M] = A_log.t(); lda = pad8(M)
+    else:
+        A_buf = torch.zeros(M, pad8(K)); A_buf[:, :K] = A_log; lda = pad8(K)
+    if b_mn:
+        B_buf = torch.zeros(K, pad8(N)); B_buf[:, :N] = B_log.t(); ldb = pad8(N)
+    else:
+        B_buf = torch.zeros(N, pad8(K)); B_buf[:, :K] = B_log; ldb = pad8(K)
+    A_d = A_buf.to(torch.bfloat16).cuda()
+    B_d = B_buf.to(torch.bfloat16).cuda()
+    bias_d = torch.randn(N, generator=g).cuda() if bias else None
+    ldo = pad8(N)
+    atomic = 1 if splits > 1 else 0
+    out = torch.zeros(M, ldo, dtype=torch.bfloat16 if out_bf16 else torch.float32, device="cuda")
+    st = lib.vc_gemm_bf16(L.ptr(A_d), a_mn, ctypes.c_longlong(lda), L.ptr(B_d), b_mn, ctypes.c_longlong(ldb),
+                          L.ptr(out), ctypes.c_longlong(ldo), L.ptr(bias_d), M, N, K, bn, splits, relu, out_bf16,
+                          atomic, L.stream_ptr())
+    L.check(st)
+    torch.cuda.synchronize()
+    ref = A_log.to(torch.bfloat16).float().cuda() @ B_log.to(torch.bfloat16).float().cuda().t()
+    if bias:
+        ref = ref + bias_d
+    if relu:
+        ref = ref.clamp_min(0)
+    got = out[:, :N].float()
+    tol = 2e-2 if out_bf16 else 2e-3
+    err = (got - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    assert err <= tol * max(1.0, scale), "M=%d N=%d K=%d a_mn=%d b_mn=%d bn=%d err=%g scale=%g" % (
+        M, N, K, a_mn, b_mn, bn, err, scale)
+    # padding columns must stay untouched
+    if ldo > N:
+        assert out[:, N:].abs().max().item() == 0
+
+
+@pytest.mark.parametrize("a_mn", [0, 1])
+@pytest.mark.parametrize("b_mn", [0, 1])
+@pytest.mark.parametrize("bn", [64, 128, 256])
+def test_gemm_major_modes(a_mn, b_mn, bn):
+    run_gemm(384, 512, 256, a_mn, b_mn, bn)
+
+
+@pytest.mark.parametrize("shape", [(6, 37, 8), (130, 300, 520), (1, 16, 64), (257, 11313 // 8, 72), (300, 200, 15000 // 10)])
+@pytest.mark.parametrize("a_mn,b_mn", [(0, 0), (1, 1), (0, 1), (1, 0)])
+def test_gemm_ragged(shape, a_mn, b_mn):
+    M, N, K = shape
+    run_gemm(M, N, K, a_mn, b_mn, 64)
+
+
+def test_gemm_small_bn():
+    for bn in (16, 32, 48):
+        run_gemm(200, 100, 192, 0, 0, bn)
+
+
+def test_gemm_splitk():
+    run_gemm(256, 256, 4096, 0, 0, 128, splits=7)
+    run_gemm(256, 256, 4096, 1, 1, 64, splits=4, bias=False)
+
+
+def test_gemm_epilogue_variants():
+    run_gemm(512, 384, 320, 0, 0, 128, relu=1, out_bf16=1)
+    run_gemm(512, 384, 320, 0, 0, 128, relu=1, out_bf16=0)
+
+
+def test_gemm_many_tiles_persistent():
+    # more tiles than SMs: exercises the persistent loop, the smem ring wrap and the TMEM double buffer
+    run_gemm(4096, 2048, 192, 0, 0, 64)
+    run_gemm(2048, 4096, 1024, 0, 0, 256)

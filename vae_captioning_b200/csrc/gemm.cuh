@@ -1,0 +1,297 @@
+// Warp-specialised persistent tcgen05 GEMM mainloop shared by every dense contraction on the
+// path (VGG16 convolutions as implicit GEMM, fc layers, the 4-gate LSTM projections, vocab logits,
+// and their dgrad / wgrad forms).
+//
+//   D[128 x BN] (fp32, TMEM) = sum_k A[128 x 64] (bf16, smem) * B[BN x 64] (bf16, smem)
+//
+// Roles (256 threads): warp 0 = TMA producer, warp 1 = tcgen05.mma issuer (one elected lane),
+// warp 2 = TMEM allocator, warps 4..7 = epilogue (one TMEM lane quarter each).
+// Three pipelines: smem full/empty ring (TMA <-> MMA), TMEM full/empty double buffer
+// (MMA <-> epilogue), and a static persistent tile schedule (tile += gridDim.x).
+//
+// Operands are staged with 128-byte swizzle. Either operand may be K-major (contraction index
+// contiguous in global memory; one TMA box {64, rows}) or MN-major (row/column index contiguous;
+// boxes {64 mn, 64 k}, 8 KiB apart) -- the UMMA descriptors carry the difference, so wgrad GEMMs
+// need no transposes. A may also come from a 4-D NHWC tensor map (3x3 SAME convolution taps with
+// TMA out-of-bounds zero fill doing the padding) or be split across two tensor maps.
+#pragma once
+#include "ptx.cuh"
+
+namespace vc {
+
+constexpr int kBM = 128;        // tile rows (UMMA M)
+constexpr int kBK = 64;         // k-block: 64 bf16 = one 128-byte swizzle row
+constexpr int kABytes = kBM * kBK * 2;
+constexpr int kGemmThreads = 256;
+constexpr int kMaxStages = 8;
+constexpr int kAccStride = 256;  // TMEM columns between the two accumulator buffers
+
+enum AMode : int { A_KMAJOR = 0, A_MNMAJOR = 1, A_CONV3x3 = 2 };
+
+struct GemmCore {
+  int m_tiles, n_tiles, k_blocks, splits;
+  int bn;        // tile columns (UMMA N): multiple of 16, <= 256; multiple of 64 when B is MN-major
+  int stages;
+  int a_mode;    // AMode
+  int b_mn;      // 1: B is MN-major
+  int a_switch;  // A_KMAJOR: k-block at which A switches to tmA2 (coordinates restart at 0)
+                 // A_MNMAJOR: m-tile at which A switches to tmA2. <0: never.
+  // A_CONV3x3 geometry: tile = bw x bh x bi pixels (bw*bh*bi == 128) of the NHWC input.
+  int bw, bh, bi, tiles_w, tiles_h, cpk;  // cpk = Cin / 64 chunks per filter tap
+};
+
+__host__ __device__ inline int gemm_stage_bytes(int bn) { return kABytes + bn * kBK * 2; }
+__host__ inline int gemm_pick_stages(int bn) {
+  int s = (227 * 1024 - 2048) / gemm_stage_bytes(bn);
+  return s > kMaxStages ? kMaxStages : s;
+}
+__host__ inline int gemm_smem_bytes(int bn, int stages) { return stages * gemm_stage_bytes(bn) + 1024 + 256; }
+
+struct TileCoord {
+  int m_blk, n_blk, split, kb_begin, kb_end;
+};
+
+__device__ __forceinline__ TileCoord decode_tile(const GemmCore& g, int tile) {
+  TileCoord t;
+  const int mn = g.m_tiles * g.n_tiles;
+  t.split = tile / mn;
+  const int rem = tile - t.split * mn;
+  t.n_blk = rem / g.m_tiles;
+  t.m_blk = rem - t.n_blk * g.m_tiles;
+  const int kps = (g.k_blocks + g.splits - 1) / g.splits;
+  t.kb_begin = t.split * kps;
+  t.kb_end = min(g.k_blocks, t.kb_begin + kps);
+  return t;
+}
+
+// Epi must provide:
+//   __device__ void operator()(uint32_t tmem_row_addr, const TileCoord& t, int row) const
+// called by each of the 128 epilogue threads (row = 0..127 = TMEM lane = tile row) once the
+// accumulator is complete. tmem_row_addr addresses column 0 of this thread's warp lane quarter.
+template <class Epi>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
+               const __grid_constant__ CUtensorMap tmB, const GemmCore g, const Epi epi) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int stage_bytes = gemm_stage_bytes(g.bn);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + g.stages * stage_bytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + kMaxStages;
+  uint64_t* tfull = bars + 2 * kMaxStages;
+  uint64_t* tempty = bars + 2 * kMaxStages + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int total_tiles = g.m_tiles * g.n_tiles * g.splits;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmA2);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < g.stages; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const TileCoord t = decode_tile(g, tile);
+        // conv tile origin
+        int cw0 = 0, ch0 = 0, ci0 = 0;
+        if (g.a_mode == A_CONV3x3) {
+          const int tw = t.m_blk % g.tiles_w;
+          const int r = t.m_blk / g.tiles_w;
+          const int th = r % g.tiles_h;
+          cw0 = tw * g.bw;
+          ch0 = th * g.bh;
+          ci0 = (r / g.tiles_h) * g.bi;
+        }
+        for (int kb = t.kb_begin; kb < t.kb_end; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * stage_bytes;
+          uint8_t* sb = sa + kABytes;
+          mbar_expect_tx(&full[stage], stage_bytes);
+          if (g.a_mode == A_KMAJOR) {
+            if (g.a_switch >= 0 && kb >= g.a_switch)
+              tma_load_2d(sa, &tmA2, &full[stage], (kb - g.a_switch) * kBK, t.m_blk * kBM);
+            else
+              tma_load_2d(sa, &tmA, &full[stage], kb * kBK, t.m_blk * kBM);
+          } else if (g.a_mode == A_MNMAJOR) {
+            const bool second = g.a_switch >= 0 && t.m_blk >= g.a_switch;
+            const CUtensorMap* tm = second ? &tmA2 : &tmA;
+            const int m0 = (second ? t.m_blk - g.a_switch : t.m_blk) * kBM;
+            tma_load_2d(sa, tm, &full[stage], m0, kb * kBK);
+            tma_load_2d(sa + 8192, tm, &full[stage], m0 + 64, kb * kBK);
+          } else {
+            const int tap = kb / g.cpk;
+            const int c0 = (kb - tap * g.cpk) * kBK;
+            const int fr = tap / 3, fs = tap - fr * 3;
+            tma_load_4d(sa, &tmA, &full[stage], c0, cw0 + fs - 1, ch0 + fr - 1, ci0);
+          }
+          if (g.b_mn) {
+            for (int j = 0; j < g.bn; j += 64)
+              tma_load_2d(sb + j * 128, &tmB, &full[stage], t.n_blk * g.bn + j, kb * kBK);
+          } else {
+            tma_load_2d(sb, &tmB, &full[stage], kb * kBK, t.n_blk * g.bn);
+          }
+          if (++stage == g.stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(kBM, g.bn, g.a_mode == A_MNMAJOR, g.b_mn != 0);
+      const uint32_t a_lbo = (g.a_mode == A_MNMAJOR) ? 8192u : 16u;
+      const uint32_t b_lbo = g.b_mn ? 8192u : 16u;
+      const uint32_t a_kstep = (g.a_mode == A_MNMAJOR) ? (2048u >> 4) : (32u >> 4);
+      const uint32_t b_kstep = g.b_mn ? (2048u >> 4) : (32u >> 4);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const TileCoord t = decode_tile(g, tile);
+        mbar_wait(&tempty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * kAccStride;
+        for (int kb = t.kb_begin; kb < t.kb_end; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * stage_bytes);
+          const uint64_t adesc = make_smem_desc(sa, a_lbo, 1024);
+          const uint64_t bdesc = make_smem_desc(sa + kABytes, b_lbo, 1024);
+#pragma unroll
+          for (int k = 0; k < kBK / 16; ++k) {
+            umma_bf16(d_tmem, adesc + uint64_t(k * a_kstep), bdesc + uint64_t(k * b_kstep), idesc,
+                      (kb > t.kb_begin || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty[stage]);
+          if (++stage == g.stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tfull[acc]);
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------ epilogue
+    const int q = warp & 3;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const TileCoord t = decode_tile(g, tile);
+      mbar_wait(&tfull[acc], acc_phase);
+      tc_fence_after();
+      if (t.kb_end > t.kb_begin) {
+        const uint32_t taddr = tmem_base + acc * kAccStride + (uint32_t(q * 32) << 16);
+        epi(taddr, t, q * 32 + lane);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<512>(tmem_base);
+}
+
+// ------------------------------------------------------------------------------------------
+// Generic store epilogue: out[m, n] = act(acc + bias[n]) as fp32 or bf16, or fp32 atomic
+// accumulation (split-K / gradient accumulation).
+struct EpiStore {
+  void* out;
+  const float* bias;  // nullable, indexed by n
+  long long ld;       // elements
+  int M, N, bn;
+  int relu;
+  int out_bf16;
+  int atomic;  // fp32 atomicAdd (bias added by split 0 only)
+  float alpha;
+
+  __device__ __forceinline__ void operator()(uint32_t taddr, const TileCoord& t, int row) const {
+    const int m = t.m_blk * kBM + row;
+    const int n_base = t.n_blk * bn;
+    const bool row_ok = m < M;
+    for (int c = 0; c < bn; c += 32) {
+      if (n_base + c >= N) break;  // warp-uniform
+      float v[32];
+      __syncwarp();
+      tmem_ld32(taddr + c, v);
+      tmem_ld_wait();
+      const int n0 = n_base + c;
+      const int nv = min(min(32, bn - c), N - n0);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        float x = v[j] * alpha;
+        if (bias != nullptr && j < nv && (!atomic || t.split == 0)) x += bias[n0 + j];
+        if (relu) x = fmaxf(x, 0.f);
+        v[j] = x;
+      }
+      if (row_ok) {
+        if (atomic) {
+          float* o = reinterpret_cast<float*>(out) + (long long)m * ld + n0;
+          for (int j = 0; j < nv; ++j) atomicAdd(o + j, v[j]);
+        } else if (out_bf16) {
+          __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out) + (long long)m * ld + n0;
+          if (nv == 32 && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              uint4 u;
+              u.x = pack_bf16(v[j], v[j + 1]);
+              u.y = pack_bf16(v[j + 2], v[j + 3]);
+              u.z = pack_bf16(v[j + 4], v[j + 5]);
+              u.w = pack_bf16(v[j + 6], v[j + 7]);
+              *reinterpret_cast<uint4*>(o + j) = u;
+            }
+          } else {
+            for (int j = 0; j < nv; ++j) o[j] = __float2bfloat16(v[j]);
+          }
+        } else {
+          float* o = reinterpret_cast<float*>(out) + (long long)m * ld + n0;
+          if (nv == 32 && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          } else {
+            for (int j = 0; j < nv; ++j) o[j] = v[j];
+          }
+        }
+      }
+    }
+  }
+};
+
+}  // namespace vc

@@ -1,0 +1,37 @@
+// Generic bf16 GEMM entry (store epilogue). Internal C++ helper + the C-ABI test entry vc_gemm_bf16.
+#include "host_util.h"
+#include "ops.h"
+
+namespace vc {
+
+int gemm_store(cudaStream_t stream, const Operand& A, const Operand* A2, long long a2_at, const Operand& B, int M,
+               int N, int K, const EpiStore& epi_in, int bn, int splits) {
+  GemmPlan plan;
+  VC_TRY(plan_gemm(&plan, A, A2, a2_at, B, M, N, K, bn, splits));
+  EpiStore epi = epi_in;
+  epi.M = M;
+  epi.N = N;
+  epi.bn = bn;
+  if (plan.core.splits > 1 && !epi.atomic)
+    return set_error(VC_E_ARG, "gemm_store: split-K requires the atomic epilogue");
+  return launch_gemm(plan, epi, stream);
+}
+
+}  // namespace vc
+
+extern "C" int vc_gemm_bf16(const void* A, int a_mn, long long lda, const void* B, int b_mn, long long ldb, void* out,
+                            long long ldo, const float* bias, int M, int N, int K, int bn, int splits, int relu,
+                            int out_bf16, int atomic, void* stream) {
+  using namespace vc;
+  Operand a{A, a_mn ? K : M, a_mn ? M : K, lda, a_mn != 0};
+  Operand b{B, b_mn ? K : N, b_mn ? N : K, ldb, b_mn != 0};
+  EpiStore epi{};
+  epi.out = out;
+  epi.bias = bias;
+  epi.ld = ldo;
+  epi.relu = relu;
+  epi.out_bf16 = out_bf16;
+  epi.atomic = atomic;
+  epi.alpha = 1.f;
+  return gemm_store(static_cast<cudaStream_t>(stream), a, nullptr, 0, b, M, N, K, epi, bn, splits);
+}

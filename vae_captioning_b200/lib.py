@@ -1,0 +1,59 @@
+"""ctypes binding of libvaecap.so -- the C-ABI boundary (include/vaecap.h).
+
+There is deliberately no fallback: if the shared library is missing or a call fails, the
+caller gets an exception. PyTorch tensors are used by callers only as device-memory containers;
+everything that crosses this boundary is a raw pointer, a size or a scalar.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libvaecap.so")
+
+_lib = None
+
+
+class VaecapError(RuntimeError):
+    pass
+
+
+_STATUS = {-1: "VC_E_ARG", -2: "VC_E_SHAPE", -3: "VC_E_CUDA", -4: "VC_E_NCCL", -5: "VC_E_STATE", -6: "VC_E_NOMEM"}
+
+
+def load():
+    """Loads (once) and returns the ctypes handle of libvaecap.so."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise VaecapError(
+            "libvaecap.so not found at %s -- build it with `python -m vae_captioning_b200.build` "
+            "(there is no CPU fallback for the hot path)" % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    lib.vc_last_error.restype = ctypes.c_char_p
+    lib.vc_abi_version.restype = ctypes.c_int
+    _lib = lib
+    return lib
+
+
+def check(status):
+    """Converts a C-ABI status into the reference's error behaviour (Python exceptions)."""
+    if status == 0:
+        return
+    msg = load().vc_last_error().decode("utf-8", "replace")
+    name = _STATUS.get(status, str(status))
+    if status in (-1, -2):
+        raise ValueError("%s: %s" % (name, msg))
+    raise VaecapError("%s: %s" % (name, msg))
+
+
+def ptr(t):
+    """Raw device/host pointer of a torch tensor (or None -> NULL)."""
+    if t is None:
+        return ctypes.c_void_p(0)
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def stream_ptr():
+    import torch
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
