@@ -1,0 +1,139 @@
+/* libvaecap -- C ABI of the B200-native CVAE captioning hot path.
+ *
+ * The reference (yiyang92/vae_captioning) has no FFI: its seam is the per-step TensorFlow
+ * `sess.run(fetches, feed_dict)` call plus the checkpoint variable names. Each entry point below
+ * replaces one such call site (cited as file:line of the reference); INTEGRATION.md shows the
+ * Python binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *  - every function returns 0 on success or a negative VC_E_* code; vc_last_error() gives the message
+ *    (thread-local); nothing throws or aborts across this boundary.
+ *  - pointers named *_dev are device pointers, *_host are host pointers (pinned memory makes the
+ *    copies asynchronous). The caller owns every I/O buffer; the handle owns parameters, optimiser
+ *    state and the activation workspace (sized at vc_create from max_batch / max_len).
+ *  - `stream` is a cudaStream_t passed as void*. Calls on one handle are not re-entrant.
+ *  - all floating-point I/O is fp32 in TensorFlow layouts (dense kernels [in,out], conv HWIO,
+ *    LSTM kernel [x;h] x [i|j|f|o]); token ids and lengths are int32.
+ */
+#ifndef VAECAP_H_
+#define VAECAP_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum { VC_OK = 0, VC_E_ARG = -1, VC_E_SHAPE = -2, VC_E_CUDA = -3, VC_E_NCCL = -4, VC_E_STATE = -5, VC_E_NOMEM = -6 };
+enum { VC_PRIOR_NORMAL = 0, VC_PRIOR_GMM = 1, VC_PRIOR_AG = 2 };
+
+/* Mirrors the fields of the reference's Parameters (utils/parameters.py:3-66) that shape the graph
+ * built in main.py:43-191. */
+typedef struct vc_config {
+  int32_t vocab_size;       /* data.dictionary.vocab_size, main.py:92 */
+  int32_t embed_size;       /* --embed_dim   (multiple of 64) */
+  int32_t encoder_hidden;   /* --enc_hid     (multiple of 64) */
+  int32_t decoder_hidden;   /* --dec_hid     (multiple of 64) */
+  int32_t latent_size;      /* --latent */
+  int32_t gen_z_samples;    /* --gen_z_samples */
+  int32_t num_clusters;     /* 90 */
+  int32_t num_captions;     /* captions per image fed per step (1..5) */
+  int32_t cnn_feature_size; /* 4096 */
+  int32_t prior;            /* VC_PRIOR_* (--prior) */
+  int32_t use_c_v;          /* --c_v */
+  int32_t no_encoder;       /* --no_encoder */
+  int32_t fine_tune;        /* --fine_tune: images in, VGG16 trained */
+  int32_t restore;          /* --restore: annealing pinned to 1 (main.py:163-164) */
+  int32_t with_cnn;         /* allocate VGG16 parameters (needed for fine_tune and vc_vgg_forward) */
+  int32_t max_batch;        /* images per step (B) */
+  int32_t max_len;          /* padded caption length (T) */
+  float dec_keep_rate;      /* --dec_drop */
+  float dec_lstm_drop;      /* --dec_lstm_drop */
+  float cnn_dropout;
+  float weight_decay;
+  float learning_rate;      /* --lr */
+  float cnn_lr;
+  float clip_norm;          /* lstm_clip_by_norm = 5.0 */
+  float ann_param;          /* --ann_param */
+  float std;                /* --std (generation prior) */
+  float temperature;
+} vc_config;
+
+/* Explicit randomness for one step. NULL pointers select the in-kernel Philox generator seeded
+ * with (seed, step). Explicit tensors are the parity mode (the oracle feeds the same values). */
+typedef struct vc_rng {
+  uint64_t seed;
+  const float* eps_dev;           /* [S, N, Z]   N(0,1) draws of zs.Normal, encoder.py:108-109 */
+  const float* emb_keep_dev;      /* [N, T, E]   0/1 keep mask of tf.nn.dropout, decoder.py:85-87 */
+  const float* out_keep_dev;      /* [N, T, H]   0/1 keep mask of DropoutWrapper, rnn_model.py:45-46 */
+  const int32_t* gmm_cluster_dev; /* [N]         tf.multinomial pick, encoder.py:72 */
+} vc_rng;
+
+/* Fetches of main.py:241-244. */
+typedef struct vc_step_out {
+  float kld;         /* np.mean(kl) */
+  float rec_loss;
+  float lower_bound; /* np.mean(lb) */
+  float annealing;
+  float global_norm; /* tf.clip_by_global_norm's norm (ops/optimizers.py:15-16) */
+  float n_tokens;    /* sum of the loss mask */
+} vc_step_out;
+
+typedef struct vc_handle vc_handle;
+
+const char* vc_last_error(void);
+int vc_abi_version(void);
+
+/* Graph construction, main.py:43-191 (+ tf.global_variables_initializer, main.py:196). Parameters start at zero;
+ * load them with vc_param_set. */
+int vc_create(const vc_config* cfg, int device, vc_handle** out);
+int vc_destroy(vc_handle* h);
+
+/* tf.train.Saver surface (main.py:186-191, 211, 288; utils/image_embeddings.py:240-246): variables by TF name. */
+int vc_num_params(vc_handle* h);
+int vc_param_info(vc_handle* h, int index, const char** name, int32_t* ndim, int64_t* shape /*[4]*/, int32_t* trainable);
+int vc_param_get(vc_handle* h, const char* name, float* dst_host);
+int vc_param_set(vc_handle* h, const char* name, const float* src_host);
+int vc_grad_get(vc_handle* h, const char* name, float* dst_host); /* tf.gradients of the last step (debug tap) */
+
+/* One training sess.run (main.py:229-244): feed {image_f_inputs, ann_inputs_enc, ann_inputs_dec, ann_lengths,
+ * anneal, c_i} -> fetch [kld, rec_loss, lower_bound, optimize, optimize_cnn, annealing].
+ * feats_host: fp32 [B, 4096] (or [B,224,224,3] images when fine_tune). cap_lbl/cap_in: int32 [B*C, T]
+ * (row n = b*C + c, utils/caption_utils.py:16-21). c_v: fp32 [B*C, 90] or NULL. global_step feeds `anneal`.
+ * All inputs are HOST pointers; the call copies them to the device on `stream`. out may be NULL (no sync). */
+int vc_train_step(vc_handle* h, const float* feats_host, const int32_t* cap_lbl_host, const int32_t* cap_in_host,
+                  const int32_t* len_host, const float* c_v_host, int B, int T, int64_t global_step, const vc_rng* rng,
+                  vc_step_out* out, void* stream);
+/* Same, with inputs already resident in device memory. */
+int vc_train_step_dev(vc_handle* h, const float* feats_dev, const int32_t* cap_lbl_dev, const int32_t* cap_in_dev,
+                      const int32_t* len_dev, const float* c_v_dev, int B, int T, int64_t global_step,
+                      const vc_rng* rng, vc_step_out* out, void* stream);
+/* Split form for data parallelism: forward+backward fills the flat gradient buffer, the caller all-reduces it
+ * (vc_grad_buffer), then vc_apply_gradients clips and runs Adam. grad_scale multiplies every gradient (1/world). */
+int vc_forward_backward_dev(vc_handle* h, const float* feats_dev, const int32_t* cap_lbl_dev, const int32_t* cap_in_dev,
+                            const int32_t* len_dev, const float* c_v_dev, int B, int T, int64_t global_step,
+                            const vc_rng* rng, void* stream);
+int vc_grad_buffer(vc_handle* h, float** dev_ptr, int64_t* count);
+int vc_apply_gradients(vc_handle* h, float grad_scale, vc_step_out* out, void* stream);
+
+/* validate(): sess.run([rec_loss]) on the training graph (main.py:262-284, dropout stays on, Q12). */
+int vc_eval_step(vc_handle* h, const float* feats_host, const int32_t* cap_lbl_host, const int32_t* cap_in_host,
+                 const int32_t* len_host, const float* c_v_host, int B, int T, const vc_rng* rng, vc_step_out* out,
+                 void* stream);
+
+/* Debug taps of the last forward (x_logits main.py:150, qz.distribution.mean/std main.py:122-124).
+ * Any pointer may be NULL. logits_host: fp32 [N*T, V] in the reference's row order (n*T + t). */
+int vc_forward_debug(vc_handle* h, float* logits_host, float* mu_host, float* std_host, float* z_host,
+                     float* kl_rows_host, float* ce_rows_host);
+
+/* Data.extract_features_from_dir's sess.run(features, {input_img}) (utils/data.py:120-125), batched:
+ * images fp32 [B,224,224,3] RGB 0..255 (host) -> fc2 fp32 [B,4096] (host). */
+int vc_vgg_forward(vc_handle* h, const float* images_host, float* fc2_host, int B, void* stream);
+int vc_vgg_forward_dev(vc_handle* h, const float* images_dev, float* fc2_dev, int B, void* stream);
+/* Debug tap: NHWC activation of a conv layer ("conv1_1".."conv5_3") of the last vc_vgg_forward as fp32. */
+int vc_vgg_activation(vc_handle* h, const char* layer, float* dst_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VAECAP_H_ */

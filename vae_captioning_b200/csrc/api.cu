@@ -1,5 +1,168 @@
-// C-ABI surface of libvaecap.so (declared in include/vaecap.h).
-#include "ops.h"
+// C-ABI surface of libvaecap.so (declared in include/vaecap.h). No exceptions cross this boundary.
+#include <new>
+#include "model.h"
 
-extern "C" const char* vc_last_error(void) { return vc::last_error().c_str(); }
-extern "C" int vc_abi_version(void) { return 1; }
+using namespace vc;
+
+struct vc_handle {
+  Model m;
+};
+
+#define VC_GUARD_BEGIN try {
+#define VC_GUARD_END                                                   \
+  }                                                                    \
+  catch (const std::bad_alloc&) {                                      \
+    return set_error(VC_E_NOMEM, "host allocation failed");            \
+  }                                                                    \
+  catch (...) {                                                        \
+    return set_error(VC_E_STATE, "unexpected C++ exception");          \
+  }
+
+extern "C" {
+
+const char* vc_last_error(void) { return last_error().c_str(); }
+int vc_abi_version(void) { return 1; }
+
+int vc_create(const vc_config* cfg, int device, vc_handle** out) {
+  VC_GUARD_BEGIN
+  if (cfg == nullptr || out == nullptr) return set_error(VC_E_ARG, "vc_create: null argument");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return set_error(VC_E_CUDA, "no CUDA device: the hot path has no CPU fallback");
+  if (device < 0 || device >= ndev) return set_error(VC_E_ARG, "device %d out of range (%d devices)", device, ndev);
+  cudaDeviceProp prop;
+  VC_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) return set_error(VC_E_CUDA, "libvaecap is built for sm_100a only (device is sm_%d%d)", prop.major, prop.minor);
+  vc_handle* h = new vc_handle();
+  int st = h->m.init(*cfg, device);
+  if (st != VC_OK) {
+    delete h;
+    return st;
+  }
+  *out = h;
+  return VC_OK;
+  VC_GUARD_END
+}
+
+int vc_destroy(vc_handle* h) {
+  if (h == nullptr) return VC_OK;
+  cudaSetDevice(h->m.device);
+  cudaDeviceSynchronize();
+  delete h;
+  return VC_OK;
+}
+
+int vc_num_params(vc_handle* h) { return h ? (int)h->m.params.size() : set_error(VC_E_ARG, "null handle"); }
+
+int vc_param_info(vc_handle* h, int index, const char** name, int32_t* ndim, int64_t* shape, int32_t* trainable) {
+  if (h == nullptr) return set_error(VC_E_ARG, "null handle");
+  if (index < 0 || index >= (int)h->m.params.size()) return set_error(VC_E_ARG, "parameter index %d out of range", index);
+  const ParamInfo& p = h->m.params[index];
+  if (name) *name = p.name.c_str();
+  if (ndim) *ndim = p.ndim;
+  if (shape) for (int i = 0; i < 4; ++i) shape[i] = p.shape[i];
+  if (trainable) *trainable = p.trainable ? 1 : 0;
+  return VC_OK;
+}
+
+int vc_param_get(vc_handle* h, const char* name, float* dst) {
+  if (!h || !name || !dst) return set_error(VC_E_ARG, "vc_param_get: null argument");
+  cudaSetDevice(h->m.device);
+  return h->m.param_get(name, dst);
+}
+int vc_param_set(vc_handle* h, const char* name, const float* src) {
+  if (!h || !name || !src) return set_error(VC_E_ARG, "vc_param_set: null argument");
+  cudaSetDevice(h->m.device);
+  return h->m.param_set(name, src);
+}
+int vc_grad_get(vc_handle* h, const char* name, float* dst) {
+  if (!h || !name || !dst) return set_error(VC_E_ARG, "vc_grad_get: null argument");
+  cudaSetDevice(h->m.device);
+  return h->m.grad_get(name, dst);
+}
+
+static StepInputs make_inputs(const float* feats, const int32_t* lbl, const int32_t* inp, const int32_t* len,
+                              const float* cv, int B, int T, int64_t gs, const vc_rng* rng) {
+  StepInputs in{};
+  in.feats = feats; in.cap_lbl = lbl; in.cap_in = inp; in.len = len; in.c_v = cv;
+  in.B = B; in.T = T; in.global_step = gs;
+  if (rng) in.rng = *rng;
+  return in;
+}
+
+int vc_forward_backward_dev(vc_handle* h, const float* feats, const int32_t* lbl, const int32_t* inp, const int32_t* len,
+                            const float* cv, int B, int T, int64_t gs, const vc_rng* rng, void* stream) {
+  VC_GUARD_BEGIN
+  if (!h || !feats || !lbl || !inp || !len) return set_error(VC_E_ARG, "vc_forward_backward_dev: null argument");
+  cudaSetDevice(h->m.device);
+  cudaStream_t s = (cudaStream_t)stream;
+  StepInputs in = make_inputs(feats, lbl, inp, len, cv, B, T, gs, rng);
+  VC_TRY(h->m.forward(in, true, s));
+  return h->m.backward(in, s);
+  VC_GUARD_END
+}
+
+int vc_grad_buffer(vc_handle* h, float** dev_ptr, int64_t* count) {
+  if (!h || !dev_ptr || !count) return set_error(VC_E_ARG, "vc_grad_buffer: null argument");
+  *dev_ptr = h->m.Gf;
+  *count = h->m.n_adam + 64;  // gradients + the 64-float tail carrying the embedding-slice squared norms
+  return VC_OK;
+}
+
+int vc_apply_gradients(vc_handle* h, float grad_scale, vc_step_out* out, void* stream) {
+  VC_GUARD_BEGIN
+  if (!h) return set_error(VC_E_ARG, "null handle");
+  cudaSetDevice(h->m.device);
+  cudaStream_t s = (cudaStream_t)stream;
+  VC_TRY(h->m.apply(grad_scale, s));
+  return h->m.fetch(out, s);
+  VC_GUARD_END
+}
+
+int vc_train_step_dev(vc_handle* h, const float* feats, const int32_t* lbl, const int32_t* inp, const int32_t* len,
+                      const float* cv, int B, int T, int64_t gs, const vc_rng* rng, vc_step_out* out, void* stream) {
+  VC_TRY(vc_forward_backward_dev(h, feats, lbl, inp, len, cv, B, T, gs, rng, stream));
+  return vc_apply_gradients(h, 1.f, out, stream);
+}
+
+int vc_train_step(vc_handle* h, const float* feats, const int32_t* lbl, const int32_t* inp, const int32_t* len,
+                  const float* cv, int B, int T, int64_t gs, const vc_rng* rng, vc_step_out* out, void* stream) {
+  VC_GUARD_BEGIN
+  if (!h || !feats || !lbl || !inp || !len) return set_error(VC_E_ARG, "vc_train_step: null argument");
+  cudaSetDevice(h->m.device);
+  cudaStream_t s = (cudaStream_t)stream;
+  StepInputs in{};
+  VC_TRY(h->m.stage_inputs(feats, lbl, inp, len, cv, B, T, &in, s));
+  in.global_step = gs;
+  if (rng) in.rng = *rng;
+  VC_TRY(h->m.forward(in, true, s));
+  VC_TRY(h->m.backward(in, s));
+  VC_TRY(h->m.apply(1.f, s));
+  return h->m.fetch(out, s);
+  VC_GUARD_END
+}
+
+int vc_eval_step(vc_handle* h, const float* feats, const int32_t* lbl, const int32_t* inp, const int32_t* len,
+                 const float* cv, int B, int T, const vc_rng* rng, vc_step_out* out, void* stream) {
+  VC_GUARD_BEGIN
+  if (!h || !feats || !lbl || !inp || !len) return set_error(VC_E_ARG, "vc_eval_step: null argument");
+  cudaSetDevice(h->m.device);
+  cudaStream_t s = (cudaStream_t)stream;
+  StepInputs in{};
+  VC_TRY(h->m.stage_inputs(feats, lbl, inp, len, cv, B, T, &in, s));
+  in.global_step = h->m.adam_t;
+  if (rng) in.rng = *rng;
+  VC_TRY(h->m.forward(in, false, s));
+  return h->m.fetch(out, s);
+  VC_GUARD_END
+}
+
+int vc_forward_debug(vc_handle* h, float* logits, float* mu, float* sd, float* z, float* kl_rows, float* ce_rows) {
+  VC_GUARD_BEGIN
+  if (!h) return set_error(VC_E_ARG, "null handle");
+  cudaSetDevice(h->m.device);
+  return h->m.forward_debug(logits, mu, sd, z, kl_rows, ce_rows);
+  VC_GUARD_END
+}
+
+}  // extern "C"

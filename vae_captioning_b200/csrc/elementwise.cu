@@ -1,0 +1,576 @@
+// HBM-bound stages of the train step: casts / weight-shadow transposes, embedding gather and
+// scatter, reparameterised sample + KL, vocab softmax cross-entropy (fwd + bwd in one pass),
+// column sums (bias gradients), global norm and the fused TF-form Adam update.
+// Each kernel is coalesced and vectorised; reductions use warp shuffles then one atomic per warp/CTA.
+#include <curand_kernel.h>
+#include "ops.h"
+
+namespace vc {
+
+static inline int grid_for(long long n, int block, int per_thread = 1) {
+  long long g = (n + (long long)block * per_thread - 1) / ((long long)block * per_thread);
+  const long long cap = (long long)num_sms() * 16;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+// ------------------------------------------------------------------------------------------
+__global__ void k_cast_f32_bf16(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long rows,
+                                int cols, long long ld_src, long long ld_dst) {
+  const long long total = rows * cols;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / cols;
+    const int c = (int)(i - r * cols);
+    dst[r * ld_dst + c] = __float2bfloat16(src[r * ld_src + c]);
+  }
+}
+int cast_f32_bf16(cudaStream_t s, const float* src, void* dst, long long rows, int cols, long long ld_src,
+                  long long ld_dst) {
+  k_cast_f32_bf16<<<grid_for(rows * cols, 256, 4), 256, 0, s>>>(src, (__nv_bfloat16*)dst, rows, cols, ld_src, ld_dst);
+  VC_CUDA(cudaGetLastError());
+  return VC_OK;
+}
+
+// dst[perm(c), r] = bf16(src[r, c]); perm groups the 4 LSTM gates of `upt` hidden units into one
+// contiguous block of 4*upt rows (gate_h > 0), otherwise identity. 32x32 smem tile transpose.
+__global__ void k_transpose_cast(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int R, int C,
+                                 long long ld_src, long long ld_dst, int gate_h, int upt) {
+  __shared__ float tile[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (r < R && c < C) ? src[(long long)r * ld_src + c] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, r = r0 + threadIdx.x;
+    if (c < C && r < R) {
+      int cd = c;
+      if (gate_h > 0) {
+        const int g = c / gate_h, u = c - g * gate_h;
+        cd = (u / upt) * (4 * upt) + g * upt + (u % upt);
+      }
+      dst[(long long)cd * ld_dst + r] = __float2bfloat16(tile[threadIdx.x][i]);
+    }
+  }
+}
+int transpose_cast(cudaStream_t s, const float* src, void* dst, int R, int C, long long ld_src, long long ld_dst,
+                   int gate_h, int upt) {
+  dim3 grid((C + 31) / 32, (R + 31) / 32), block(32, 8);
+  k_transpose_cast<<<grid, block, 0, s>>>(src, (__nv_bfloat16*)dst, R, C, ld_src, ld_dst, gate_h, upt);
+  VC_CUDA(cudaGetLastError());
+  return VC_OK;
+}
+
+// out_bf16[(b*C + c), :] = bf16(src[b, :])  for c in [0, C): feature tiling (main.py:84-89) applied
+// after the projection (Q7); written to up to two destinations (encoder and decoder X slot 0).
+__global__ void k_tile_cast(const float* __restrict__ src, __nv_bfloat16* __restrict__ d0, __nv_bfloat16* __restrict__ d1,
+                            int B, int C, int E) {
+  const long long total = (long long)B * C * E;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int e = (int)(i % E);
+    const long long n = i / E;
+    const __nv_bfloat16 v = __float2bfloat16(src[(n / C) * E + e]);
+    if (d0) d0[i] = v;
+    if (d1) d1[i] = v;
+  }
+}
+int tile_cast(cudaStream_t s, const float* src, void* d0, void* d1, int B, int C, int E) {
+  k_tile_cast<<<grid_for((long long)B * C * E, 256, 2), 256, 0, s>>>(src, (__nv_bfloat16*)d0, (__nv_bfloat16*)d1, B, C, E);
+  VC_CUDA(cudaGetLastError());
+  return VC_OK;
+}
+
+// dst[b, e] = sum_c (a[(b*C+c), e] + b2[(b*C+c), e])  -> fp32 and bf16 copies
+__global__ void k_tile_reduce(const float* __restrict__ a, const float* __restrict__ b2, float* __restrict__ dst_f,
+                              __nv_bfloat16* __restrict__ dst_h, int B, int C, int E) {
+  const long long total = (long long)B * E;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int e = (int)(i % E);
+    const long long b = i / E;
+    float acc = 0.f;
+    for (int c = 0; c < C; ++c) {
+      const long long o = (b * C + c) * E + e;
+      acc += a[o];
+      if (b2) acc += b2[o];
+    }
+    if (dst_f) dst_f[i] = acc;
+    if (dst_h) dst_h[i] = __float2bfloat16(acc);
+  }
+}
+int tile_reduce(cudaStream_t s, const float* a, const float* b2, float* dst_f, void* dst_h, int B, int C, int E) {
+  k_tile_reduce<<<grid_for((long long)B * E, 256), 256, 0, s>>>(a, b2, dst_f, (__nv_bfloat16*)dst_h, B, C, E);
+  VC_CUDA(cudaGetLastError());
+  return VC_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// Embedding gather: X[t, n, :] = table_bf16[tok[n, t], :] (* keep_mask[n, t, :] / keep). One warp per row.
+__global__ void k_embed_gather(const __nv_bfloat16* __restrict__ table, const int* __restrict__ tok,
+                               __nv_bfloat16* __restrict__ X, const float* __restrict__ keep_mask, float inv_keep, int N,
+                               int T, int E, int V) {
+  const int warps_per_block = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31;
+  for (long long row = blockIdx.x * (long long)warps_per_block + (threadIdx.x >> 5); row < (long long)N * T;
+       row += (long long)gridDim.x * warps_per_block) {
+    const int t = (int)(row / N), n = (int)(row - (long long)t * N);
+    int id = tok[(long long)n * T + t];
+    id = id < 0 ? 0 : (id >= V ? V - 1 : id);
+    const __nv_bfloat16* src = table + (long long)id * E;
+    __nv_bfloat16* dst = X + row * E;
+    if (keep_mask == nullptr) {
+      for (int e = lane * 8; e < E; e += 256) *reinterpret_cast<uint4*>(dst + e) = *reinterpret_cast<const uint4*>(src + e);
+    } else {
+      const float* mk = keep_mask + ((long long)n * T + t) * E;
+      for (int e = lane; e < E; e += 32) dst[e] = __float2bfloat16(__bfloat162float(src[e]) * mk[e] * inv_keep);
+    }
+  }
+}
+int embed_gather(cudaStream_t s, const void* table, const int* tok, void* X, const float* keep_mask, float inv_keep,
+                 int N, int T, int E, int V) {
+  if (E % 8 != 0) return set_error(VC_E_SHAPE, "embed_size must be a multiple of 8");
+  k_embed_gather<<<grid_for((long long)N * T, 8), 256, 0, s>>>((const __nv_bfloat16*)table, tok, (__nv_bfloat16*)X,
+                                                              keep_mask, inv_keep, N, T, E, V);
+  VC_CUDA(cudaGetLastError());
+  return VC_OK;
+}
+
+// Embedding backward: per token row g = dX[t, n, :] (* keep_mask / keep); normsq += |g|^2 (the
+// IndexedSlices.values norm TF's clip_by_global_norm uses, Q4); grad_table[tok] += g.
+__global__ void k_embed_scatter(const float* __restrict__ dX, const int* __restrict__ tok, float* __restrict__ gtable,
+                                const float* __restrict__ keep_mask, float inv_keep, float* __restrict__ normsq, int N,
+                                int T, int E, int V) {
+  const int warps_per_block = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31;
+  float acc = 0.f;
+  for (long long row = blockIdx.x * (long long)warps_per_block + (threadIdx.x >> 5); row < (long long)N * T;
+       row += (long long)gridDim.x * warps_per_block) {
+    const int t = (int)(row / N), n = (int)(row - (long long)t * N);
+    int id = tok[(long long)n * T + t];
+    id = id < 0 ? 0 : (id >= V ? V - 1 : id);
+    const float* src = dX + row * E;
+    const float* mk = keep_mask ? keep_mask + ((long long)n * T + t) * E : nullptr;
+    for (int e = lane; e < E; e += 32) {
+      float g = src[e];
+      if (mk) g *= mk[e] * inv_keep;
+      acc += g * g;
+      if (g != 0.f) atomicAdd(gtable + (long long)id * E + e, g);
+    }
+  }
+  acc = warp_sum(acc);
+  if (lane == 0 && acc != 0.f) atomicAdd(normsq, acc);
+}
+int embed_scatter(cudaStream_t s, const float* dX, const int* tok, float* gtable, const float* keep_mask, float inv_keep,
+                  float* normsq, int N, int T, int E, int V) {
+  k_embed_scatter<<<grid_for((long long)N * T, 8), 256, 0, s>>>(dX, tok, gtable, keep_mask, inv_keep, normsq, N, T, E, V);
+  VC_CUDA(cudaGetLastError());
+  return VC_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// Reparameterised sample + KL (encoder.py:108-109, main.py:118-145).
+// heads [N, ld] fp32: mu at [0, Z), log-std at [zp, zp+Z) (Normal prior) -> std = exp(logstd).
+// For GMM/AG the caller provides mu/std directly (mix kernel) and passes heads == nullptr.
+// z[s, n, k] = mu + std * eps (bf16, consumed by the z_rnn GEMM through the Q1 row-major view).
+// eps: explicit fp32 [S,N,Z] (parity) or Philox(seed, offset) when eps == nullptr.
+__device__ __forceinline__ float4 philox_normal4(unsigned long long seed, unsigned long long offset, long long quad) {
+  curandStatePhilox4_32_10_t st;
+  curand_init(seed, (unsigned long long)quad, offset, &st);
+  return curand_normal4(&st);
+}
+
+__global__ void k_heads_to_musd(const float* __restrict__ heads, long long ld, int zp, float* __restrict__ mu,
+                                float* __restrict__ sd, int N, int Z) {
+  const long long total = (long long)N * Z;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long n = i / Z;
+    const int k = (int)(i - n * Z);
+    mu[i] = heads[n * ld + k];
+    sd[i] = __expf(heads[n * ld + zp + k]);
+  }
+}
+int heads_to_musd(cudaStream_t s, const float* heads, long long ld, int zp, float* mu, float* sd, int N, int Z) {
+  k_heads_to_musd<<<grid_for((long long)N * Z, 256), 256, 0, s>>>(heads, ld, zp, mu, sd, N, Z);
+  VC_CUDA(cudaGetLastError());
+  return VC_OK;
+}
+
+// KL rows. prior 0/1 (Normal/GMM): kl_row[n] = -0.5 * sum_k (1 + log(sd^2+1e-5) - mu^2 - sd^2)
+// prior 2 (AG): kl_row[n] = -0.5 * sum_k (0.5 + log(sd+1e-5) - log(cs+1e-5) - ((mu-cm)^2 + sd^2)/(2cs^2+1e-7)),
+// cm = c_v[n,:] @ c_means. Also writes dKL/dmu, dKL/dsd (per-row, unscaled) for the backward pass.
+__global__ void k_kl_rows(const float* __restrict__ mu, const float* __restrict__ sd, const float* __restrict__ cm,
+                          int prior, float* __restrict__ kl_row, float* __restrict__ dkl_dmu,
+                          float* __restrict__ dkl_dsd, float* __restrict__ kl_sum, int N, int Z) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= N) return;
+  const float cs = 0.1f;
+  float acc = 0.f;
+  for (int k = lane; k < Z; k += 32) {
+    const long long i = (long long)warp * Z + k;
+    const float m = mu[i], s = sd[i];
+    if (prior != 2) {
+      acc += 1.f + logf(s * s + 0.00001f) - m * m - s * s;
+      dkl_dmu[i] = m;                                          // -0.5 * (-2 mu)
+      dkl_dsd[i] = -0.5f * (2.f * s / (s * s + 0.00001f) - 2.f * s);
+    } else {
+      const float d = m - cm[i];
+      const float den = 2.f * cs * cs + 0.0000001f;
+      acc += 0.5f + logf(s + 0.00001f) - logf(cs + 0.00001f) - (d * d + s * s) / den;
+      dkl_dmu[i] = -0.5f * (-2.f * d / den);
+      dkl_dsd[i] = -0.5f * (1.f / (s + 0.00001f) - 2.f * s / den);
+    }
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) {
+    kl_row[warp] = -0.5f * acc;
+    atomicAdd(kl_sum, -0.5f * acc);
+  }
+}
+int kl_rows(cudaStream_t s, const float* mu, const float* sd, const float* cm, int prior, float* kl_row, float* dkl_dmu,
+            float* dkl_dsd, float* kl_sum, int N, int Z) {
+  k_kl_rows<<<(N * 32 + 255) / 256, 256, 0, s>>>(mu, sd, cm, prior, kl_row, dkl_dmu, dkl_dsd, kl_sum, N, Z);
+  VC_CUDA(cudaGetLastError());
+  return VC_OK;
+}
+
+__global__ void k_sample_z(const float* __restrict__ mu, const float* __restrict__ sd, const float* __restrict__ eps,
+                           unsigned long long seed, unsigned long long offset, __nv_bfloat16* __restrict__ z,
+                           float* __restrict__ z_f32, int S, long long NZ) {
+  // one thread per 4 consecutive elements of [S, N*Z]
+  const long long quads = ((long long)S * NZ + 3) / 4;
+  for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < quads; q += (long long)gridDim.x * blockDim.x) {
+    float e[4];
+    const long long i0 = q * 4;
+    if (eps == nullptr) {
+      const float4 r = philox_normal4(seed, offset, q);
+      e[0] = r.x; e[1] = r.y; e[2] = r.z; e[3] = r.w;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const long long i = i0 + j;
+      if (i >= (long long)S * NZ) break;
+      const long long r = i % NZ;
+      const float ee = eps ? eps[i] : e[j];
+      const float v = mu[r] + sd[r] * ee;
+      z[i] = __float2bfloat16(v);
+      if (z_f32) z_f32[i] = v;
+    }
+  }
+}
+int sample_z(cudaStream_t s, const float* mu, const float* sd, const float* eps, unsigned long long seed,
+             unsigned long long offset, void* z, float* z_f32, int S, long long NZ) {
+  k_sample_z<<<grid_for(((long long)S * NZ + 3) / 4, 256), 256, 0, s>>>(mu, sd, eps, seed, offset, (__nv_bfloat16*)z, z_f32,
+                                                                        S, NZ);
+  VC_CUDA(cudaGetLastError());
+  return VC_OK;
+}
+
+// dmu[r] = sum_s dz[s, r]; dsd[r] = sum_s dz[s, r] * eps[s, r]   (r over N*Z; dz fp32 [S, N*Z]),
+// then adds kl_scale * dKL and emits the head gradient in bf16:
+//   Normal: dheads[n, k] = dmu, dheads[n, zp + k] = dsd * sd (d/dlogstd).  Otherwise writes dmu/dsd fp32.
+__global__ void k_dz_reduce(const float* __restrict__ dz, const float* __restrict__ eps, unsigned long long seed,
+                            unsigned long long offset, const float* __restrict__ sd, const float* __restrict__ dkl_dmu,
+                            const float* __restrict__ dkl_dsd, float kl_scale, __nv_bfloat16* __restrict__ dheads,
+                            long long ld, int zp, float* __restrict__ dmu_out, float* __restrict__ dsd_out, int S, int N,
+                            int Z) {
+  const long long NZ = (long long)N * Z;
+  // each thread owns 4 consecutive r (a Philox quad never straddles rows of s because NZ % 4 == 0 is required
+  // for the Philox path; the explicit-eps path has no such constraint)
+  const long long quads = (NZ + 3) / 4;
+  for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < quads; q += (long long)gridDim.x * blockDim.x) {
+    float am[4] = {0, 0, 0, 0}, as[4] = {0, 0, 0, 0};
+    for (int s = 0; s < S; ++s) {
+      const long long base = (long long)s * NZ + q * 4;
+      float e[4];
+      if (eps == nullptr) {
+        const float4 r = philox_normal4(seed, offset, base / 4);
+        e[0] = r.x; e[1] = r.y; e[2] = r.z; e[3] = r.w;
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (q * 4 + j >= NZ) break;
+        const float g = dz[base + j];
+        am[j] += g;
+        as[j] += g * (eps ? eps[base + j] : e[j]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const long long r = q * 4 + j;
+      if (r >= NZ) break;
+      const float gm = am[j] + kl_scale * dkl_dmu[r];
+      const float gs = as[j] + kl_scale * dkl_dsd[r];
+      if (dheads) {
+        const long long n = r / Z;
+        const int k = (int)(r - n * Z);
+        dheads[n * ld + k] = __float2bfloat16(gm);
+        dheads[n * ld + zp + k] = __float2bfloat16(gs * sd[r]);
+      }
+      if (dmu_out) dmu_out[r] = gm;
+      if (dsd_out) dsd_out[r] = gs;
+    }
+  }
+}
+int dz_reduce(cudaStream_t s, const float* dz, const float* eps, unsigned long long seed, unsigned long long offset,
+              const float* sd, const float* dkl_dmu, const float* dkl_dsd, float kl_scale, void* dheads, long long ld,
+              int zp, float* dmu_out, float* dsd_out, int S, int N, int Z) {
+  if (eps == nullptr && ((long long)N * Z) % 4 != 0)
+    return set_error(VC_E_SHAPE, "Philox sampling needs N*Z to be a multiple of 4");
+  k_dz_reduce<<<grid_for(((long long)N * Z + 3) / 4, 128), 128, 0, s>>>(dz, eps, seed, offset, sd, dkl_dmu, dkl_dsd, kl_scale,
+                                                                       (__nv_bfloat16*)dheads, ld, zp, dmu_out, dsd_out,
+                                                                       S, N, Z);
+  VC_CUDA(cudaGetLastError());
+  return VC_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// Vocab softmax cross-entropy over bf16 logits rows [rows, ld] (row = t*N + n, time-major), labels
+// lbl[n*T + t]. One CTA per row; the row lives in registers between the two passes, so logits are
+// read once and (optionally) overwritten in place by dlogits = (softmax - onehot) * mask * gscale.
+// Accumulates sums[0] += ce*mask, sums[1] += mask. gscale = loss_scale / count[0] (count = sum mask).
+constexpr int kCeThreads = 256;
+constexpr int kCeMaxPerThread = 48;  // supports V up to 256*48*... (bf16x2 pairs): 24576
+
+__global__ void __launch_bounds__(kCeThreads)
+k_ce(__nv_bfloat16* __restrict__ logits, long long ld, const int* __restrict__ lbl, int N, int T, int V,
+     float* __restrict__ sums, float* __restrict__ ce_rows, const float* __restrict__ count, float loss_scale,
+     int write_grad) {
+  const int row = blockIdx.x;
+  const int t = row / N, n = row - t * N;
+  const int label = lbl[(long long)n * T + t];
+  __nv_bfloat162* p = reinterpret_cast<__nv_bfloat162*>(logits + (long long)row * ld);
+  const int pairs = (V + 1) / 2;
+  constexpr int kPairs = kCeMaxPerThread / 2;
+  float2 v[kPairs];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int c = 0; c < kPairs; ++c) {
+    const int i = threadIdx.x + c * kCeThreads;
+    float2 f = make_float2(-INFINITY, -INFINITY);
+    if (i < pairs) {
+      f = __bfloat1622float2(p[i]);
+      if (2 * i + 1 >= V) f.y = -INFINITY;
+    }
+    v[c] = f;
+    mx = fmaxf(mx, fmaxf(f.x, f.y));
+  }
+  __shared__ float red[kCeThreads / 32];
+  __shared__ float bcast;
+  mx = warp_max(mx);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float m2 = threadIdx.x < kCeThreads / 32 ? red[threadIdx.x] : -INFINITY;
+    m2 = warp_max(m2);
+    if (threadIdx.x == 0) bcast = m2;
+  }
+  __syncthreads();
+  mx = bcast;
+  float sum = 0.f;
+#pragma unroll
+  for (int c = 0; c < kPairs; ++c) {
+    v[c].x = __expf(v[c].x - mx);
+    v[c].y = __expf(v[c].y - mx);
+    sum += v[c].x + v[c].y;
+  }
+  __syncthreads();
+  sum = warp_sum(sum);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sum;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float s2 = threadIdx.x < kCeThreads / 32 ? red[threadIdx.x] : 0.f;
+    s2 = warp_sum(s2);
+    if (threadIdx.x == 0) bcast = s2;
+  }
+  __syncthreads();
+  sum = bcast;
+  const float mask = label != 0 ? 1.f : 0.f;  // tf.sign(tf.to_float(labels)), labels >= 0
+  if (threadIdx.x == 0) {
+    const int lc = label < 0 ? 0 : (label >= V ? V - 1 : label);
+    const float ll = __bfloat162float(logits[(long long)row * ld + lc]);
+    const float ce = logf(sum) + mx - ll;
+    if (ce_rows) ce_rows[(long long)n * T + t] = ce;
+    if (mask != 0.f) {
+      atomicAdd(&sums[0], ce);
+      atomicAdd(&sums[1], 1.f);
+    }
+  }
+  if (write_grad) {
+    __syncthreads();  // the label logit was read above before anyone overwrites it
+    const float g = mask * loss_scale / fmaxf(count[0], 1.f) / sum;
+    const float gm = mask * loss_scale / fmaxf(count[0], 1.f);
+#pragma unroll
+    for (int c = 0; c < kPairs; ++c) {
+      const int i = threadIdx.x + c * kCeThreads;
+      if (i < pairs) {
+        float a = v[c].x * g, b = v[c].y * g;
+        if (2 * i == label) a -= gm;
+        if (2 * i + 1 == label) b -= gm;
+        if (2 * i + 1 >= V) b = 0.f;
+        p[i] = __floats2bfloat162_rn(a, b);
+      }
+    }
+  }
+}
+int ce_rows(cudaStream_t s, void* logits, long long ld, const int* lbl, int N, int T, int V, float* sums, float* ce_out,
+            const float* count, float loss_scale, int write_grad) {
+  if (V > kCeThreads * kCeMaxPerThread) return set_error(VC_E_SHAPE, "vocab_size %d exceeds CE kernel limit", V);
+  if (ld % 2 != 0) return set_error(VC_E_SHAPE, "logits pitch must be even");
+  k_ce<<<N * T, kCeThreads, 0, s>>>((__nv_bfloat16*)logits, ld, lbl, N, T, V, sums, ce_out, count, loss_scale, write_grad);
+  VC_CUDA(cudaGetLastError());
+  return VC_OK;
+}
+
+// count[0] = number of labels != 0 (sum of the loss mask)
+__global__ void k_count_mask(const int* __restrict__ lbl, long long n, float* __restrict__ count) {
+  float acc = 0.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    acc += lbl[i] != 0 ? 1.f : 0.f;
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0 && acc != 0.f) atomicAdd(count, acc);
+}
+int count_mask(cudaStream_t s, const int* lbl, long long n, float* count) {
+  k_count_mask<<<grid_for(n, 256, 4), 256, 0, s>>>(lbl, n, count);
+  VC_CUDA(cudaGetLastError());
+  return VC_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// Column sums of a bf16 matrix [rows, ld] -> out[col] += sum (fp32 atomics, one per column per CTA).
+__global__ void k_colsum_bf16(const __nv_bfloat16* __restrict__ x, long long rows, int cols, long long ld,
+                              float* __restrict__ out, int rows_per_cta) {
+  const int c2 = (blockIdx.x * blockDim.x + threadIdx.x) * 2;
+  if (c2 >= cols) return;
+  const long long r0 = (long long)blockIdx.y * rows_per_cta;
+  const long long r1 = min(rows, r0 + rows_per_cta);
+  float a = 0.f, b = 0.f;
+  for (long long r = r0; r < r1; ++r) {
+    const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(x + r * ld + c2));
+    a += f.x;
+    b += f.y;
+  }
+  atomicAdd(out + c2, a);
+  if (c2 + 1 < cols) atomicAdd(out + c2 + 1, b);
+}
+int colsum_bf16(cudaStream_t s, const void* x, long long rows, int cols, long long ld, float* out) {
+  if (ld % 2 != 0) return set_error(VC_E_SHAPE, "colsum pitch must be even");
+  const int threads = 128;
+  const int gx = ((cols + 1) / 2 + threads - 1) / threads;
+  int gy = (num_sms() * 8 + gx - 1) / gx;
+  if (gy > rows) gy = (int)rows;
+  if (gy < 1) gy = 1;
+  const int rpc = (int)((rows + gy - 1) / gy);
+  dim3 grid(gx, (unsigned)((rows + rpc - 1) / rpc));
+  k_colsum_bf16<<<grid, threads, 0, s>>>((const __nv_bfloat16*)x, rows, cols, ld, out, rpc);
+  VC_CUDA(cudaGetLastError());
+  return VC_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// Global norm (sum of squares into *out) and fused clip + TF-form Adam (Q5):
+//   g' = g * clip / max(sqrt(normsq), clip);  m = b1 m + (1-b1) g';  v = b2 v + (1-b2) g'^2;
+//   p -= lr_t * m / (sqrt(v) + eps),  lr_t = lr sqrt(1-b2^t)/(1-b1^t) (computed by the host).
+__global__ void k_sumsq(const float* __restrict__ g, long long n, float* __restrict__ out) {
+  float acc = 0.f;
+  const long long n4 = n / 4;
+  const float4* g4 = reinterpret_cast<const float4*>(g);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 v = g4[i];
+    acc += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+  }
+  for (long long i = n4 * 4 + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    acc += g[i] * g[i];
+  acc = warp_sum(acc);
+  __shared__ float red[32];
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float a = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+    a = warp_sum(a);
+    if (threadIdx.x == 0 && a != 0.f) atomicAdd(out, a);
+  }
+}
+int sumsq(cudaStream_t s, const float* g, long long n, float* out) {
+  if (n <= 0) return VC_OK;
+  k_sumsq<<<grid_for(n, 256, 8), 256, 0, s>>>(g, n, out);
+  VC_CUDA(cudaGetLastError());
+  return VC_OK;
+}
+
+// normsq_parts: the squared norm is the sum of up to 4 device scalars (dense grads + per-token embedding slices).
+__global__ void k_adam(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                       long long n, const float* __restrict__ normsq_parts, int n_parts, float clip, float gscale,
+                       float lr_t, float b1, float b2, float eps, float* __restrict__ norm_out) {
+  float scale = gscale;
+  if (clip > 0.f) {
+    float ns = 0.f;
+    for (int i = 0; i < n_parts; ++i) ns += normsq_parts[i];
+    const float norm = sqrtf(ns) * gscale;
+    scale = gscale * clip / fmaxf(norm, clip);
+    if (norm_out && blockIdx.x == 0 && threadIdx.x == 0) *norm_out = norm;
+  }
+  const long long n4 = n / 4;
+  float4* p4 = reinterpret_cast<float4*>(p);
+  const float4* g4 = reinterpret_cast<const float4*>(g);
+  float4* m4 = reinterpret_cast<float4*>(m);
+  float4* v4 = reinterpret_cast<float4*>(v);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 pp = p4[i], gg = g4[i], mm = m4[i], vv = v4[i];
+#define VC_ADAM1(c)                                 \
+  {                                                 \
+    const float gs = gg.c * scale;                  \
+    mm.c = b1 * mm.c + (1.f - b1) * gs;             \
+    vv.c = b2 * vv.c + (1.f - b2) * gs * gs;        \
+    pp.c -= lr_t * mm.c / (sqrtf(vv.c) + eps);      \
+  }
+    VC_ADAM1(x) VC_ADAM1(y) VC_ADAM1(z) VC_ADAM1(w)
+#undef VC_ADAM1
+    p4[i] = pp;
+    m4[i] = mm;
+    v4[i] = vv;
+  }
+}
+int adam_step(cudaStream_t s, float* p, const float* g, float* m, float* v, long long n, const float* normsq_parts,
+              int n_parts, float clip, float gscale, float lr_t, float b1, float b2, float eps, float* norm_out) {
+  if (n <= 0) return VC_OK;
+  if (n % 4 != 0) return set_error(VC_E_ARG, "adam_step: length must be a multiple of 4 (padded flat buffer)");
+  k_adam<<<grid_for(n / 4, 256, 2), 256, 0, s>>>(p, g, m, v, n, normsq_parts, n_parts, clip, gscale, lr_t, b1, b2, eps, norm_out);
+  VC_CUDA(cudaGetLastError());
+  return VC_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// bf16 [rows, ld] (time-major rows t*N+n) -> fp32 [N*T, V] in the reference's row order n*T+t (debug tap).
+__global__ void k_logits_to_ref(const __nv_bfloat16* __restrict__ src, long long ld, float* __restrict__ dst, int N, int T,
+                                int V) {
+  const long long total = (long long)N * T * V;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % V);
+    const long long r = i / V;  // n*T + t
+    const int n = (int)(r / T), t = (int)(r - (long long)n * T);
+    dst[i] = __bfloat162float(src[((long long)t * N + n) * ld + c]);
+  }
+}
+int logits_to_ref(cudaStream_t s, const void* src, long long ld, float* dst, int N, int T, int V) {
+  k_logits_to_ref<<<grid_for((long long)N * T * V, 256, 4), 256, 0, s>>>((const __nv_bfloat16*)src, ld, dst, N, T, V);
+  VC_CUDA(cudaGetLastError());
+  return VC_OK;
+}
+
+__global__ void k_bf16_to_f32(const __nv_bfloat16* __restrict__ src, float* __restrict__ dst, long long rows, int cols,
+                              long long ld_src, long long ld_dst) {
+  const long long total = rows * cols;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / cols;
+    const int c = (int)(i - r * cols);
+    dst[r * ld_dst + c] = __bfloat162float(src[r * ld_src + c]);
+  }
+}
+int bf16_to_f32(cudaStream_t s, const void* src, float* dst, long long rows, int cols, long long ld_src, long long ld_dst) {
+  k_bf16_to_f32<<<grid_for(rows * cols, 256, 4), 256, 0, s>>>((const __nv_bfloat16*)src, dst, rows, cols, ld_src, ld_dst);
+  VC_CUDA(cudaGetLastError());
+  return VC_OK;
+}
+
+}  // namespace vc

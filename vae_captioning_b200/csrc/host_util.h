@@ -6,12 +6,12 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include "../../include/vaecap.h"
 #include "gemm.cuh"
 
 namespace vc {
 
-// Status codes of the C ABI (include/vaecap.h).
-enum : int { VC_OK = 0, VC_E_ARG = -1, VC_E_SHAPE = -2, VC_E_CUDA = -3, VC_E_NCCL = -4, VC_E_STATE = -5, VC_E_NOMEM = -6 };
+// Status codes VC_OK / VC_E_* come from the C ABI header (include/vaecap.h).
 
 std::string& last_error();  // thread-local message of the last failing call
 int set_error(int code, const char* fmt, ...);
@@ -20,7 +20,7 @@ int set_error(int code, const char* fmt, ...);
   do {                                                                                           \
     cudaError_t _e = (expr);                                                                     \
     if (_e != cudaSuccess)                                                                       \
-      return ::vc::set_error(::vc::VC_E_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, \
+      return ::vc::set_error(VC_E_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, \
                              __LINE__);                                                          \
   } while (0)
 #define VC_TRY(expr)           \

@@ -1,0 +1,666 @@
+// Train / eval step orchestration of the CVAE captioning graph (reference: main.py:43-191 builds
+// it, main.py:229-244 runs it). Everything is enqueued on the caller's stream; the only
+// synchronisation is the optional fetch of the step scalars.
+#include "model.h"
+#include <cmath>
+
+namespace vc {
+
+static inline int64_t round_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
+
+Model::~Model() {
+  for (void* p : allocs) cudaFree(p);
+  if (host_scal) cudaFreeHost(host_scal);
+}
+
+template <class T>
+int Model::dalloc(T** p, size_t count, bool zero) {
+  void* q = nullptr;
+  if (count == 0) count = 1;
+  cudaError_t e = cudaMalloc(&q, count * sizeof(T));
+  if (e != cudaSuccess) return set_error(VC_E_NOMEM, "cudaMalloc(%zu bytes) failed: %s", count * sizeof(T), cudaGetErrorString(e));
+  if (zero) VC_CUDA(cudaMemset(q, 0, count * sizeof(T)));
+  allocs.push_back(q);
+  *p = reinterpret_cast<T*>(q);
+  return VC_OK;
+}
+
+int Model::add_param(const std::string& name, std::vector<int64_t> shape, int region) {
+  ParamInfo pi;
+  pi.name = name;
+  pi.ndim = (int)shape.size();
+  pi.count = 1;
+  for (int i = 0; i < 4; ++i) pi.shape[i] = i < pi.ndim ? shape[i] : 1;
+  for (auto d : shape) pi.count *= d;
+  pi.region = region;
+  pi.trainable = region != 1;
+  pi.offset = -1;
+  index[name] = (int)params.size();
+  params.push_back(pi);
+  return VC_OK;
+}
+
+int Model::param_index(const char* name) const { return pidx(name); }
+
+static const char* kVggNames[13] = {"conv1_1", "conv1_2", "conv2_1", "conv2_2", "conv3_1", "conv3_2", "conv3_3",
+                                    "conv4_1", "conv4_2", "conv4_3", "conv5_1", "conv5_2", "conv5_3"};
+static const int kVggCin[13] = {3, 64, 64, 128, 128, 256, 256, 256, 512, 512, 512, 512, 512};
+static const int kVggCout[13] = {64, 64, 128, 128, 256, 256, 256, 512, 512, 512, 512, 512, 512};
+
+int Model::init(const vc_config& c, int dev) {
+  cfg = c;
+  device = dev;
+  VC_CUDA(cudaSetDevice(dev));
+  const int E = cfg.embed_size, He = cfg.encoder_hidden, Hd = cfg.decoder_hidden, Z = cfg.latent_size,
+            S = cfg.gen_z_samples, V = cfg.vocab_size, F = cfg.cnn_feature_size, K = cfg.num_clusters;
+  if (E % 64 || He % 64 || Hd % 64) return set_error(VC_E_SHAPE, "embed/hidden sizes must be multiples of 64");
+  if (F % 8) return set_error(VC_E_SHAPE, "cnn_feature_size must be a multiple of 8");
+  if (!cfg.no_encoder && ((int64_t)S * Z) % 8) return set_error(VC_E_SHAPE, "gen_z_samples*latent must be a multiple of 8");
+  if (cfg.prior < 0 || cfg.prior > 2) return set_error(VC_E_ARG, "unknown prior %d", cfg.prior);
+  if (cfg.num_captions < 1 || cfg.max_batch < 1 || cfg.max_len < 1) return set_error(VC_E_ARG, "bad batch geometry");
+  const bool has_cv = cfg.use_c_v || cfg.prior != VC_PRIOR_NORMAL;
+  maxN = cfg.max_batch * cfg.num_captions;
+  maxT = cfg.max_len;
+  ZP = (int)round_up(Z, 8);
+  VP = (int)round_up(V, 8);
+  KP = (int)round_up(K, 8);
+
+  // ---- parameter table, region 0 first, embeddings last inside region 0
+  add_param("imf_emb/kernel", {F, E}, 0);
+  add_param("imf_emb/bias", {E}, 0);
+  if (has_cv) {
+    const int r = cfg.use_c_v ? 0 : 1;  // created for GMM/AG even without --c_v but then unused (no gradient)
+    add_param("cv_emb/kernel", {K, E}, r);
+    add_param("cv_emb/bias", {E}, r);
+  }
+  if (!cfg.no_encoder) {
+    add_param("encoder/multi_rnn_cell/cell_0/lstm_cell/kernel", {E + He, 4 * He}, 0);
+    add_param("encoder/multi_rnn_cell/cell_0/lstm_cell/bias", {4 * He}, 0);
+    if (cfg.prior == VC_PRIOR_NORMAL) {
+      add_param("encoder/dense/kernel", {He, Z}, 0);
+      add_param("encoder/dense/bias", {Z}, 0);
+      add_param("encoder/dense_1/kernel", {He, Z}, 0);
+      add_param("encoder/dense_1/bias", {Z}, 0);
+    } else {
+      const char* tag = cfg.prior == VC_PRIOR_GMM ? "gmm_ll" : "ag_ll";
+      char buf[128];
+      for (int k = 0; k < K; ++k) {
+        snprintf(buf, sizeof(buf), "encoder/%s_%d/dense/kernel", tag, k);
+        add_param(buf, {He, Z}, 0);
+        snprintf(buf, sizeof(buf), "encoder/%s_%d/dense/bias", tag, k);
+        add_param(buf, {Z}, 0);
+        snprintf(buf, sizeof(buf), "encoder/%s_%d/dense_1/kernel", tag, k);
+        add_param(buf, {He, Z}, 0);
+        snprintf(buf, sizeof(buf), "encoder/%s_%d/dense_1/bias", tag, k);
+        add_param(buf, {Z}, 0);
+      }
+    }
+  }
+  add_param("decoder/net/multi_rnn_cell/cell_0/lstm_cell/kernel", {E + Hd, 4 * Hd}, 0);
+  add_param("decoder/net/multi_rnn_cell/cell_0/lstm_cell/bias", {4 * Hd}, 0);
+  if (!cfg.no_encoder) {
+    add_param("decoder/net/z_rnn/kernel", {(int64_t)Z * S, E}, 0);
+    add_param("decoder/net/z_rnn/bias", {E}, 0);
+  }
+  add_param("decoder/rnn_logits/kernel", {Hd, V}, 0);
+  add_param("decoder/rnn_logits/bias", {V}, 0);
+  const int first_emb = (int)params.size();
+  if (!cfg.no_encoder) add_param("encoder/enc_embeddings", {V, E}, 0);
+  add_param("decoder/net/dec_embeddings", {V, E}, 0);
+  if (cfg.with_cnn || cfg.fine_tune) {
+    const int r = cfg.fine_tune ? 2 : 1;
+    for (int l = 0; l < 13; ++l) {
+      const bool c5 = l >= 10;  // conv5_x variables are named weights_conv / biases_conv (image_embeddings.py:176-201)
+      add_param(std::string("cnn/") + kVggNames[l] + (c5 ? "/weights_conv" : "/weights"), {3, 3, kVggCin[l], kVggCout[l]}, r);
+      add_param(std::string("cnn/") + kVggNames[l] + (c5 ? "/biases_conv" : "/biases"), {kVggCout[l]}, r);
+    }
+    add_param("cnn/fc1/weights", {25088, 4096}, r);
+    add_param("cnn/fc1/biases", {4096}, r);
+    add_param("cnn/fc2/weights", {4096, 4096}, r);
+    add_param("cnn/fc2/biases", {4096}, r);
+  }
+  // offsets: region 0 (dense, then embeddings), 64-float tail, region 1, region 2
+  int64_t off = 0;
+  for (int i = 0; i < (int)params.size(); ++i)
+    if (params[i].region == 0 && i < first_emb) { params[i].offset = off; off += round_up(params[i].count, 64); }
+  n_dense = off;
+  for (int i = first_emb; i < (int)params.size(); ++i)
+    if (params[i].region == 0) { params[i].offset = off; off += round_up(params[i].count, 64); }
+  n_adam = off;
+  off += 64;
+  for (auto& p : params)
+    if (p.region == 1) { p.offset = off; off += round_up(p.count, 64); }
+  n_frozen = off - n_adam - 64;
+  for (auto& p : params)
+    if (p.region == 2) { p.offset = off; off += round_up(p.count, 64); }
+  n_cnn = off - n_adam - 64 - n_frozen;
+  n_total = off;
+  VC_TRY(dalloc(&Pf, n_total));
+  const int64_t n_opt = cfg.fine_tune ? n_total : n_adam + 64;
+  VC_TRY(dalloc(&Gf, n_opt));
+  VC_TRY(dalloc(&Mf, n_opt));
+  VC_TRY(dalloc(&Vf, n_opt));
+  g_tail = Gf + n_adam;
+
+  // ---- shadows
+  const int N = maxN, T = maxT;
+  VC_TRY(dalloc((uint16_t**)&imf_wt, (size_t)E * F));
+  if (has_cv) VC_TRY(dalloc((uint16_t**)&cv_wt, (size_t)E * KP));
+  auto setup_lstm = [&](LstmNet& L, const char* kname, const char* bname, int H, int pre) -> int {
+    L.p_kernel = pidx(kname);
+    L.p_bias = pidx(bname);
+    L.E = E;
+    L.H = H;
+    L.pre = pre;
+    L.steps = pre + T;
+    VC_TRY(dalloc((uint16_t**)&L.w_t_perm, (size_t)4 * H * (E + H)));
+    VC_TRY(dalloc((uint16_t**)&L.w_nat, (size_t)4 * H * (E + H)));
+    VC_TRY(dalloc((uint16_t**)&L.X, (size_t)L.steps * N * E));
+    VC_TRY(dalloc((uint16_t**)&L.Hs, (size_t)(L.steps + 1) * N * H));
+    VC_TRY(dalloc(&L.Cs, (size_t)(L.steps + 1) * N * H));
+    VC_TRY(dalloc((uint16_t**)&L.G, (size_t)L.steps * N * 4 * H));
+    VC_TRY(dalloc((uint16_t**)&L.dG, (size_t)L.steps * N * 4 * H));
+    VC_TRY(dalloc(&L.dX, (size_t)L.steps * N * E));
+    VC_TRY(dalloc(&L.dh_carry, (size_t)N * H));
+    VC_TRY(dalloc(&L.dc_carry, (size_t)N * H));
+    return VC_OK;
+  };
+  const int cvstep = cfg.use_c_v ? 1 : 0;
+  if (!cfg.no_encoder)
+    VC_TRY(setup_lstm(enc, "encoder/multi_rnn_cell/cell_0/lstm_cell/kernel", "encoder/multi_rnn_cell/cell_0/lstm_cell/bias",
+                      He, 1 + cvstep));
+  VC_TRY(setup_lstm(dec, "decoder/net/multi_rnn_cell/cell_0/lstm_cell/kernel",
+                    "decoder/net/multi_rnn_cell/cell_0/lstm_cell/bias", Hd, 1 + cvstep + (cfg.no_encoder ? 0 : 1)));
+  if (!cfg.no_encoder) {
+    heads_cols = (cfg.prior == VC_PRIOR_NORMAL ? 1 : K) * 2 * ZP;
+    VC_TRY(dalloc((uint16_t**)&heads_wt, (size_t)heads_cols * He));
+    VC_TRY(dalloc((uint16_t**)&heads_nat, (size_t)He * heads_cols));
+    VC_TRY(dalloc(&heads_bias, (size_t)heads_cols));
+    VC_TRY(dalloc((uint16_t**)&z_wt, (size_t)E * S * Z));
+    VC_TRY(dalloc((uint16_t**)&z_nat, (size_t)E * S * Z));
+    VC_TRY(dalloc((uint16_t**)&enc_emb_h, (size_t)V * E));
+  }
+  VC_TRY(dalloc((uint16_t**)&wo_t, (size_t)V * Hd));
+  VC_TRY(dalloc((uint16_t**)&wo_nat, (size_t)Hd * VP));
+  VC_TRY(dalloc((uint16_t**)&dec_emb_h, (size_t)V * E));
+
+  // ---- workspace
+  const int B = cfg.max_batch;
+  VC_TRY(dalloc((uint16_t**)&feats_h, (size_t)B * F));
+  VC_TRY(dalloc(&imf_f, (size_t)B * E));
+  VC_TRY(dalloc((uint16_t**)&dimf_h, (size_t)B * E));
+  if (has_cv) {
+    VC_TRY(dalloc((uint16_t**)&cv_h, (size_t)N * KP));
+    VC_TRY(dalloc(&cv_f, (size_t)N * E));
+    VC_TRY(dalloc((uint16_t**)&dcv_h, (size_t)N * E));
+  }
+  VC_TRY(dalloc((uint16_t**)&Out, (size_t)T * N * Hd));
+  VC_TRY(dalloc((uint16_t**)&logits, (size_t)T * N * VP));
+  VC_TRY(dalloc(&dOut, (size_t)T * N * Hd));
+  VC_TRY(dalloc(&ce_row, (size_t)T * N));
+  if (!cfg.no_encoder) {
+    VC_TRY(dalloc(&heads_f, (size_t)N * heads_cols));
+    VC_TRY(dalloc(&mu, (size_t)N * Z));
+    VC_TRY(dalloc(&sd, (size_t)N * Z));
+    VC_TRY(dalloc(&kl_row, (size_t)N));
+    VC_TRY(dalloc(&dkl_dmu, (size_t)N * Z));
+    VC_TRY(dalloc(&dkl_dsd, (size_t)N * Z));
+    VC_TRY(dalloc(&cm, (size_t)N * Z));
+    VC_TRY(dalloc((uint16_t**)&z, (size_t)S * N * Z));
+    VC_TRY(dalloc(&zdec_f, (size_t)N * E));
+    VC_TRY(dalloc((uint16_t**)&dzdec_h, (size_t)N * E));
+    VC_TRY(dalloc(&dz, (size_t)S * N * Z));
+    VC_TRY(dalloc((uint16_t**)&dheads, (size_t)N * heads_cols));
+  }
+  VC_TRY(dalloc(&scal, 64));
+  VC_TRY(dalloc(&tmp_bias, (size_t)std::max(heads_cols, 4 * std::max(He, Hd)) + 64));
+  const size_t img_elems = cfg.fine_tune ? (size_t)224 * 224 * 3 : (size_t)F;
+  VC_TRY(dalloc(&st_feats, (size_t)B * img_elems));
+  VC_TRY(dalloc(&st_cv, (size_t)N * K));
+  VC_TRY(dalloc(&st_lbl, (size_t)N * T));
+  VC_TRY(dalloc(&st_in, (size_t)N * T));
+  VC_TRY(dalloc(&st_len, (size_t)N));
+  VC_CUDA(cudaMallocHost((void**)&host_scal, 64 * sizeof(float)));
+  shadows_dirty = true;
+  return VC_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+int Model::param_set(const char* name, const float* src) {
+  const int i = pidx(name);
+  if (i < 0) return set_error(VC_E_ARG, "unknown variable '%s'", name);
+  VC_CUDA(cudaMemcpy(pp(i), src, params[i].count * sizeof(float), cudaMemcpyHostToDevice));
+  shadows_dirty = true;
+  return VC_OK;
+}
+int Model::param_get(const char* name, float* dst) {
+  const int i = pidx(name);
+  if (i < 0) return set_error(VC_E_ARG, "unknown variable '%s'", name);
+  VC_CUDA(cudaDeviceSynchronize());
+  VC_CUDA(cudaMemcpy(dst, pp(i), params[i].count * sizeof(float), cudaMemcpyDeviceToHost));
+  return VC_OK;
+}
+int Model::grad_get(const char* name, float* dst) {
+  const int i = pidx(name);
+  if (i < 0) return set_error(VC_E_ARG, "unknown variable '%s'", name);
+  if (params[i].region == 1 || (params[i].region == 2 && !cfg.fine_tune))
+    return set_error(VC_E_STATE, "variable '%s' has no gradient in this configuration", name);
+  VC_CUDA(cudaDeviceSynchronize());
+  VC_CUDA(cudaMemcpy(dst, gp(i), params[i].count * sizeof(float), cudaMemcpyDeviceToHost));
+  return VC_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+int Model::refresh_shadows(cudaStream_t s) {
+  const int E = cfg.embed_size, Z = cfg.latent_size, S = cfg.gen_z_samples, V = cfg.vocab_size, F = cfg.cnn_feature_size,
+            K = cfg.num_clusters;
+  VC_TRY(transpose_cast(s, pp(pidx("imf_emb/kernel")), imf_wt, F, E, E, F, 0, 0));
+  if (cv_wt) VC_TRY(transpose_cast(s, pp(pidx("cv_emb/kernel")), cv_wt, K, E, E, KP, 0, 0));
+  auto lstm = [&](LstmNet& L) -> int {
+    VC_TRY(transpose_cast(s, pp(L.p_kernel), L.w_t_perm, L.E + L.H, 4 * L.H, 4 * L.H, L.E + L.H, L.H, 64));
+    VC_TRY(cast_f32_bf16(s, pp(L.p_kernel), L.w_nat, L.E + L.H, 4 * L.H, 4 * L.H, 4 * L.H));
+    return VC_OK;
+  };
+  if (!cfg.no_encoder) {
+    VC_TRY(lstm(enc));
+    const int He = cfg.encoder_hidden;
+    const int nh = cfg.prior == VC_PRIOR_NORMAL ? 1 : K;
+    for (int k = 0; k < nh; ++k) {
+      int pk[2], pb[2];
+      if (cfg.prior == VC_PRIOR_NORMAL) {
+        pk[0] = pidx("encoder/dense/kernel"); pb[0] = pidx("encoder/dense/bias");
+        pk[1] = pidx("encoder/dense_1/kernel"); pb[1] = pidx("encoder/dense_1/bias");
+      } else {
+        // the four variables of head k were registered consecutively
+        const char* tag = cfg.prior == VC_PRIOR_GMM ? "gmm_ll" : "ag_ll";
+        char buf[128];
+        snprintf(buf, sizeof(buf), "encoder/%s_%d/dense/kernel", tag, k);
+        pk[0] = pidx(buf); pb[0] = pk[0] + 1; pk[1] = pk[0] + 2; pb[1] = pk[0] + 3;
+      }
+      for (int w = 0; w < 2; ++w) {
+        const int64_t col = ((int64_t)k * 2 + w) * ZP;
+        VC_TRY(transpose_cast(s, pp(pk[w]), (uint16_t*)heads_wt + col * He, He, Z, Z, He, 0, 0));
+        VC_TRY(cast_f32_bf16(s, pp(pk[w]), (uint16_t*)heads_nat + col, He, Z, Z, heads_cols));
+        VC_CUDA(cudaMemcpyAsync(heads_bias + col, pp(pb[w]), Z * sizeof(float), cudaMemcpyDeviceToDevice, s));
+      }
+    }
+    const int pz = pidx("decoder/net/z_rnn/kernel");
+    VC_TRY(transpose_cast(s, pp(pz), z_wt, S * Z, E, E, (int64_t)S * Z, 0, 0));
+    VC_TRY(cast_f32_bf16(s, pp(pz), z_nat, (int64_t)S * Z, E, E, E));
+    VC_TRY(cast_f32_bf16(s, pp(pidx("encoder/enc_embeddings")), enc_emb_h, V, E, E, E));
+  }
+  VC_TRY(lstm(dec));
+  const int po = pidx("decoder/rnn_logits/kernel");
+  VC_TRY(transpose_cast(s, pp(po), wo_t, cfg.decoder_hidden, V, V, cfg.decoder_hidden, 0, 0));
+  VC_TRY(cast_f32_bf16(s, pp(po), wo_nat, cfg.decoder_hidden, V, V, VP));
+  VC_TRY(cast_f32_bf16(s, pp(pidx("decoder/net/dec_embeddings")), dec_emb_h, V, E, E, E));
+  shadows_dirty = false;
+  return VC_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+int Model::stage_inputs(const float* feats, const int32_t* lbl, const int32_t* inp, const int32_t* len, const float* cv,
+                        int B, int T, StepInputs* out, cudaStream_t s) {
+  if (B < 1 || B > cfg.max_batch || T < 1 || T > maxT)
+    return set_error(VC_E_SHAPE, "batch %d x len %d exceeds the handle's max_batch %d / max_len %d", B, T, cfg.max_batch, maxT);
+  const int N = B * cfg.num_captions;
+  const size_t fe = cfg.fine_tune ? (size_t)224 * 224 * 3 : (size_t)cfg.cnn_feature_size;
+  VC_CUDA(cudaMemcpyAsync(st_feats, feats, B * fe * sizeof(float), cudaMemcpyHostToDevice, s));
+  VC_CUDA(cudaMemcpyAsync(st_lbl, lbl, (size_t)N * T * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+  VC_CUDA(cudaMemcpyAsync(st_in, inp, (size_t)N * T * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+  VC_CUDA(cudaMemcpyAsync(st_len, len, (size_t)N * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+  out->feats = st_feats;
+  out->cap_lbl = st_lbl;
+  out->cap_in = st_in;
+  out->len = st_len;
+  out->c_v = nullptr;
+  if (cv != nullptr) {
+    VC_CUDA(cudaMemcpyAsync(st_cv, cv, (size_t)N * cfg.num_clusters * sizeof(float), cudaMemcpyHostToDevice, s));
+    out->c_v = st_cv;
+  }
+  out->B = B;
+  out->T = T;
+  return VC_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+int Model::lstm_forward(LstmNet& L, int N, int T, const int32_t* len, void* out, const float* out_keep, cudaStream_t s) {
+  const int steps = L.pre + T;
+  uint16_t* X = (uint16_t*)L.X;
+  uint16_t* Hs = (uint16_t*)L.Hs;
+  uint16_t* Gt = (uint16_t*)L.G;
+  // zero initial state (cell_0.zero_state, encoder.py:42-44 / decoder.py:96-98); slot 0 is re-zeroed every
+  // call because the slot pitch depends on the current batch size
+  VC_CUDA(cudaMemsetAsync(Hs, 0, (size_t)N * L.H * 2, s));
+  VC_CUDA(cudaMemsetAsync(L.Cs, 0, (size_t)N * L.H * sizeof(float), s));
+  for (int st = 0; st < steps; ++st) {
+    LstmFwdArgs a{};
+    const int t = st - L.pre;
+    a.x = X + (size_t)st * N * L.E;
+    a.h_prev = Hs + (size_t)st * N * L.H;
+    a.c_prev = L.Cs + (size_t)st * N * L.H;
+    a.h_out = Hs + (size_t)(st + 1) * N * L.H;
+    a.c_out = L.Cs + (size_t)(st + 1) * N * L.H;
+    a.gates = Gt + (size_t)st * N * 4 * L.H;
+    a.out = (out != nullptr && t >= 0) ? (uint16_t*)out + (size_t)t * N * L.H : nullptr;
+    a.w_t_perm = L.w_t_perm;
+    a.bias = pp(L.p_bias);
+    a.lengths = t >= 0 ? len : nullptr;
+    a.out_keep = (out_keep != nullptr && t >= 0) ? out_keep + (size_t)t * L.H : nullptr;  // mask is [N, T, H]
+    a.out_keep_ld = (long long)T * L.H;
+    a.inv_keep = 1.f / cfg.dec_lstm_drop;
+    a.t = t;
+    a.N = N;
+    a.E = L.E;
+    a.H = L.H;
+    VC_TRY(lstm_fwd_step(s, a));
+  }
+  return VC_OK;
+}
+
+int Model::lstm_backward(LstmNet& L, int N, int T, const int32_t* len, const float* d_out, const float* out_keep,
+                         cudaStream_t s) {
+  const int steps = L.pre + T;
+  uint16_t* Gt = (uint16_t*)L.G;
+  uint16_t* dGt = (uint16_t*)L.dG;
+  for (int st = steps - 1; st >= 0; --st) {
+    LstmBwdArgs a{};
+    const int t = st - L.pre;
+    a.d_gates_next = st == steps - 1 ? nullptr : dGt + (size_t)(st + 1) * N * 4 * L.H;
+    a.w_nat = L.w_nat;
+    a.gates = Gt + (size_t)st * N * 4 * L.H;
+    a.c_prev = L.Cs + (size_t)st * N * L.H;
+    a.c_cur = L.Cs + (size_t)(st + 1) * N * L.H;
+    a.d_out = (d_out != nullptr && t >= 0) ? d_out + (size_t)t * N * L.H : nullptr;
+    a.out_keep = (out_keep != nullptr && t >= 0) ? out_keep + (size_t)t * L.H : nullptr;
+    a.out_keep_ld = (long long)T * L.H;
+    a.inv_keep = 1.f / cfg.dec_lstm_drop;
+    a.dh_carry = L.dh_carry;
+    a.dc_carry = L.dc_carry;
+    a.d_gates = dGt + (size_t)st * N * 4 * L.H;
+    a.lengths = t >= 0 ? len : nullptr;
+    a.t = t;
+    a.N = N;
+    a.E = L.E;
+    a.H = L.H;
+    VC_TRY(lstm_bwd_step(s, a));
+  }
+  // weight gradient: dW[E+H, 4H] = [X ; H_prev]^T x dG over all steps (one GEMM, split-K, fp32 atomics)
+  const long long rows = (long long)steps * N;
+  Operand AX{L.X, rows, L.E, L.E, true};
+  Operand AH{L.Hs, rows, L.H, L.H, true};
+  Operand BG{L.dG, rows, 4LL * L.H, 4LL * L.H, true};
+  EpiStore e{};
+  e.out = gp(L.p_kernel);
+  e.ld = 4 * L.H;
+  e.atomic = 1;
+  e.alpha = 1.f;
+  const int tiles = ((L.E + L.H + 127) / 128) * ((4 * L.H + 255) / 256);
+  int splits = std::max(1, num_sms() / std::max(1, tiles));
+  if (L.E % 128 == 0) {
+    VC_TRY(gemm_store(s, AX, &AH, L.E, BG, L.E + L.H, 4 * L.H, (int)rows, e, 256, splits));
+  } else {  // E not a multiple of the 128-row tile: two GEMMs
+    EpiStore e2 = e;
+    VC_TRY(gemm_store(s, AX, nullptr, 0, BG, L.E, 4 * L.H, (int)rows, e, 256, splits));
+    e2.out = gp(L.p_kernel) + (size_t)L.E * 4 * L.H;
+    VC_TRY(gemm_store(s, AH, nullptr, 0, BG, L.H, 4 * L.H, (int)rows, e2, 256, splits));
+  }
+  VC_TRY(colsum_bf16(s, L.dG, rows, 4 * L.H, 4 * L.H, gp(L.p_bias)));
+  // input gradient: dX[steps*N, E] = dG x W_x^T  (B = rows 0..E of the natural shadow)
+  Operand AG{L.dG, rows, 4LL * L.H, 4LL * L.H, false};
+  Operand BW{L.w_nat, L.E, 4LL * L.H, 4LL * L.H, false};
+  EpiStore ex{};
+  ex.out = L.dX;
+  ex.ld = L.E;
+  ex.alpha = 1.f;
+  VC_TRY(gemm_store(s, AG, nullptr, 0, BW, (int)rows, L.E, 4 * L.H, ex, L.E % 256 == 0 ? 256 : 64, 1));
+  return VC_OK;
+}
+
+static float annealing_coeff(const vc_config& c, int64_t gs) {  // main.py:162-170
+  if (c.fine_tune || c.restore) return 1.f;
+  if (c.ann_param > 1.f) return (tanhf(((float)gs - 1000.f * c.ann_param) / 1000.f) + 1.f) / 2.f;
+  return 1.f;
+}
+
+// ------------------------------------------------------------------------------------------
+// scal layout: 0 ce_sum, 1 mask_sum, 2 mask count (pre-pass), 3 kl_sum, 7 global norm
+int Model::forward(const StepInputs& in, bool write_grad, cudaStream_t s) {
+  const int B = in.B, T = in.T, C = cfg.num_captions, N = B * C;
+  const int E = cfg.embed_size, Hd = cfg.decoder_hidden, Z = cfg.latent_size, S = cfg.gen_z_samples, V = cfg.vocab_size,
+            F = cfg.cnn_feature_size, K = cfg.num_clusters;
+  if (B < 1 || B > cfg.max_batch || T < 1 || T > maxT) return set_error(VC_E_SHAPE, "batch/len out of range");
+  if (cfg.fine_tune) return set_error(VC_E_STATE, "fine_tune training is not implemented in this build");
+  if (cfg.prior != VC_PRIOR_NORMAL) return set_error(VC_E_STATE, "GMM/AG priors are not implemented in this build");
+  const bool has_cv = cfg.use_c_v || cfg.prior != VC_PRIOR_NORMAL;
+  if (has_cv && in.c_v == nullptr) return set_error(VC_E_ARG, "this configuration needs cluster vectors (c_v)");
+  if (cfg.dec_keep_rate < 1.f && in.rng.emb_keep_dev == nullptr)
+    return set_error(VC_E_ARG, "dec_keep_rate < 1 needs rng.emb_keep_dev (Philox dropout masks are not implemented)");
+  if (cfg.dec_lstm_drop < 1.f && in.rng.out_keep_dev == nullptr)
+    return set_error(VC_E_ARG, "dec_lstm_drop < 1 needs rng.out_keep_dev (Philox dropout masks are not implemented)");
+  if (shadows_dirty) VC_TRY(refresh_shadows(s));
+  VC_CUDA(cudaMemsetAsync(scal, 0, 64 * sizeof(float), s));
+
+  // image features -> embedding space (main.py:84-94; projection before tiling, Q7)
+  VC_TRY(cast_f32_bf16(s, in.feats, feats_h, B, F, F, F));
+  VC_CUDA(cudaMemsetAsync(imf_f, 0, (size_t)B * E * sizeof(float), s));
+  {
+    Operand A{feats_h, B, F, F, false}, Bw{imf_wt, E, F, F, false};
+    EpiStore e{};
+    e.out = imf_f; e.ld = E; e.bias = pp(pidx("imf_emb/bias")); e.atomic = 1; e.alpha = 1.f;
+    VC_TRY(gemm_store(s, A, nullptr, 0, Bw, B, E, F, e, 64, 8));
+  }
+  VC_TRY(tile_cast(s, imf_f, cfg.no_encoder ? nullptr : enc.X, dec.X, B, C, E));
+  if (has_cv) {  // main.py:103-114
+    VC_TRY(cast_f32_bf16(s, in.c_v, cv_h, N, K, K, KP));
+    if (cfg.use_c_v) {
+      Operand A{cv_h, N, K, KP, false}, Bw{cv_wt, E, K, KP, false};
+      EpiStore e{};
+      e.out = cv_f; e.ld = E; e.bias = pp(pidx("cv_emb/bias")); e.alpha = 1.f;
+      VC_TRY(gemm_store(s, A, nullptr, 0, Bw, N, E, K, e, 64, 1));
+      VC_TRY(tile_cast(s, cv_f, cfg.no_encoder ? nullptr : (uint16_t*)enc.X + (size_t)N * E,
+                       (uint16_t*)dec.X + (size_t)N * E, N, 1, E));
+    }
+  }
+  if (!cfg.no_encoder) {
+    // q(z | x, I): vae_model/encoder.py:24-110 (the encoder consumes the label sequence, Q8)
+    const int He = cfg.encoder_hidden;
+    VC_TRY(embed_gather(s, enc_emb_h, in.cap_lbl, (uint16_t*)enc.X + (size_t)enc.pre * N * E, nullptr, 1.f, N, T, E, V));
+    VC_TRY(lstm_forward(enc, N, T, in.len, nullptr, nullptr, s));
+    const uint16_t* hT = (uint16_t*)enc.Hs + (size_t)(enc.pre + T) * N * He;
+    {
+      Operand A{hT, N, He, He, false}, Bw{heads_wt, heads_cols, He, He, false};
+      EpiStore e{};
+      e.out = heads_f; e.ld = heads_cols; e.bias = heads_bias; e.alpha = 1.f;
+      VC_TRY(gemm_store(s, A, nullptr, 0, Bw, N, heads_cols, He, e, 64, 1));
+    }
+    VC_TRY(heads_to_musd(s, heads_f, heads_cols, ZP, mu, sd, N, Z));
+    VC_TRY(kl_rows(s, mu, sd, cm, cfg.prior, kl_row, dkl_dmu, dkl_dsd, scal + 3, N, Z));
+    VC_TRY(sample_z(s, mu, sd, in.rng.eps_dev, in.rng.seed, (unsigned long long)in.global_step, z, nullptr, S, (long long)N * Z));
+    // p(x | z, I): z reshaped row-major [S,N,Z] -> [N, S*Z] (Q1), decoder.py:109-113
+    VC_CUDA(cudaMemsetAsync(zdec_f, 0, (size_t)N * E * sizeof(float), s));
+    {
+      const int SZ = S * Z;
+      Operand A{z, N, SZ, SZ, false}, Bw{z_wt, E, SZ, SZ, false};
+      EpiStore e{};
+      e.out = zdec_f; e.ld = E; e.bias = pp(pidx("decoder/net/z_rnn/bias")); e.atomic = 1; e.alpha = 1.f;
+      const int tiles = ((N + 127) / 128) * ((E + 127) / 128);
+      VC_TRY(gemm_store(s, A, nullptr, 0, Bw, N, E, SZ, e, 128, std::max(1, num_sms() / tiles)));
+    }
+    VC_TRY(tile_cast(s, zdec_f, nullptr, (uint16_t*)dec.X + (size_t)(dec.pre - 1) * N * E, N, 1, E));
+  }
+  // decoder (decoder.py:77-129)
+  VC_TRY(embed_gather(s, dec_emb_h, in.cap_in, (uint16_t*)dec.X + (size_t)dec.pre * N * E,
+                      cfg.dec_keep_rate < 1.f ? in.rng.emb_keep_dev : nullptr, 1.f / cfg.dec_keep_rate, N, T, E, V));
+  VC_TRY(lstm_forward(dec, N, T, in.len, Out, cfg.dec_lstm_drop < 1.f ? in.rng.out_keep_dev : nullptr, s));
+  {
+    Operand A{Out, (long long)T * N, Hd, Hd, false}, Bw{wo_t, V, Hd, Hd, false};
+    EpiStore e{};
+    e.out = logits; e.ld = VP; e.bias = pp(pidx("decoder/rnn_logits/bias")); e.out_bf16 = 1; e.alpha = 1.f;
+    VC_TRY(gemm_store(s, A, nullptr, 0, Bw, T * N, V, Hd, e, 256, 1));
+  }
+  // masked cross-entropy (main.py:152-158); AG differentiates the sum of an [N] lower bound (Q2)
+  VC_TRY(count_mask(s, in.cap_lbl, (long long)N * T, scal + 2));
+  const float loss_scale = cfg.prior == VC_PRIOR_AG ? (float)N : 1.f;
+  VC_TRY(ce_rows(s, logits, VP, in.cap_lbl, N, T, V, scal, ce_row, scal + 2, loss_scale, write_grad ? 1 : 0));
+  last_ann = annealing_coeff(cfg, in.global_step);
+  have_forward = true;
+  logits_intact = !write_grad;
+  lastN = N;
+  lastT = T;
+  return VC_OK;
+}
+
+int Model::backward(const StepInputs& in, cudaStream_t s) {
+  const int B = in.B, T = in.T, C = cfg.num_captions, N = B * C;
+  const int E = cfg.embed_size, Hd = cfg.decoder_hidden, Z = cfg.latent_size, S = cfg.gen_z_samples, V = cfg.vocab_size,
+            F = cfg.cnn_feature_size, K = cfg.num_clusters;
+  VC_CUDA(cudaMemsetAsync(Gf, 0, (size_t)(n_adam + 64) * sizeof(float), s));
+  const long long rows = (long long)T * N;
+  // logits layer: dOut = dlogits x W_o^T ; dW_o = Out^T x dlogits ; db_o = colsum(dlogits)
+  {
+    Operand A{logits, rows, V, VP, false}, Bw{wo_nat, Hd, V, VP, false};
+    EpiStore e{};
+    e.out = dOut; e.ld = Hd; e.alpha = 1.f;
+    VC_TRY(gemm_store(s, A, nullptr, 0, Bw, (int)rows, Hd, V, e, Hd % 256 == 0 ? 256 : 64, 1));
+    Operand A2{Out, rows, Hd, Hd, true}, B2{logits, rows, V, VP, true};
+    EpiStore e2{};
+    e2.out = gp(pidx("decoder/rnn_logits/kernel")); e2.ld = V; e2.alpha = 1.f;
+    VC_TRY(gemm_store(s, A2, nullptr, 0, B2, Hd, V, (int)rows, e2, 256, 1));
+    VC_TRY(colsum_bf16(s, logits, rows, V, VP, gp(pidx("decoder/rnn_logits/bias"))));
+  }
+  // decoder BPTT
+  VC_CUDA(cudaMemsetAsync(dec.dh_carry, 0, (size_t)N * Hd * sizeof(float), s));
+  VC_CUDA(cudaMemsetAsync(dec.dc_carry, 0, (size_t)N * Hd * sizeof(float), s));
+  VC_TRY(lstm_backward(dec, N, T, in.len, dOut, cfg.dec_lstm_drop < 1.f ? in.rng.out_keep_dev : nullptr, s));
+  VC_TRY(embed_scatter(s, dec.dX + (size_t)dec.pre * N * E, in.cap_in, gp(pidx("decoder/net/dec_embeddings")),
+                       cfg.dec_keep_rate < 1.f ? in.rng.emb_keep_dev : nullptr, 1.f / cfg.dec_keep_rate, g_tail + 1, N, T,
+                       E, V));
+  if (!cfg.no_encoder) {
+    const int He = cfg.encoder_hidden;
+    const int SZ = S * Z;
+    // z_rnn: dz = dzdec x W_z^T ; dW_z = z^T x dzdec ; db_z = colsum(dzdec)
+    const float* dzdec = dec.dX + (size_t)(dec.pre - 1) * N * E;
+    VC_TRY(cast_f32_bf16(s, dzdec, dzdec_h, N, E, E, E));
+    {
+      Operand A{dzdec_h, N, E, E, false}, Bw{z_nat, SZ, E, E, false};
+      EpiStore e{};
+      e.out = dz; e.ld = SZ; e.alpha = 1.f;
+      VC_TRY(gemm_store(s, A, nullptr, 0, Bw, N, SZ, E, e, 256, 1));
+      Operand A2{z, N, SZ, SZ, true}, B2{dzdec_h, N, E, E, true};
+      EpiStore e2{};
+      e2.out = gp(pidx("decoder/net/z_rnn/kernel")); e2.ld = E; e2.alpha = 1.f;
+      VC_TRY(gemm_store(s, A2, nullptr, 0, B2, SZ, E, N, e2, E % 256 == 0 ? 256 : 64, 1));
+      VC_TRY(colsum_bf16(s, dzdec_h, N, E, E, gp(pidx("decoder/net/z_rnn/bias"))));
+    }
+    // reparameterisation + KL -> head gradients. lower_bound = rec + ann * KL / 10 (main.py:172-174);
+    // Normal/GMM KL is a batch mean, AG a per-row vector whose sum is differentiated (Q2).
+    const float ann = annealing_coeff(cfg, in.global_step);
+    const float kl_scale = cfg.prior == VC_PRIOR_AG ? ann / 10.f : ann / (10.f * N);
+    VC_TRY(dz_reduce(s, dz, in.rng.eps_dev, in.rng.seed, (unsigned long long)in.global_step, sd, dkl_dmu, dkl_dsd, kl_scale,
+                     dheads, heads_cols, ZP, nullptr, nullptr, S, N, Z));
+    const uint16_t* hT = (uint16_t*)enc.Hs + (size_t)(enc.pre + T) * N * He;
+    {
+      Operand A{dheads, N, heads_cols, heads_cols, false}, Bw{heads_nat, He, heads_cols, heads_cols, false};
+      EpiStore e{};
+      e.out = enc.dh_carry; e.ld = He; e.alpha = 1.f;
+      VC_TRY(gemm_store(s, A, nullptr, 0, Bw, N, He, heads_cols, e, 64, 1));
+      VC_CUDA(cudaMemsetAsync(tmp_bias, 0, (size_t)heads_cols * sizeof(float), s));
+      VC_TRY(colsum_bf16(s, dheads, N, heads_cols, heads_cols, tmp_bias));
+      const int pk[2] = {pidx("encoder/dense/kernel"), pidx("encoder/dense_1/kernel")};
+      const int pb[2] = {pidx("encoder/dense/bias"), pidx("encoder/dense_1/bias")};
+      for (int w = 0; w < 2; ++w) {
+        Operand A2{hT, N, He, He, true}, B2{(uint16_t*)dheads + (size_t)w * ZP, N, Z, heads_cols, true};
+        EpiStore e2{};
+        e2.out = gp(pk[w]); e2.ld = Z; e2.alpha = 1.f;
+        VC_TRY(gemm_store(s, A2, nullptr, 0, B2, He, Z, N, e2, 64, 1));
+        VC_CUDA(cudaMemcpyAsync(gp(pb[w]), tmp_bias + (size_t)w * ZP, Z * sizeof(float), cudaMemcpyDeviceToDevice, s));
+      }
+    }
+    VC_CUDA(cudaMemsetAsync(enc.dc_carry, 0, (size_t)N * He * sizeof(float), s));
+    VC_TRY(lstm_backward(enc, N, T, in.len, nullptr, nullptr, s));
+    VC_TRY(embed_scatter(s, enc.dX + (size_t)enc.pre * N * E, in.cap_lbl, gp(pidx("encoder/enc_embeddings")), nullptr, 1.f,
+                         g_tail + 0, N, T, E, V));
+  }
+  // imf_emb: gradient of the tiled projection sums over the C captions of an image (Q7)
+  VC_TRY(tile_reduce(s, dec.dX, cfg.no_encoder ? nullptr : enc.dX, nullptr, dimf_h, B, C, E));
+  {
+    Operand A{feats_h, B, F, F, true}, Bw{dimf_h, B, E, E, true};
+    EpiStore e{};
+    e.out = gp(pidx("imf_emb/kernel")); e.ld = E; e.alpha = 1.f;
+    VC_TRY(gemm_store(s, A, nullptr, 0, Bw, F, E, B, e, E % 256 == 0 ? 256 : 64, 1));
+    VC_TRY(colsum_bf16(s, dimf_h, B, E, E, gp(pidx("imf_emb/bias"))));
+  }
+  if (cfg.use_c_v) {
+    VC_TRY(tile_reduce(s, dec.dX + (size_t)N * E, cfg.no_encoder ? nullptr : enc.dX + (size_t)N * E, nullptr, dcv_h, N, 1, E));
+    Operand A{cv_h, N, K, KP, true}, Bw{dcv_h, N, E, E, true};
+    EpiStore e{};
+    e.out = gp(pidx("cv_emb/kernel")); e.ld = E; e.alpha = 1.f;
+    VC_TRY(gemm_store(s, A, nullptr, 0, Bw, K, E, N, e, E % 256 == 0 ? 256 : 64, 1));
+    VC_TRY(colsum_bf16(s, dcv_h, N, E, E, gp(pidx("cv_emb/bias"))));
+  }
+  // squared norm of the dense (non-embedding) gradients -> tail[2]; embedding slices are in tail[0..1] (Q4)
+  return VC_OK;
+}
+
+int Model::apply(float grad_scale, cudaStream_t s) {
+  // ops/optimizers.py:13-40: clip_by_global_norm(5.0) then Adam(lr, beta1=0.8); TF Adam form (Q5)
+  VC_CUDA(cudaMemsetAsync(g_tail + 2, 0, sizeof(float), s));
+  VC_TRY(sumsq(s, Gf, n_dense, g_tail + 2));
+  adam_t += 1;
+  const double b1 = 0.8, b2 = 0.999;
+  const float lr_t = (float)(cfg.learning_rate * std::sqrt(1.0 - std::pow(b2, (double)adam_t)) / (1.0 - std::pow(b1, (double)adam_t)));
+  VC_TRY(adam_step(s, Pf, Gf, Mf, Vf, n_adam, g_tail, 3, cfg.clip_norm, grad_scale, lr_t, (float)b1, (float)b2, 1e-8f, scal + 7));
+  shadows_dirty = true;
+  VC_TRY(refresh_shadows(s));
+  return VC_OK;
+}
+
+int Model::fetch(vc_step_out* out, cudaStream_t s) {
+  if (out == nullptr) return VC_OK;
+  VC_CUDA(cudaMemcpyAsync(host_scal, scal, 16 * sizeof(float), cudaMemcpyDeviceToHost, s));
+  VC_CUDA(cudaStreamSynchronize(s));
+  const float cnt = host_scal[1] > 0.f ? host_scal[1] : 1.f;
+  out->rec_loss = host_scal[0] / cnt;
+  out->n_tokens = host_scal[1];
+  out->kld = cfg.no_encoder ? 0.f : host_scal[3] / (float)lastN;
+  out->global_norm = host_scal[7];
+  out->annealing = last_ann;
+  out->lower_bound = cfg.no_encoder ? out->rec_loss : out->rec_loss + last_ann * out->kld / 10.f;
+  return VC_OK;
+}
+
+int Model::forward_debug(float* logits_host, float* mu_host, float* std_host, float* z_host, float* kl_host, float* ce_host) {
+  if (!have_forward) return set_error(VC_E_STATE, "no forward pass has run on this handle");
+  VC_CUDA(cudaDeviceSynchronize());
+  const int N = lastN, T = lastT, V = cfg.vocab_size, Z = cfg.latent_size, S = cfg.gen_z_samples;
+  if (logits_host != nullptr) {
+    if (!logits_intact)
+      return set_error(VC_E_STATE, "logits were overwritten by the backward pass; run vc_eval_step first");
+    float* tmp = nullptr;
+    VC_CUDA(cudaMalloc((void**)&tmp, (size_t)N * T * V * sizeof(float)));
+    int st = logits_to_ref(0, logits, VP, tmp, N, T, V);
+    if (st == VC_OK && cudaMemcpy(logits_host, tmp, (size_t)N * T * V * sizeof(float), cudaMemcpyDeviceToHost) != cudaSuccess)
+      st = set_error(VC_E_CUDA, "logits copy failed");
+    cudaFree(tmp);
+    VC_TRY(st);
+  }
+  if (ce_host != nullptr) VC_CUDA(cudaMemcpy(ce_host, ce_row, (size_t)N * T * sizeof(float), cudaMemcpyDeviceToHost));
+  if (cfg.no_encoder) return VC_OK;
+  if (mu_host != nullptr) VC_CUDA(cudaMemcpy(mu_host, mu, (size_t)N * Z * sizeof(float), cudaMemcpyDeviceToHost));
+  if (std_host != nullptr) VC_CUDA(cudaMemcpy(std_host, sd, (size_t)N * Z * sizeof(float), cudaMemcpyDeviceToHost));
+  if (kl_host != nullptr) VC_CUDA(cudaMemcpy(kl_host, kl_row, (size_t)N * sizeof(float), cudaMemcpyDeviceToHost));
+  if (z_host != nullptr) {
+    float* tmp = nullptr;
+    const size_t n = (size_t)S * N * Z;
+    VC_CUDA(cudaMalloc((void**)&tmp, n * sizeof(float)));
+    int st = bf16_to_f32(0, z, tmp, 1, (int)n, n, n);
+    if (st == VC_OK && cudaMemcpy(z_host, tmp, n * sizeof(float), cudaMemcpyDeviceToHost) != cudaSuccess)
+      st = set_error(VC_E_CUDA, "z copy failed");
+    cudaFree(tmp);
+    VC_TRY(st);
+  }
+  return VC_OK;
+}
+
+}  // namespace vc

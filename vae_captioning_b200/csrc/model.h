@@ -1,0 +1,116 @@
+// The CVAE captioning model state behind vc_handle: parameter store (TF names), bf16 weight
+// shadows, time-major activation workspace, and the train / eval step orchestration.
+#pragma once
+#include <map>
+#include <string>
+#include <vector>
+#include "../../include/vaecap.h"
+#include "ops.h"
+
+namespace vc {
+
+struct ParamInfo {
+  std::string name;
+  int ndim;
+  int64_t shape[4];
+  int64_t count;
+  int64_t offset;  // element offset into the flat fp32 buffers
+  int region;      // 0: clipped Adam (non-CNN), 1: frozen (created but never updated), 2: CNN
+  bool trainable;
+};
+
+struct LstmNet {
+  int p_kernel = -1, p_bias = -1;
+  int E = 0, H = 0, pre = 0, steps = 0;
+  void* w_t_perm = nullptr;  // bf16 [4H interleaved, E+H]
+  void* w_nat = nullptr;     // bf16 [E+H, 4H]
+  void* X = nullptr;         // bf16 [steps, N, E]
+  void* Hs = nullptr;        // bf16 [steps+1, N, H]
+  float* Cs = nullptr;       // fp32 [steps+1, N, H]
+  void* G = nullptr;         // bf16 [steps, N, 4H] activated gates
+  void* dG = nullptr;        // bf16 [steps, N, 4H]
+  float* dX = nullptr;       // fp32 [steps, N, E]
+  float* dh_carry = nullptr;
+  float* dc_carry = nullptr;
+};
+
+struct StepInputs {
+  const float* feats;     // device fp32 [B, F] (or images when fine_tune)
+  const int32_t* cap_lbl; // device [N, T]
+  const int32_t* cap_in;
+  const int32_t* len;
+  const float* c_v;       // device fp32 [N, K] or null
+  int B, T;
+  int64_t global_step;
+  vc_rng rng;
+};
+
+class Model {
+ public:
+  vc_config cfg;
+  int device = 0;
+  int maxN = 0, maxT = 0;
+  std::vector<ParamInfo> params;
+  std::map<std::string, int> index;
+  int64_t n_adam = 0, n_dense = 0, n_frozen = 0, n_cnn = 0, n_total = 0;  // element counts (padded)
+  float *Pf = nullptr, *Gf = nullptr, *Mf = nullptr, *Vf = nullptr;  // flat fp32: params, grads, Adam m, v
+  float* g_tail = nullptr;  // 4 floats after the Adam region of G: [|enc slices|^2, |dec slices|^2, |dense|^2, -]
+  int64_t adam_t = 0;       // TF global_step of the optimiser (1-based after the first update)
+  bool shadows_dirty = true;
+  bool have_forward = false, logits_intact = false;
+  int lastN = 0, lastT = 0;
+  float last_ann = 1.f;
+
+  // --- shadows (bf16 unless noted)
+  void *imf_wt = nullptr, *cv_wt = nullptr, *heads_wt = nullptr, *heads_nat = nullptr, *z_wt = nullptr, *z_nat = nullptr,
+       *wo_t = nullptr, *wo_nat = nullptr, *enc_emb_h = nullptr, *dec_emb_h = nullptr;
+  float* heads_bias = nullptr;  // fp32 [2*ZP]
+  int ZP = 0, VP = 0, KP = 0, heads_cols = 0;
+
+  LstmNet enc, dec;
+
+  // --- workspace
+  void *feats_h = nullptr, *cv_h = nullptr, *Out = nullptr, *logits = nullptr, *z = nullptr, *dheads = nullptr,
+       *dzdec_h = nullptr, *dimf_h = nullptr, *dcv_h = nullptr;
+  float *imf_f = nullptr, *cv_f = nullptr, *heads_f = nullptr, *mu = nullptr, *sd = nullptr, *kl_row = nullptr,
+        *dkl_dmu = nullptr, *dkl_dsd = nullptr, *zdec_f = nullptr, *dOut = nullptr, *dz = nullptr, *ce_row = nullptr,
+        *scal = nullptr, *tmp_bias = nullptr, *cm = nullptr;
+  // staging for host-pointer entry points
+  float *st_feats = nullptr, *st_cv = nullptr;
+  int32_t *st_lbl = nullptr, *st_in = nullptr, *st_len = nullptr;
+  float* host_scal = nullptr;  // pinned
+
+  std::vector<void*> allocs;
+
+  ~Model();
+  int init(const vc_config& c, int dev);
+  int param_index(const char* name) const;
+  int param_set(const char* name, const float* src);
+  int param_get(const char* name, float* dst);
+  int grad_get(const char* name, float* dst);
+
+  int refresh_shadows(cudaStream_t s);
+  int forward(const StepInputs& in, bool write_grad, cudaStream_t s);
+  int backward(const StepInputs& in, cudaStream_t s);
+  int apply(float grad_scale, cudaStream_t s);
+  int fetch(vc_step_out* out, cudaStream_t s);
+  int stage_inputs(const float* feats, const int32_t* lbl, const int32_t* inp, const int32_t* len, const float* cv,
+                   int B, int T, StepInputs* out, cudaStream_t s);
+  int forward_debug(float* logits_host, float* mu_host, float* std_host, float* z_host, float* kl_host, float* ce_host);
+
+ private:
+  template <class T>
+  int dalloc(T** p, size_t count, bool zero = true);
+  int add_param(const std::string& name, std::vector<int64_t> shape, int region);
+  int lstm_forward(LstmNet& L, int N, int T, const int32_t* len, void* out, const float* out_keep, cudaStream_t s);
+  int lstm_backward(LstmNet& L, int N, int T, const int32_t* len, const float* d_out, const float* out_keep,
+                    cudaStream_t s);
+  float* gp(int pi) { return Gf + params[pi].offset; }
+  float* pp(int pi) { return Pf + params[pi].offset; }
+  int pidx(const std::string& n) const {
+    auto it = index.find(n);
+    return it == index.end() ? -1 : it->second;
+  }
+};
+
+}  // namespace vc

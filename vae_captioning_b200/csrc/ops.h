@@ -8,4 +8,70 @@ namespace vc {
 int gemm_store(cudaStream_t stream, const Operand& A, const Operand* A2, long long a2_at, const Operand& B, int M,
                int N, int K, const EpiStore& epi, int bn, int splits);
 
+// lstm.cu ----------------------------------------------------------------------------------
+struct LstmFwdArgs {
+  const void* x;         // bf16 [N, E] input of this step
+  const void* h_prev;    // bf16 [N, H]
+  const float* c_prev;   // fp32 [N, H]
+  void* h_out;           // bf16 [N, H]
+  float* c_out;          // fp32 [N, H]
+  void* gates;           // bf16 [N, 4H] (nullable)
+  void* out;             // bf16 [N, H] emitted output (nullable)
+  const void* w_t_perm;  // bf16 [4H (gate-interleaved), E+H]
+  const float* bias;     // fp32 [4H]
+  const int* lengths;    // nullable
+  const float* out_keep; // nullable
+  long long out_keep_ld;
+  float inv_keep;
+  int t, N, E, H;
+};
+int lstm_fwd_step(cudaStream_t stream, const LstmFwdArgs& a);
+
+struct LstmBwdArgs {
+  const void* d_gates_next;  // bf16 [N, 4H] gate gradients of step t+1 (nullptr for the last step)
+  const void* w_nat;         // bf16 [E+H, 4H] natural-layout weight shadow
+  const void* gates;         // bf16 [N, 4H] activated gates of step t
+  const float* c_prev;
+  const float* c_cur;
+  const float* d_out;        // nullable fp32 [N, H]
+  const float* out_keep;     // nullable
+  long long out_keep_ld;
+  float inv_keep;
+  float* dh_carry;
+  float* dc_carry;
+  void* d_gates;             // bf16 [N, 4H] out
+  const int* lengths;        // nullable
+  int t, N, E, H;
+};
+int lstm_bwd_step(cudaStream_t stream, const LstmBwdArgs& a);
+
+// elementwise.cu ---------------------------------------------------------------------------
+int cast_f32_bf16(cudaStream_t s, const float* src, void* dst, long long rows, int cols, long long ld_src,
+                  long long ld_dst);
+int bf16_to_f32(cudaStream_t s, const void* src, float* dst, long long rows, int cols, long long ld_src, long long ld_dst);
+int transpose_cast(cudaStream_t s, const float* src, void* dst, int R, int C, long long ld_src, long long ld_dst,
+                   int gate_h, int upt);
+int tile_cast(cudaStream_t s, const float* src, void* d0, void* d1, int B, int C, int E);
+int tile_reduce(cudaStream_t s, const float* a, const float* b2, float* dst_f, void* dst_h, int B, int C, int E);
+int embed_gather(cudaStream_t s, const void* table, const int* tok, void* X, const float* keep_mask, float inv_keep,
+                 int N, int T, int E, int V);
+int embed_scatter(cudaStream_t s, const float* dX, const int* tok, float* gtable, const float* keep_mask, float inv_keep,
+                  float* normsq, int N, int T, int E, int V);
+int heads_to_musd(cudaStream_t s, const float* heads, long long ld, int zp, float* mu, float* sd, int N, int Z);
+int kl_rows(cudaStream_t s, const float* mu, const float* sd, const float* cm, int prior, float* kl_row, float* dkl_dmu,
+            float* dkl_dsd, float* kl_sum, int N, int Z);
+int sample_z(cudaStream_t s, const float* mu, const float* sd, const float* eps, unsigned long long seed,
+             unsigned long long offset, void* z, float* z_f32, int S, long long NZ);
+int dz_reduce(cudaStream_t s, const float* dz, const float* eps, unsigned long long seed, unsigned long long offset,
+              const float* sd, const float* dkl_dmu, const float* dkl_dsd, float kl_scale, void* dheads, long long ld,
+              int zp, float* dmu_out, float* dsd_out, int S, int N, int Z);
+int ce_rows(cudaStream_t s, void* logits, long long ld, const int* lbl, int N, int T, int V, float* sums, float* ce_out,
+            const float* count, float loss_scale, int write_grad);
+int count_mask(cudaStream_t s, const int* lbl, long long n, float* count);
+int colsum_bf16(cudaStream_t s, const void* x, long long rows, int cols, long long ld, float* out);
+int sumsq(cudaStream_t s, const float* g, long long n, float* out);
+int adam_step(cudaStream_t s, float* p, const float* g, float* m, float* v, long long n, const float* normsq_parts,
+              int n_parts, float clip, float gscale, float lr_t, float b1, float b2, float eps, float* norm_out);
+int logits_to_ref(cudaStream_t s, const void* src, long long ld, float* dst, int N, int T, int V);
+
 }  // namespace vc
