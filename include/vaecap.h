@@ -67,6 +67,7 @@ typedef struct vc_rng {
   const float* emb_keep_dev;      /* [N, T, E]   0/1 keep mask of tf.nn.dropout, decoder.py:85-87 */
   const float* out_keep_dev;      /* [N, T, H]   0/1 keep mask of DropoutWrapper, rnn_model.py:45-46 */
   const int32_t* gmm_cluster_dev; /* [N]         tf.multinomial pick, encoder.py:72 */
+  const float* cnn_keep_dev;      /* [2, B, 4096] 0/1 keep masks of the fc1 / fc2 dropout, image_embeddings.py:225-237 */
 } vc_rng;
 
 /* Fetches of main.py:241-244. */

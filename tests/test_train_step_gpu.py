@@ -1,0 +1,167 @@
+"""ELBO train step on the GPU (through the C ABI) vs the CPU oracle on the same seeded inputs.
+
+Tolerances (stated): the CUDA path computes in bf16 operands / fp32 accumulate.
+ * against the oracle in bf16-emulation mode (rounds where the CUDA path rounds): logits within
+   1.5e-2 * max|logit| (a bf16 ulp is 0.8 %), mu/std 5e-3 rel, rec_loss 2e-3 rel, KL 5e-3 rel;
+ * against the exact fp64 oracle: logits 2e-2 * max(1, max|logit|), rec_loss 5e-3 rel, KL 1e-2 rel;
+ * gradients (bf16 dlogits / gate gradients): 4e-2 of the tensor's max-abs, global norm 2e-2 rel.
+"""
+import numpy as np
+import pytest
+import torch
+
+from helpers import O, SMALL, TINY, engine_for, feed_of, make_case, rel_err, rng_for
+
+pytestmark = pytest.mark.gpu
+
+
+def run_forward(sizes, B, T, ragged, **kw):
+    cfg, params, batch = make_case(sizes, B, T, seed=3, ragged=ragged, **kw)
+    eng = engine_for(cfg, params, B, T)
+    N = B * cfg.num_captions
+    out = eng.eval_step(rng=rng_for(batch), **feed_of(batch))
+    taps = eng.debug_taps(N, T, z=True)
+    with torch.no_grad():
+        ref_e = O.forward(params, cfg, batch, emulate=True)
+        ref_x = O.forward(params, cfg, batch, emulate=False)
+    eng.close()
+    ref_x["n_tokens"] = float((batch["cap_lbl"] != 0).sum())
+    return cfg, out, taps, ref_e, ref_x
+
+
+@pytest.mark.parametrize("sizes,B,T,ragged", [(TINY, 2, 5, False), (TINY, 3, 6, True), (SMALL, 4, 7, True),
+                                              (SMALL, 30, 9, False)])
+def test_forward_normal_prior(sizes, B, T, ragged):
+    cfg, out, taps, ref_e, ref_x = run_forward(sizes, B, T, ragged)
+    lg = ref_e["logits"].numpy()
+    assert rel_err(taps["logits"], lg) <= 1.5e-2
+    assert rel_err(taps["mu"], ref_e["mu"].numpy()) <= 5e-3
+    assert rel_err(taps["std"], ref_e["std"].numpy()) <= 5e-3
+    assert abs(out["rec_loss"] - float(ref_e["rec_loss"])) <= 2e-3 * abs(float(ref_e["rec_loss"]))
+    assert abs(out["kld"] - float(ref_e["kld"])) <= 5e-3 * abs(float(ref_e["kld"])) + 1e-6
+    # exact fp64 oracle, stated bf16 tolerance
+    lx = ref_x["logits"].numpy()
+    assert np.max(np.abs(taps["logits"] - lx)) <= 2e-2 * max(1.0, np.max(np.abs(lx)))
+    assert abs(out["rec_loss"] - float(ref_x["rec_loss"])) <= 5e-3 * abs(float(ref_x["rec_loss"]))
+    assert abs(out["kld"] - float(ref_x["kld"])) <= 1e-2 * abs(float(ref_x["kld"])) + 1e-6
+    assert abs(out["lower_bound"] - float(ref_x["lower_bound"])) <= 5e-3 * abs(float(ref_x["lower_bound"]))
+    assert out["n_tokens"] == ref_x["n_tokens"]
+
+
+def test_padding_semantics():
+    """dynamic_rnn(sequence_length): logits past the caption end equal the logits bias exactly."""
+    cfg, params, batch = make_case(TINY, 3, 6, seed=5, ragged=True)
+    eng = engine_for(cfg, params, 3, 6)
+    N, T = 9, 6
+    eng.eval_step(rng=rng_for(batch), **feed_of(batch))
+    lg = eng.debug_taps(N, T)["logits"].reshape(N, T, -1)
+    b_o = params["decoder/rnn_logits/bias"].to(torch.bfloat16).float().numpy()
+    ln = batch["lengths"].numpy()
+    for n in range(N):
+        for t in range(int(ln[n]), T):
+            np.testing.assert_array_equal(lg[n, t], b_o)
+    eng.close()
+
+
+def test_no_encoder_and_dropout_masks():
+    for kw in (dict(no_encoder=True), dict(dec_keep_rate=0.7, dec_lstm_drop=0.8), dict(use_c_v=True)):
+        cfg, out, taps, ref_e, ref_x = run_forward(SMALL, 3, 6, True, **kw)
+        assert rel_err(taps["logits"], ref_e["logits"].numpy()) <= 1.5e-2, kw
+        assert abs(out["rec_loss"] - float(ref_x["rec_loss"])) <= 5e-3 * abs(float(ref_x["rec_loss"])), kw
+
+
+def grads_case(sizes, B, T, ragged, **kw):
+    cfg, params, batch = make_case(sizes, B, T, seed=11, ragged=ragged, **kw)
+    eng = engine_for(cfg, params, B, T)
+    f = feed_of(batch)
+    dev = lambda a, dt: torch.tensor(np.ascontiguousarray(a)).to(dt).cuda()
+    eng.forward_backward_device(dev(f["image_f_inputs"], torch.float32), dev(f["ann_inputs_enc"], torch.int32),
+                                dev(f["ann_inputs_dec"], torch.int32), dev(f["ann_lengths"], torch.int32), 0,
+                                c_i=dev(f["c_i"], torch.float32) if f["c_i"] is not None else None, rng=rng_for(batch))
+    torch.cuda.synchronize()
+    res, grads, gnorm = O.compute_grads(params, cfg, batch, emulate=False)
+    return cfg, eng, grads, gnorm
+
+
+@pytest.mark.parametrize("sizes,B,T,ragged,kw", [
+    (TINY, 2, 5, False, {}), (SMALL, 4, 7, True, {}), (SMALL, 3, 6, True, dict(use_c_v=True)),
+    (SMALL, 3, 5, True, dict(no_encoder=True)), (SMALL, 3, 5, True, dict(dec_keep_rate=0.7, dec_lstm_drop=0.8)),
+    (SMALL, 4, 6, False, dict(ann_param=3.0))])
+def test_gradients(sizes, B, T, ragged, kw):
+    cfg, eng, grads, gnorm = grads_case(sizes, B, T, ragged, **kw)
+    worst = {}
+    for name, g in grads.items():
+        if g is None:
+            continue
+        got = eng.get_gradient(name)
+        ref = g.numpy()
+        scale = max(np.max(np.abs(ref)), 1e-12)
+        worst[name] = float(np.max(np.abs(got - ref)) / scale)
+    out = eng.apply_gradients(1.0)
+    eng.close()
+    bad = {k: v for k, v in worst.items() if v > 4e-2}
+    assert not bad, bad
+    assert abs(out["global_norm"] - gnorm) <= 2e-2 * gnorm
+
+
+def test_adam_three_steps():
+    """Post-update parameters after 1 and 3 steps (TF-form Adam, beta1 = 0.8, clip 5.0; Q4/Q5)."""
+    cfg, params, batch = make_case(SMALL, 4, 6, seed=21, ragged=True)
+    eng = engine_for(cfg, params, 4, 6)
+    p_ref = {k: v.clone() for k, v in params.items()}
+    opt = {"t": 0, "m": {}, "v": {}}
+    for step in range(3):
+        out = eng.train_step(anneal=step, rng=rng_for(batch), **feed_of(batch))
+        b2 = dict(batch)
+        b2["global_step"] = step
+        ref = O.train_step(p_ref, opt, cfg, b2)
+        assert abs(out["rec_loss"] - ref["rec_loss"]) <= 5e-3 * abs(ref["rec_loss"]), step
+        assert abs(out["kld"] - float(ref["kld"])) <= 2e-2 * abs(float(ref["kld"])) + 1e-6, step
+        assert abs(out["global_norm"] - ref["global_norm"]) <= 3e-2 * ref["global_norm"], step
+    # Adam's first steps move every weight by ~lr * sign(g): compare the *update* direction and size
+    lr = cfg.learning_rate
+    for name in ("decoder/rnn_logits/kernel", "decoder/net/multi_rnn_cell/cell_0/lstm_cell/kernel", "imf_emb/kernel",
+                 "encoder/dense/kernel", "decoder/net/z_rnn/kernel", "encoder/enc_embeddings"):
+        got = eng.get_variable(name).astype(np.float64) - params[name].numpy()
+        want = p_ref[name].numpy() - params[name].numpy()
+        # updates are bounded by ~3 * lr each; gradient noise from bf16 perturbs small-|g| entries, so compare in L2
+        num = np.linalg.norm(got - want)
+        den = np.linalg.norm(want)
+        assert num <= 0.15 * den, (name, num, den)
+        assert np.max(np.abs(got)) <= 3.5 * 3 * lr
+    eng.close()
+
+
+def test_clip_identity_and_adam_first_step_kat():
+    """Known-answer: with |g| <= clip the clip is the identity, and Adam's first step is
+    lr_t * (1-b1) g / (sqrt((1-b2) g^2) + eps) with lr_t = lr sqrt(1-b2)/(1-b1)  ~=  lr * sign(g)."""
+    cfg, params, batch = make_case(TINY, 2, 5, seed=2)
+    eng = engine_for(cfg, params, 2, 5)
+    before = eng.get_variable("decoder/rnn_logits/bias").astype(np.float64)
+    out = eng.train_step(anneal=0, rng=rng_for(batch), **feed_of(batch))
+    assert out["global_norm"] < cfg.lstm_clip_by_norm
+    g = eng.get_gradient("decoder/rnn_logits/bias").astype(np.float64)
+    after = eng.get_variable("decoder/rnn_logits/bias").astype(np.float64)
+    b1, b2, eps, lr = 0.8, 0.999, 1e-8, cfg.learning_rate
+    lr_t = lr * np.sqrt(1 - b2) / (1 - b1)
+    want = before - lr_t * (1 - b1) * g / (np.sqrt((1 - b2) * g * g) + eps)
+    np.testing.assert_allclose(after, want, rtol=0, atol=2e-3 * lr)
+    eng.close()
+
+
+def test_error_behaviour():
+    cfg, params, batch = make_case(TINY, 2, 5, seed=2)
+    eng = engine_for(cfg, params, 2, 5)
+    f = feed_of(batch)
+    with pytest.raises(ValueError):
+        eng.set_variable("no/such/variable", np.zeros(3))
+    with pytest.raises(ValueError):
+        eng.set_variable("imf_emb/bias", np.zeros(3))
+    bad = dict(f)
+    bad["ann_inputs_enc"] = f["ann_inputs_enc"][:, :3]
+    with pytest.raises(ValueError):
+        eng.train_step(anneal=0, rng=rng_for(batch), **bad)
+    big = make_case(TINY, 4, 5, seed=2)[2]
+    with pytest.raises(ValueError):  # exceeds the handle's max_batch
+        eng.train_step(anneal=0, rng=rng_for(big), **feed_of(big))
+    eng.close()
