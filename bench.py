@@ -1,0 +1,378 @@
+#!/usr/bin/env python
+"""Benchmark of the ELBO train step (BASELINE.json metric: captions/sec).
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+  python bench.py --impl reference ...                      # CPU restatement of the reference graph
+
+Workload (config.workload): BASELINE.json configs[1] -- Normal-prior CVAE, bf16 operands, on-device
+VGG16 forward, batch = 256 images x 5 captions = 1280 captions per step per GPU, T = 20, V = 11313.
+Under torchrun every rank runs the same per-GPU batch (weak scaling) and the gradients are summed
+with one all-reduce; the printed value is the whole-job captions/s.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (images per step per GPU, on-device VGG forward, prior, c_v)
+    "cfg2_vgg_normal_b256": dict(B=256, vgg=True, prior="Normal", c_v=False),
+    "cfg1_feats_normal_b32": dict(B=32, vgg=False, prior="Normal", c_v=False),
+    "feats_normal_b256": dict(B=256, vgg=False, prior="Normal", c_v=False),
+    "cfg3_feats_gmm_cv_b128": dict(B=128, vgg=False, prior="GMM", c_v=True),
+}
+DEFAULT_WORKLOAD = "cfg2_vgg_normal_b256"
+C, T, V = 5, 20, 11313
+
+
+def params_for(w):
+    from vae_captioning_b200.parameters import Parameters
+    p = Parameters()
+    p.prior = w["prior"]
+    p.use_c_v = w["c_v"]
+    p.batch_size = w["B"]
+    p.vocab_size = V
+    return p
+
+
+# ------------------------------------------------------------------------------------------------
+# algorithmic work per kernel family per step: FLOPs for tensor-bound, bytes for HBM-bound
+VGG = [(224, 3, 64), (224, 64, 64), (112, 64, 128), (112, 128, 128), (56, 128, 256), (56, 256, 256), (56, 256, 256),
+       (28, 256, 512), (28, 512, 512), (28, 512, 512), (14, 512, 512), (14, 512, 512), (14, 512, 512)]
+
+
+def family_work(p, B, has_enc=True):
+    N, E, He, Hd, Z, S, F = B * C, p.embed_size, p.encoder_hidden, p.decoder_hidden, p.latent_size, p.gen_z_samples, 4096
+    cv = 1 if p.use_c_v else 0
+    enc_steps, dec_steps = T + 1 + cv, T + 2 + cv
+    n_adam = (F * E + E + (E + He) * 4 * He + 4 * He + 2 * (He * Z + Z) + (E + Hd) * 4 * Hd + 4 * Hd + Z * S * E + E +
+              Hd * V + V + 2 * V * E)
+    w = {
+        "conv": ("tensor", sum(2.0 * hw * hw * 9 * ci * co for hw, ci, co in VGG) * B),
+        "fc": ("tensor", 2.0 * B * (25088 * 4096 + 4096 * 4096)),
+        "lstm_fwd_step": ("tensor", 2.0 * N * ((E + He) * 4 * He * enc_steps + (E + Hd) * 4 * Hd * dec_steps)),
+        "lstm_bwd_step": ("tensor", 2.0 * N * (He * 4 * He * (enc_steps - 1) + Hd * 4 * Hd * (dec_steps - 1))),
+        "lstm_wgrad": ("tensor", 2.0 * N * ((E + He) * 4 * He * enc_steps + (E + Hd) * 4 * Hd * dec_steps)),
+        "lstm_dx": ("tensor", 2.0 * N * (E * 4 * He * enc_steps + E * 4 * Hd * dec_steps)),
+        "logits_fwd": ("tensor", 2.0 * N * T * Hd * V),
+        "logits_dgrad": ("tensor", 2.0 * N * T * Hd * V),
+        "logits_wgrad": ("tensor", 2.0 * N * T * Hd * V),
+        "z_rnn": ("tensor", 2.0 * N * S * Z * E),
+        "z_rnn_dgrad": ("tensor", 2.0 * N * S * Z * E),
+        "z_rnn_wgrad": ("tensor", 2.0 * N * S * Z * E),
+        "imf_emb": ("tensor", 2.0 * B * F * E),
+        "imf_emb_bwd": ("tensor", 2.0 * B * F * E),
+        # HBM-bound stages: bytes that must move
+        "ce": ("hbm", 2.0 * N * T * V * 2),            # bf16 logits read once, dlogits written once
+        "adam": ("hbm", 28.0 * n_adam),                 # read p,g,m,v; write p,m,v (fp32)
+        "sumsq": ("hbm", 4.0 * n_adam),
+        "sample_z": ("hbm", S * N * Z * 2.0 + 2 * N * Z * 4.0),
+        "dz_reduce": ("hbm", S * N * Z * 4.0),
+    }
+    return w
+
+
+def total_flops(p, B, vgg):
+    w = family_work(p, B)
+    tot = sum(v for k, (kind, v) in w.items() if kind == "tensor" and k not in ("conv", "fc"))
+    tot += 3 * 2.0 * B * C * p.encoder_hidden * 2 * p.latent_size  # heads fwd+bwd
+    if vgg:
+        tot += w["conv"][1] + w["fc"][1]
+    return tot
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self._stop_evt = threading.Event()
+
+    def run(self):
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [x.strip() for x in out.strip().split(",")]
+                if len(parts) >= 6:
+                    self.samples.append(parts)
+            except Exception:
+                pass
+            self._stop_evt.wait(0.1)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=6)
+        sm = [float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
+        reasons = set()
+        for s in self.samples:
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[2:6]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(self.samples)}
+
+
+def cpu_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+# ------------------------------------------------------------------------------------------------
+def run_reference(args, w, name):
+    """The reference's CPU path: the oracle (torch-CPU fp32 restatement; TF1/zhusuan cannot be installed)
+    on a bounded sample of the workload, all host threads."""
+    import torch
+    from oracle import cvae_oracle as O
+    cores = cpu_cores()
+    torch.set_num_threads(cores)
+    Bs = args.ref_batch
+    cfg = O.Config(prior=w["prior"], use_c_v=w["c_v"], vocab_size=V)
+    params = O.init_params(cfg, seed=1, with_cnn=w["vgg"], dtype=torch.float32)
+    batch = O.synthetic_batch(cfg, Bs, T, seed=0, dtype=torch.float32, with_images=w["vgg"])
+    opt = {"t": 0, "m": {}, "v": {}}
+
+    def step():
+        b = dict(batch)
+        if w["vgg"]:
+            with torch.no_grad():
+                b["feats"] = O.vgg16_fc2(params, batch["images"])
+        O.train_step(params, opt, cfg, b)
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = (time.perf_counter() - t0) / args.steps
+    val = Bs * C / dt
+    sample = "%d images x %d captions per step (full workload: %d images), fp32 torch-CPU restatement of the TF1 graph" % (
+        Bs, C, w["B"])
+    return {"metric": "captions/sec (ELBO train step)", "value": val, "unit": "captions/s", "impl": "reference",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+            "config": {"workload": name, "images_per_step": Bs, "captions_per_step": Bs * C, "seq_len": T, "vocab": V},
+            "cpu_baseline": {"value": val, "unit": "captions/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": "captions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument("--ref-batch", type=int, default=32, help="images per step of the bounded CPU sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-profile", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (used under ncu only)")
+    args = ap.parse_args()
+    w = WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        if rank == 0:
+            print(json.dumps(run_reference(args, w, args.workload)), flush=True)
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    from vae_captioning_b200 import lib as L
+    from vae_captioning_b200.engine import Engine
+    from vae_captioning_b200 import synthetic
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the hot path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    lib = L.load()
+    lib.vc_launch_count.restype = ctypes.c_ulonglong
+
+    p = params_for(w)
+    B = w["B"]
+    N = B * C
+    eng = Engine(p, vocab_size=V, max_batch=B, max_len=T, device=local_rank, with_cnn=w["vgg"])
+    eng.load_state(synthetic.init_weights(eng.variables(), seed=1))
+    feed = synthetic.make_batch(B, C, T, V, seed=rank, images=w["vgg"], cluster_vectors=w["c_v"] or w["prior"] != "Normal")
+
+    # pinned host buffers (e2e leg) and device-resident copies (value leg)
+    host = {k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory() for k, v in feed.items()}
+    dev = {k: v.cuda(non_blocking=True) for k, v in host.items()}
+    torch.cuda.synchronize()
+    grad_ptr, grad_n = eng.grad_buffer()
+    grad_t = None
+    if world > 1:
+        grad_t = L.alias_tensor(grad_ptr, grad_n, torch.float32, local_rank)
+
+    step_no = [0]
+
+    def step_device():
+        feats = dev["image_f_inputs"]
+        if w["vgg"]:
+            feats = eng.vgg_forward_device(feats)
+        if world == 1:
+            eng.train_step_device(feats, dev["ann_inputs_enc"], dev["ann_inputs_dec"], dev["ann_lengths"], step_no[0],
+                                  c_i=dev.get("c_i"), rng={"seed": 1234}, fetch=False)
+        else:
+            eng.forward_backward_device(feats, dev["ann_inputs_enc"], dev["ann_inputs_dec"], dev["ann_lengths"],
+                                        step_no[0], c_i=dev.get("c_i"), rng={"seed": 1234 + rank})
+            dist.all_reduce(grad_t)
+            eng.apply_gradients(1.0 / world, fetch=False)
+        step_no[0] += 1
+
+    def step_e2e():
+        # public API with HOST buffers: H2D of the step's inputs and D2H of the loss inside the timed region
+        if world == 1:
+            out = eng.train_step(host["image_f_inputs"].numpy(), host["ann_inputs_enc"].numpy(),
+                                 host["ann_inputs_dec"].numpy(), host["ann_lengths"].numpy(), step_no[0],
+                                 c_i=host["c_i"].numpy() if "c_i" in host else None, rng={"seed": 1234}, images=w["vgg"])
+        else:
+            d = {k: v.cuda(non_blocking=True) for k, v in host.items()}
+            feats = eng.vgg_forward_device(d["image_f_inputs"]) if w["vgg"] else d["image_f_inputs"]
+            eng.forward_backward_device(feats, d["ann_inputs_enc"], d["ann_inputs_dec"], d["ann_lengths"], step_no[0],
+                                        c_i=d.get("c_i"), rng={"seed": 1234 + rank})
+            dist.all_reduce(grad_t)
+            out = eng.apply_gradients(1.0 / world, fetch=True)
+        step_no[0] += 1
+        return out
+
+    def timed(fn, steps):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dist.barrier()
+            ms = float(t.item())
+        return ms
+
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    l0 = lib.vc_launch_count()
+    ms = timed(step_device, args.steps)
+    launches = int(lib.vc_launch_count() - l0)
+    clocks = sampler.stop() if sampler else None
+    value = world * N * args.steps / (ms / 1e3)
+
+    # e2e leg
+    last, ms_e2e, e2e_val = None, float("nan"), None
+    if not args.no_e2e:
+        for _ in range(2):
+            last = step_e2e()
+        ms_e2e = timed(step_e2e, args.steps)
+        e2e_val = world * N * args.steps / (ms_e2e / 1e3)
+    h2d = sum(v.numel() * v.element_size() for v in host.values())
+
+    # per-kernel-family timing with CUDA events on the launching stream (extra steps after the timed region)
+    roofline = None
+    families = {}
+    if rank == 0 and not args.no_profile:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        psteps = 3
+        lib.vc_profile_enable(1)
+        for _ in range(psteps):
+            step_device()
+        names = ctypes.create_string_buffer(8192)
+        msb = (ctypes.c_float * 256)()
+        cnt = (ctypes.c_int * 256)()
+        n = lib.vc_profile_collect(names, 8192, msb, cnt, 256)
+        lib.vc_profile_enable(0)
+        fam_names = names.value.decode().split(",") if n else []
+        work = family_work(p, B)
+        for i, fn in enumerate(fam_names):
+            families[fn] = {"ms_per_step": msb[i] / psteps, "launches_per_step": cnt[i] / psteps}
+            if fn in work:
+                kind, amount = work[fn]
+                rate = amount / (msb[i] / psteps / 1e3)
+                families[fn].update(bound=kind, achieved=rate / (1e12 if kind == "tensor" else 1e9))
+        if families:
+            top = max(families, key=lambda k: families[k]["ms_per_step"])
+            f = families[top]
+            if "bound" in f:
+                tensor = f["bound"] == "tensor"
+                peak = peaks.get("bf16_tflops_sustained" if tensor else "hbm_gbs")
+                src = "measured (MEASURED_PEAKS.json, %s)" % ("sustained bf16" if tensor else "copy")
+                if peak is None:
+                    peak, src = (1590.0 if tensor else 6650.0), "fallback"
+                traffic = None
+                try:
+                    traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(top)
+                except Exception:
+                    pass
+                roofline = {"kernel": top, "bound": f["bound"], "achieved": f["achieved"], "peak": peak,
+                            "unit": "TFLOP/s" if tensor else "GB/s", "frac": f["achieved"] / peak, "traffic": traffic,
+                            "peak_source": src, "ms_per_launch": f["ms_per_step"] / max(f["launches_per_step"], 1),
+                            "share_of_step": f["ms_per_step"] / sum(x["ms_per_step"] for x in families.values())}
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        ra = argparse.Namespace(**vars(args))
+        ra.steps, ra.warmup = 3, 1
+        r = run_reference(ra, w, args.workload)
+        cpu_baseline = r["cpu_baseline"]
+
+    if rank == 0:
+        peaks_tf = None
+        try:
+            peaks_tf = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("bf16_tflops_sustained")
+        except Exception:
+            pass
+        tf = total_flops(p, B, w["vgg"]) * world / (ms / args.steps / 1e3) / 1e12
+        line = {"metric": "captions/sec (ELBO train step)", "value": value, "unit": "captions/s", "n_gpus": world,
+                "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": args.workload, "images_per_step_per_gpu": B, "captions_per_step_per_gpu": N,
+                           "seq_len": T, "vocab": V, "prior": w["prior"], "on_device_vgg16_forward": w["vgg"],
+                           "parallelism": "dp%d" % world,
+                           "l2_policy": "per-step working set (>= 0.6 GB logits + 80 MB weights/optimizer state) exceeds the 126 MB L2"},
+                "e2e": {"value": e2e_val, "unit": "captions/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 64,
+                        "ms_per_step": ms_e2e / args.steps, "last_step": last},
+                "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
+                "step_tflops": tf, "step_tensor_frac": (tf / world / peaks_tf) if peaks_tf else None,
+                "families": families}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    eng.close()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

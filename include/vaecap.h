@@ -85,6 +85,14 @@ typedef struct vc_handle vc_handle;
 const char* vc_last_error(void);
 int vc_abi_version(void);
 
+/* Measurement hooks (no reference counterpart; the reference has no profiling):
+ * vc_launch_count: kernels this library has launched in this process so far.
+ * vc_profile_enable(1) starts bracketing every launch with CUDA events on its stream; vc_profile_collect
+ * synchronises and returns per-kernel-family totals: comma-joined names, milliseconds and launch counts. */
+unsigned long long vc_launch_count(void);
+int vc_profile_enable(int on);
+int vc_profile_collect(char* names, int names_cap, float* ms, int* counts, int cap);
+
 /* Graph construction, main.py:43-191 (+ tf.global_variables_initializer, main.py:196). Parameters start at zero;
  * load them with vc_param_set. */
 int vc_create(const vc_config* cfg, int device, vc_handle** out);
@@ -105,6 +113,12 @@ int vc_grad_get(vc_handle* h, const char* name, float* dst_host); /* tf.gradient
 int vc_train_step(vc_handle* h, const float* feats_host, const int32_t* cap_lbl_host, const int32_t* cap_in_host,
                   const int32_t* len_host, const float* c_v_host, int B, int T, int64_t global_step, const vc_rng* rng,
                   vc_step_out* out, void* stream);
+/* Same step fed with raw images (fp32 [B,224,224,3] RGB 0..255, host): the VGG16 forward that
+ * Data.extract_features_from_dir runs offline (utils/data.py:86-130) happens on the device inside the call; the
+ * CNN is not trained (use fine_tune for that). Needs with_cnn. */
+int vc_train_step_images(vc_handle* h, const float* images_host, const int32_t* cap_lbl_host, const int32_t* cap_in_host,
+                         const int32_t* len_host, const float* c_v_host, int B, int T, int64_t global_step,
+                         const vc_rng* rng, vc_step_out* out, void* stream);
 /* Same, with inputs already resident in device memory. */
 int vc_train_step_dev(vc_handle* h, const float* feats_dev, const int32_t* cap_lbl_dev, const int32_t* cap_in_dev,
                       const int32_t* len_dev, const float* c_v_dev, int B, int T, int64_t global_step,
@@ -131,7 +145,10 @@ int vc_forward_debug(vc_handle* h, float* logits_host, float* mu_host, float* st
  * images fp32 [B,224,224,3] RGB 0..255 (host) -> fc2 fp32 [B,4096] (host). */
 int vc_vgg_forward(vc_handle* h, const float* images_host, float* fc2_host, int B, void* stream);
 int vc_vgg_forward_dev(vc_handle* h, const float* images_dev, float* fc2_dev, int B, void* stream);
-/* Debug tap: NHWC activation of a conv layer ("conv1_1".."conv5_3") of the last vc_vgg_forward as fp32. */
+/* Debug taps: vc_vgg_keep_activations(h, 1) makes later forwards materialise every conv output instead of fusing
+ * the 2x2 max-pools into the conv epilogues; vc_vgg_activation then returns the NHWC activation of a layer
+ * ("conv1_1".."conv5_3", post-ReLU; "pool1".."pool5") of the last forward as fp32. */
+int vc_vgg_keep_activations(vc_handle* h, int on);
 int vc_vgg_activation(vc_handle* h, const char* layer, float* dst_host);
 
 #ifdef __cplusplus

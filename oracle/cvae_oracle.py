@@ -444,7 +444,7 @@ def train_step(params, opt, cfg, batch, emulate=False, c_means=None):
             m = opt["m"].get(n, torch.zeros_like(params[n]))
             v = opt["v"].get(n, torch.zeros_like(params[n]))
             params[n], opt["m"][n], opt["v"][n] = adam_update(params[n], g, m, v, cfg.cnn_lr, opt["t"])
-    return {"kld": res["kld"].detach(), "rec_loss": float(res["rec_loss"]), "lower_bound": res["lower_bound"].detach(),
+    return {"kld": res["kld"].detach(), "rec_loss": float(res["rec_loss"].detach()), "lower_bound": res["lower_bound"].detach(),
             "annealing": res["annealing"], "global_norm": gnorm, "grads": grads, "res": res}
 
 

@@ -22,6 +22,14 @@ extern "C" {
 
 const char* vc_last_error(void) { return last_error().c_str(); }
 int vc_abi_version(void) { return 1; }
+unsigned long long vc_launch_count(void) { return launch_count(); }
+int vc_profile_enable(int on) {
+  prof_enable(on != 0);
+  return VC_OK;
+}
+int vc_profile_collect(char* names, int names_cap, float* ms, int* counts, int cap) {
+  return prof_collect(names, names_cap, ms, counts, cap);
+}
 
 int vc_create(const vc_config* cfg, int device, vc_handle** out) {
   VC_GUARD_BEGIN
@@ -142,6 +150,31 @@ int vc_train_step(vc_handle* h, const float* feats, const int32_t* lbl, const in
   VC_GUARD_END
 }
 
+int vc_train_step_images(vc_handle* h, const float* images, const int32_t* lbl, const int32_t* inp, const int32_t* len,
+                         const float* cv, int B, int T, int64_t gs, const vc_rng* rng, vc_step_out* out, void* stream) {
+  VC_GUARD_BEGIN
+  if (!h || !images || !lbl || !inp || !len) return set_error(VC_E_ARG, "vc_train_step_images: null argument");
+  Model& m = h->m;
+  cudaSetDevice(m.device);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (m.vgg.empty()) return set_error(VC_E_STATE, "this handle was created without the CNN (with_cnn = 0)");
+  if (m.cfg.fine_tune) return vc_train_step(h, images, lbl, inp, len, cv, B, T, gs, rng, out, stream);
+  if (B < 1 || B > m.cfg.max_batch) return set_error(VC_E_SHAPE, "batch %d exceeds max_batch %d", B, m.cfg.max_batch);
+  VC_CUDA(cudaMemcpyAsync(m.st_images, images, (size_t)B * 224 * 224 * 3 * sizeof(float), cudaMemcpyHostToDevice, s));
+  VC_TRY(m.vgg_forward(m.st_images, nullptr, B, false, nullptr, s));
+  StepInputs in{};
+  // captions / lengths / c_v are staged as usual; the features come from the on-device forward
+  VC_TRY(m.stage_inputs(nullptr, lbl, inp, len, cv, B, T, &in, s));
+  in.feats = m.fc2_f;
+  in.global_step = gs;
+  if (rng) in.rng = *rng;
+  VC_TRY(m.forward(in, true, s));
+  VC_TRY(m.backward(in, s));
+  VC_TRY(m.apply(1.f, s));
+  return m.fetch(out, s);
+  VC_GUARD_END
+}
+
 int vc_eval_step(vc_handle* h, const float* feats, const int32_t* lbl, const int32_t* inp, const int32_t* len,
                  const float* cv, int B, int T, const vc_rng* rng, vc_step_out* out, void* stream) {
   VC_GUARD_BEGIN
@@ -162,6 +195,44 @@ int vc_forward_debug(vc_handle* h, float* logits, float* mu, float* sd, float* z
   if (!h) return set_error(VC_E_ARG, "null handle");
   cudaSetDevice(h->m.device);
   return h->m.forward_debug(logits, mu, sd, z, kl_rows, ce_rows);
+  VC_GUARD_END
+}
+
+int vc_vgg_keep_activations(vc_handle* h, int on) {
+  if (!h) return set_error(VC_E_ARG, "null handle");
+  h->m.vgg_keep = on != 0;
+  return VC_OK;
+}
+
+int vc_vgg_forward_dev(vc_handle* h, const float* images, float* fc2, int B, void* stream) {
+  VC_GUARD_BEGIN
+  if (!h || !images) return set_error(VC_E_ARG, "vc_vgg_forward_dev: null argument");
+  cudaSetDevice(h->m.device);
+  return h->m.vgg_forward(images, fc2, B, h->m.vgg_keep, nullptr, (cudaStream_t)stream);
+  VC_GUARD_END
+}
+
+int vc_vgg_forward(vc_handle* h, const float* images_host, float* fc2_host, int B, void* stream) {
+  VC_GUARD_BEGIN
+  if (!h || !images_host || !fc2_host) return set_error(VC_E_ARG, "vc_vgg_forward: null argument");
+  Model& m = h->m;
+  cudaSetDevice(m.device);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (m.vgg.empty()) return set_error(VC_E_STATE, "this handle was created without the CNN (with_cnn = 0)");
+  if (B < 1 || B > m.cfg.max_batch) return set_error(VC_E_SHAPE, "vc_vgg_forward: batch %d exceeds max_batch %d", B, m.cfg.max_batch);
+  VC_CUDA(cudaMemcpyAsync(m.st_images, images_host, (size_t)B * 224 * 224 * 3 * sizeof(float), cudaMemcpyHostToDevice, s));
+  VC_TRY(m.vgg_forward(m.st_images, nullptr, B, m.vgg_keep, nullptr, s));
+  VC_CUDA(cudaMemcpyAsync(fc2_host, m.fc2_f, (size_t)B * 4096 * sizeof(float), cudaMemcpyDeviceToHost, s));
+  VC_CUDA(cudaStreamSynchronize(s));
+  return VC_OK;
+  VC_GUARD_END
+}
+
+int vc_vgg_activation(vc_handle* h, const char* layer, float* dst_host) {
+  VC_GUARD_BEGIN
+  if (!h || !layer || !dst_host) return set_error(VC_E_ARG, "vc_vgg_activation: null argument");
+  cudaSetDevice(h->m.device);
+  return h->m.vgg_activation(layer, dst_host);
   VC_GUARD_END
 }
 

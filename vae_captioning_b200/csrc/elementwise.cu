@@ -27,7 +27,10 @@ __global__ void k_cast_f32_bf16(const float* __restrict__ src, __nv_bfloat16* __
 }
 int cast_f32_bf16(cudaStream_t s, const float* src, void* dst, long long rows, int cols, long long ld_src,
                   long long ld_dst) {
-  k_cast_f32_bf16<<<grid_for(rows * cols, 256, 4), 256, 0, s>>>(src, (__nv_bfloat16*)dst, rows, cols, ld_src, ld_dst);
+  {
+    ProfScope ps(s, "cast_f32_bf16");
+    k_cast_f32_bf16<<<grid_for(rows * cols, 256, 4), 256, 0, s>>>(src, (__nv_bfloat16*)dst, rows, cols, ld_src, ld_dst);
+  }
   VC_CUDA(cudaGetLastError());
   return VC_OK;
 }
@@ -58,7 +61,10 @@ __global__ void k_transpose_cast(const float* __restrict__ src, __nv_bfloat16* _
 int transpose_cast(cudaStream_t s, const float* src, void* dst, int R, int C, long long ld_src, long long ld_dst,
                    int gate_h, int upt) {
   dim3 grid((C + 31) / 32, (R + 31) / 32), block(32, 8);
-  k_transpose_cast<<<grid, block, 0, s>>>(src, (__nv_bfloat16*)dst, R, C, ld_src, ld_dst, gate_h, upt);
+  {
+    ProfScope ps(s, "transpose_cast");
+    k_transpose_cast<<<grid, block, 0, s>>>(src, (__nv_bfloat16*)dst, R, C, ld_src, ld_dst, gate_h, upt);
+  }
   VC_CUDA(cudaGetLastError());
   return VC_OK;
 }
@@ -77,7 +83,10 @@ __global__ void k_tile_cast(const float* __restrict__ src, __nv_bfloat16* __rest
   }
 }
 int tile_cast(cudaStream_t s, const float* src, void* d0, void* d1, int B, int C, int E) {
-  k_tile_cast<<<grid_for((long long)B * C * E, 256, 2), 256, 0, s>>>(src, (__nv_bfloat16*)d0, (__nv_bfloat16*)d1, B, C, E);
+  {
+    ProfScope ps(s, "tile_cast");
+    k_tile_cast<<<grid_for((long long)B * C * E, 256, 2), 256, 0, s>>>(src, (__nv_bfloat16*)d0, (__nv_bfloat16*)d1, B, C, E);
+  }
   VC_CUDA(cudaGetLastError());
   return VC_OK;
 }
@@ -100,7 +109,10 @@ __global__ void k_tile_reduce(const float* __restrict__ a, const float* __restri
   }
 }
 int tile_reduce(cudaStream_t s, const float* a, const float* b2, float* dst_f, void* dst_h, int B, int C, int E) {
-  k_tile_reduce<<<grid_for((long long)B * E, 256), 256, 0, s>>>(a, b2, dst_f, (__nv_bfloat16*)dst_h, B, C, E);
+  {
+    ProfScope ps(s, "tile_reduce");
+    k_tile_reduce<<<grid_for((long long)B * E, 256), 256, 0, s>>>(a, b2, dst_f, (__nv_bfloat16*)dst_h, B, C, E);
+  }
   VC_CUDA(cudaGetLastError());
   return VC_OK;
 }
@@ -130,8 +142,11 @@ __global__ void k_embed_gather(const __nv_bfloat16* __restrict__ table, const in
 int embed_gather(cudaStream_t s, const void* table, const int* tok, void* X, const float* keep_mask, float inv_keep,
                  int N, int T, int E, int V) {
   if (E % 8 != 0) return set_error(VC_E_SHAPE, "embed_size must be a multiple of 8");
-  k_embed_gather<<<grid_for((long long)N * T, 8), 256, 0, s>>>((const __nv_bfloat16*)table, tok, (__nv_bfloat16*)X,
-                                                              keep_mask, inv_keep, N, T, E, V);
+  {
+    ProfScope ps(s, "embed_gather");
+    k_embed_gather<<<grid_for((long long)N * T, 8), 256, 0, s>>>((const __nv_bfloat16*)table, tok, (__nv_bfloat16*)X,
+                                                                keep_mask, inv_keep, N, T, E, V);
+  }
   VC_CUDA(cudaGetLastError());
   return VC_OK;
 }
@@ -163,7 +178,10 @@ __global__ void k_embed_scatter(const float* __restrict__ dX, const int* __restr
 }
 int embed_scatter(cudaStream_t s, const float* dX, const int* tok, float* gtable, const float* keep_mask, float inv_keep,
                   float* normsq, int N, int T, int E, int V) {
-  k_embed_scatter<<<grid_for((long long)N * T, 8), 256, 0, s>>>(dX, tok, gtable, keep_mask, inv_keep, normsq, N, T, E, V);
+  {
+    ProfScope ps(s, "embed_scatter");
+    k_embed_scatter<<<grid_for((long long)N * T, 8), 256, 0, s>>>(dX, tok, gtable, keep_mask, inv_keep, normsq, N, T, E, V);
+  }
   VC_CUDA(cudaGetLastError());
   return VC_OK;
 }
@@ -191,7 +209,10 @@ __global__ void k_heads_to_musd(const float* __restrict__ heads, long long ld, i
   }
 }
 int heads_to_musd(cudaStream_t s, const float* heads, long long ld, int zp, float* mu, float* sd, int N, int Z) {
-  k_heads_to_musd<<<grid_for((long long)N * Z, 256), 256, 0, s>>>(heads, ld, zp, mu, sd, N, Z);
+  {
+    ProfScope ps(s, "heads_to_musd");
+    k_heads_to_musd<<<grid_for((long long)N * Z, 256), 256, 0, s>>>(heads, ld, zp, mu, sd, N, Z);
+  }
   VC_CUDA(cudaGetLastError());
   return VC_OK;
 }
@@ -229,7 +250,10 @@ __global__ void k_kl_rows(const float* __restrict__ mu, const float* __restrict_
 }
 int kl_rows(cudaStream_t s, const float* mu, const float* sd, const float* cm, int prior, float* kl_row, float* dkl_dmu,
             float* dkl_dsd, float* kl_sum, int N, int Z) {
-  k_kl_rows<<<(N * 32 + 255) / 256, 256, 0, s>>>(mu, sd, cm, prior, kl_row, dkl_dmu, dkl_dsd, kl_sum, N, Z);
+  {
+    ProfScope ps(s, "kl_rows");
+    k_kl_rows<<<(N * 32 + 255) / 256, 256, 0, s>>>(mu, sd, cm, prior, kl_row, dkl_dmu, dkl_dsd, kl_sum, N, Z);
+  }
   VC_CUDA(cudaGetLastError());
   return VC_OK;
 }
@@ -260,8 +284,11 @@ __global__ void k_sample_z(const float* __restrict__ mu, const float* __restrict
 }
 int sample_z(cudaStream_t s, const float* mu, const float* sd, const float* eps, unsigned long long seed,
              unsigned long long offset, void* z, float* z_f32, int S, long long NZ) {
-  k_sample_z<<<grid_for(((long long)S * NZ + 3) / 4, 256), 256, 0, s>>>(mu, sd, eps, seed, offset, (__nv_bfloat16*)z, z_f32,
-                                                                        S, NZ);
+  {
+    ProfScope ps(s, "sample_z");
+    k_sample_z<<<grid_for(((long long)S * NZ + 3) / 4, 256), 256, 0, s>>>(mu, sd, eps, seed, offset, (__nv_bfloat16*)z, z_f32,
+                                                                          S, NZ);
+  }
   VC_CUDA(cudaGetLastError());
   return VC_OK;
 }
@@ -317,9 +344,12 @@ int dz_reduce(cudaStream_t s, const float* dz, const float* eps, unsigned long l
               int zp, float* dmu_out, float* dsd_out, int S, int N, int Z) {
   if (eps == nullptr && ((long long)N * Z) % 4 != 0)
     return set_error(VC_E_SHAPE, "Philox sampling needs N*Z to be a multiple of 4");
-  k_dz_reduce<<<grid_for(((long long)N * Z + 3) / 4, 128), 128, 0, s>>>(dz, eps, seed, offset, sd, dkl_dmu, dkl_dsd, kl_scale,
-                                                                       (__nv_bfloat16*)dheads, ld, zp, dmu_out, dsd_out,
-                                                                       S, N, Z);
+  {
+    ProfScope ps(s, "dz_reduce");
+    k_dz_reduce<<<grid_for(((long long)N * Z + 3) / 4, 128), 128, 0, s>>>(dz, eps, seed, offset, sd, dkl_dmu, dkl_dsd, kl_scale,
+                                                                         (__nv_bfloat16*)dheads, ld, zp, dmu_out, dsd_out,
+                                                                         S, N, Z);
+  }
   VC_CUDA(cudaGetLastError());
   return VC_OK;
 }
@@ -417,7 +447,10 @@ int ce_rows(cudaStream_t s, void* logits, long long ld, const int* lbl, int N, i
             const float* count, float loss_scale, int write_grad) {
   if (V > kCeThreads * kCeMaxPerThread) return set_error(VC_E_SHAPE, "vocab_size %d exceeds CE kernel limit", V);
   if (ld % 2 != 0) return set_error(VC_E_SHAPE, "logits pitch must be even");
-  k_ce<<<N * T, kCeThreads, 0, s>>>((__nv_bfloat16*)logits, ld, lbl, N, T, V, sums, ce_out, count, loss_scale, write_grad);
+  {
+    ProfScope ps(s, "ce");
+    k_ce<<<N * T, kCeThreads, 0, s>>>((__nv_bfloat16*)logits, ld, lbl, N, T, V, sums, ce_out, count, loss_scale, write_grad);
+  }
   VC_CUDA(cudaGetLastError());
   return VC_OK;
 }
@@ -431,7 +464,10 @@ __global__ void k_count_mask(const int* __restrict__ lbl, long long n, float* __
   if ((threadIdx.x & 31) == 0 && acc != 0.f) atomicAdd(count, acc);
 }
 int count_mask(cudaStream_t s, const int* lbl, long long n, float* count) {
-  k_count_mask<<<grid_for(n, 256, 4), 256, 0, s>>>(lbl, n, count);
+  {
+    ProfScope ps(s, "count_mask");
+    k_count_mask<<<grid_for(n, 256, 4), 256, 0, s>>>(lbl, n, count);
+  }
   VC_CUDA(cudaGetLastError());
   return VC_OK;
 }
@@ -462,7 +498,10 @@ int colsum_bf16(cudaStream_t s, const void* x, long long rows, int cols, long lo
   if (gy < 1) gy = 1;
   const int rpc = (int)((rows + gy - 1) / gy);
   dim3 grid(gx, (unsigned)((rows + rpc - 1) / rpc));
-  k_colsum_bf16<<<grid, threads, 0, s>>>((const __nv_bfloat16*)x, rows, cols, ld, out, rpc);
+  {
+    ProfScope ps(s, "colsum_bf16");
+    k_colsum_bf16<<<grid, threads, 0, s>>>((const __nv_bfloat16*)x, rows, cols, ld, out, rpc);
+  }
   VC_CUDA(cudaGetLastError());
   return VC_OK;
 }
@@ -493,7 +532,10 @@ __global__ void k_sumsq(const float* __restrict__ g, long long n, float* __restr
 }
 int sumsq(cudaStream_t s, const float* g, long long n, float* out) {
   if (n <= 0) return VC_OK;
-  k_sumsq<<<grid_for(n, 256, 8), 256, 0, s>>>(g, n, out);
+  {
+    ProfScope ps(s, "sumsq");
+    k_sumsq<<<grid_for(n, 256, 8), 256, 0, s>>>(g, n, out);
+  }
   VC_CUDA(cudaGetLastError());
   return VC_OK;
 }
@@ -535,7 +577,10 @@ int adam_step(cudaStream_t s, float* p, const float* g, float* m, float* v, long
               int n_parts, float clip, float gscale, float lr_t, float b1, float b2, float eps, float* norm_out) {
   if (n <= 0) return VC_OK;
   if (n % 4 != 0) return set_error(VC_E_ARG, "adam_step: length must be a multiple of 4 (padded flat buffer)");
-  k_adam<<<grid_for(n / 4, 256, 2), 256, 0, s>>>(p, g, m, v, n, normsq_parts, n_parts, clip, gscale, lr_t, b1, b2, eps, norm_out);
+  {
+    ProfScope ps(s, "adam");
+    k_adam<<<grid_for(n / 4, 256, 2), 256, 0, s>>>(p, g, m, v, n, normsq_parts, n_parts, clip, gscale, lr_t, b1, b2, eps, norm_out);
+  }
   VC_CUDA(cudaGetLastError());
   return VC_OK;
 }
@@ -553,7 +598,10 @@ __global__ void k_logits_to_ref(const __nv_bfloat16* __restrict__ src, long long
   }
 }
 int logits_to_ref(cudaStream_t s, const void* src, long long ld, float* dst, int N, int T, int V) {
-  k_logits_to_ref<<<grid_for((long long)N * T * V, 256, 4), 256, 0, s>>>((const __nv_bfloat16*)src, ld, dst, N, T, V);
+  {
+    ProfScope ps(s, "logits_to_ref");
+    k_logits_to_ref<<<grid_for((long long)N * T * V, 256, 4), 256, 0, s>>>((const __nv_bfloat16*)src, ld, dst, N, T, V);
+  }
   VC_CUDA(cudaGetLastError());
   return VC_OK;
 }
@@ -568,7 +616,10 @@ __global__ void k_bf16_to_f32(const __nv_bfloat16* __restrict__ src, float* __re
   }
 }
 int bf16_to_f32(cudaStream_t s, const void* src, float* dst, long long rows, int cols, long long ld_src, long long ld_dst) {
-  k_bf16_to_f32<<<grid_for(rows * cols, 256, 4), 256, 0, s>>>((const __nv_bfloat16*)src, dst, rows, cols, ld_src, ld_dst);
+  {
+    ProfScope ps(s, "bf16_to_f32");
+    k_bf16_to_f32<<<grid_for(rows * cols, 256, 4), 256, 0, s>>>((const __nv_bfloat16*)src, dst, rows, cols, ld_src, ld_dst);
+  }
   VC_CUDA(cudaGetLastError());
   return VC_OK;
 }

@@ -36,16 +36,39 @@ struct GemmCore {
   int b_mn;      // 1: B is MN-major
   int a_switch;  // A_KMAJOR: k-block at which A switches to tmA2 (coordinates restart at 0)
                  // A_MNMAJOR: m-tile at which A switches to tmA2. <0: never.
-  // A_CONV3x3 geometry: tile = bw x bh x bi pixels (bw*bh*bi == 128) of the NHWC input.
-  int bw, bh, bi, tiles_w, tiles_h, cpk;  // cpk = Cin / 64 chunks per filter tap
+  // A_CONV3x3 geometry. A tile is 4 patches of 32 pixels; a patch is pw x ph x pn (w, h, image) with
+  // pw*ph*pn == 32, so each epilogue warp owns one patch and 2x2 max-pool partners are lanes of the
+  // same warp. Patches are arranged tw x th x (4/(tw*th)) inside the tile.
+  int pw, ph, pn, tw, th, tiles_w, tiles_h, cpk;  // cpk = Cin / 64 chunks per filter tap
 };
 
+struct PatchOrigin {
+  int w, h, n;
+};
+// Origin (w, h, image) of patch q (0..3) of tile m_blk.
+__device__ __forceinline__ PatchOrigin conv_patch_origin(const GemmCore& g, int m_blk, int q) {
+  const int tiw = m_blk % g.tiles_w;
+  const int r = m_blk / g.tiles_w;
+  const int tih = r % g.tiles_h;
+  const int tin = r / g.tiles_h;
+  const int tn = 4 / (g.tw * g.th);
+  const int qx = q % g.tw, qy = (q / g.tw) % g.th, qn = q / (g.tw * g.th);
+  PatchOrigin o;
+  o.w = (tiw * g.tw + qx) * g.pw;
+  o.h = (tih * g.th + qy) * g.ph;
+  o.n = (tin * tn + qn) * g.pn;
+  return o;
+}
+
 __host__ __device__ inline int gemm_stage_bytes(int bn) { return kABytes + bn * kBK * 2; }
-__host__ inline int gemm_pick_stages(int bn) {
-  int s = (227 * 1024 - 2048) / gemm_stage_bytes(bn);
+// dynamic smem = [1024-align slack][stages x (A tile + B tile)][epilogue staging][barriers, 256 B]
+__host__ inline int gemm_pick_stages(int bn, int epi_bytes) {
+  int s = (227 * 1024 - 1024 - 256 - epi_bytes) / gemm_stage_bytes(bn);
   return s > kMaxStages ? kMaxStages : s;
 }
-__host__ inline int gemm_smem_bytes(int bn, int stages) { return stages * gemm_stage_bytes(bn) + 1024 + 256; }
+__host__ inline int gemm_smem_bytes(int bn, int stages, int epi_bytes) {
+  return stages * gemm_stage_bytes(bn) + epi_bytes + 1024 + 256;
+}
 
 struct TileCoord {
   int m_blk, n_blk, split, kb_begin, kb_end;
@@ -65,17 +88,22 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmCore& g, int tile) {
 }
 
 // Epi must provide:
-//   __device__ void operator()(uint32_t tmem_row_addr, const TileCoord& t, int row) const
+//   static constexpr int kSmemBytes;   // epilogue staging (multiple of 1024), split evenly over the 4 warps
+//   __device__ void operator()(uint32_t tmem_row_addr, const GemmCore& g, const TileCoord& t, int row,
+//                              uint8_t* warp_smem, int& phase) const
 // called by each of the 128 epilogue threads (row = 0..127 = TMEM lane = tile row) once the
-// accumulator is complete. tmem_row_addr addresses column 0 of this thread's warp lane quarter.
+// accumulator is complete. tmem_row_addr addresses column 0 of this thread's warp lane quarter;
+// warp_smem is this warp's quarter of the staging area; phase is per-thread state carried across tiles.
+//   __device__ void finish() const     // called once per epilogue thread after the last tile
 template <class Epi>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
-               const __grid_constant__ CUtensorMap tmB, const GemmCore g, const Epi epi) {
+               const __grid_constant__ CUtensorMap tmB, const GemmCore g, const __grid_constant__ Epi epi) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int stage_bytes = gemm_stage_bytes(g.bn);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + g.stages * stage_bytes);
+  uint8_t* epi_smem = smem + g.stages * stage_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_smem + Epi::kSmemBytes);
   uint64_t* full = bars;
   uint64_t* empty = bars + kMaxStages;
   uint64_t* tfull = bars + 2 * kMaxStages;
@@ -115,15 +143,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const TileCoord t = decode_tile(g, tile);
-        // conv tile origin
-        int cw0 = 0, ch0 = 0, ci0 = 0;
+        PatchOrigin po[4];
         if (g.a_mode == A_CONV3x3) {
-          const int tw = t.m_blk % g.tiles_w;
-          const int r = t.m_blk / g.tiles_w;
-          const int th = r % g.tiles_h;
-          cw0 = tw * g.bw;
-          ch0 = th * g.bh;
-          ci0 = (r / g.tiles_h) * g.bi;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) po[q] = conv_patch_origin(g, t.m_blk, q);
         }
         for (int kb = t.kb_begin; kb < t.kb_end; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
@@ -145,7 +168,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int tap = kb / g.cpk;
             const int c0 = (kb - tap * g.cpk) * kBK;
             const int fr = tap / 3, fs = tap - fr * 3;
-            tma_load_4d(sa, &tmA, &full[stage], c0, cw0 + fs - 1, ch0 + fr - 1, ci0);
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              tma_load_4d(sa + q * 4096, &tmA, &full[stage], c0, po[q].w + fs - 1, po[q].h + fr - 1, po[q].n);
           }
           if (g.b_mn) {
             for (int j = 0; j < g.bn; j += 64)
@@ -206,13 +231,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int q = warp & 3;
     int acc = 0;
     uint32_t acc_phase = 0;
+    int epi_phase = 0;
+    uint8_t* warp_smem = epi_smem + q * (Epi::kSmemBytes / 4);
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const TileCoord t = decode_tile(g, tile);
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
       if (t.kb_end > t.kb_begin) {
         const uint32_t taddr = tmem_base + acc * kAccStride + (uint32_t(q * 32) << 16);
-        epi(taddr, t, q * 32 + lane);
+        epi(taddr, g, t, q * 32 + lane, warp_smem, epi_phase);
       }
       tc_fence_before();
       __syncwarp();
@@ -222,6 +249,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         acc_phase ^= 1;
       }
     }
+    epi.finish();
   }
   tc_fence_before();
   __syncthreads();
@@ -240,8 +268,11 @@ struct EpiStore {
   int out_bf16;
   int atomic;  // fp32 atomicAdd (bias added by split 0 only)
   float alpha;
+  static constexpr int kSmemBytes = 0;
+  __device__ __forceinline__ void finish() const {}
 
-  __device__ __forceinline__ void operator()(uint32_t taddr, const TileCoord& t, int row) const {
+  __device__ __forceinline__ void operator()(uint32_t taddr, const GemmCore&, const TileCoord& t, int row, uint8_t*,
+                                             int&) const {
     const int m = t.m_blk * kBM + row;
     const int n_base = t.n_blk * bn;
     const bool row_ok = m < M;
@@ -290,6 +321,93 @@ struct EpiStore {
           }
         }
       }
+    }
+  }
+};
+
+// ------------------------------------------------------------------------------------------
+// bf16 tile store through shared memory + TMA: out = act(acc * alpha + bias[n]) written as 64-column
+// (128-byte) swizzled rows into a per-warp staging buffer, then one bulk tensor store per warp per
+// chunk. TMA clips rows/columns/pixels that fall outside the tensor, so ragged M, N and image
+// borders need no predicates. Three output geometries:
+//   kRows   : plain [M, N] matrix, box {64, 32}
+//   kConv   : NHWC conv output, one box {64, pw, ph, pn} per patch (warp)
+//   kConvPool: same with a fused 2x2/2 max-pool (partners are lanes of the warp), box {64, pw/2, ph/2, pn}
+enum TmaOutMode : int { kRows = 0, kConv = 1, kConvPool = 2 };
+
+struct EpiTma {
+  CUtensorMap tm;
+  const float* bias;  // nullable, indexed by n
+  int N, bn, relu, mode;
+  float alpha;
+  static constexpr int kSmemBytes = 32 * 1024;  // 4 warps x 2 buffers x (32 rows x 128 B)
+
+  __device__ __forceinline__ void finish() const {
+    if ((threadIdx.x & 31) == 0) bulk_wait_all();
+  }
+
+  __device__ __forceinline__ void operator()(uint32_t taddr, const GemmCore& g, const TileCoord& t, int row,
+                                             uint8_t* warp_smem, int& phase) const {
+    const int lane = row & 31, q = row >> 5;
+    const int n_base = t.n_blk * bn;
+    PatchOrigin po{0, 0, 0};
+    if (mode != kRows) po = conv_patch_origin(g, t.m_blk, q);
+#pragma unroll 1
+    for (int c = 0; c < bn; c += 64) {
+      const int n0 = n_base + c;
+      if (n0 >= N) break;  // warp-uniform
+      float v[64];
+      __syncwarp();
+      tmem_ld32(taddr + c, v);
+      tmem_ld32(taddr + c + 32, v + 32);  // bn is a multiple of 64 for this epilogue
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 64; ++j) {
+        float x = v[j] * alpha;
+        if (bias != nullptr && n0 + j < N) x += bias[n0 + j];
+        if (relu) x = fmaxf(x, 0.f);
+        v[j] = x;
+      }
+      int srow = lane;
+      bool writer = true;
+      if (mode == kConvPool) {
+#pragma unroll
+        for (int j = 0; j < 64; ++j) {
+          float x = fmaxf(v[j], __shfl_xor_sync(0xffffffffu, v[j], 1));
+          v[j] = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, g.pw));
+        }
+        const int w = lane % g.pw, h = (lane / g.pw) % g.ph, n = lane / (g.pw * g.ph);
+        writer = ((w | h) & 1) == 0;
+        srow = (w >> 1) + (g.pw >> 1) * ((h >> 1) + (g.ph >> 1) * n);
+      }
+      // the buffer we are about to fill was handed to a bulk store two chunks ago
+      if (lane == 0) bulk_wait_read<1>();
+      __syncwarp();
+      uint8_t* buf = warp_smem + (phase & 1) * 4096;
+      if (writer) {
+        uint8_t* rp = buf + srow * 128;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          uint4 u;
+          u.x = pack_bf16(v[8 * j + 0], v[8 * j + 1]);
+          u.y = pack_bf16(v[8 * j + 2], v[8 * j + 3]);
+          u.z = pack_bf16(v[8 * j + 4], v[8 * j + 5]);
+          u.w = pack_bf16(v[8 * j + 6], v[8 * j + 7]);
+          *reinterpret_cast<uint4*>(rp + ((j ^ (srow & 7)) << 4)) = u;
+        }
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) {
+        if (mode == kRows)
+          tma_store_2d(&tm, buf, n0, t.m_blk * kBM + q * 32);
+        else if (mode == kConv)
+          tma_store_4d(&tm, buf, n0, po.w, po.h, po.n);
+        else
+          tma_store_4d(&tm, buf, n0, po.w >> 1, po.h >> 1, po.n);
+        bulk_commit();
+      }
+      phase ^= 1;
     }
   }
 };

@@ -1,6 +1,8 @@
 #include "host_util.h"
 #include <cstdarg>
+#include <atomic>
 #include <mutex>
+#include <vector>
 
 namespace vc {
 
@@ -26,6 +28,79 @@ int num_sms() {
     if (cudaGetDevice(&dev) != cudaSuccess ||
         cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
       n = 148;
+  }
+  return n;
+}
+
+// ------------------------------------------------------------------------------------------
+namespace {
+struct ProfRec {
+  const char* tag;
+  cudaEvent_t e0, e1;
+};
+std::atomic<unsigned long long> g_launches{0};
+bool g_prof_on = false;
+std::vector<ProfRec> g_recs;
+size_t g_used = 0;
+thread_local const char* t_tag = nullptr;
+}  // namespace
+
+unsigned long long launch_count() { return g_launches.load(); }
+
+void prof_enable(bool on) {
+  g_prof_on = on;
+  if (on) g_used = 0;
+}
+
+ProfTag::ProfTag(const char* tag) : prev(t_tag) { t_tag = tag; }
+ProfTag::~ProfTag() { t_tag = prev; }
+
+ProfScope::ProfScope(cudaStream_t stream, const char* default_tag) : s(stream), slot(-1) {
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  if (!g_prof_on) return;
+  if (g_used == g_recs.size()) {
+    ProfRec r{};
+    if (cudaEventCreate(&r.e0) != cudaSuccess || cudaEventCreate(&r.e1) != cudaSuccess) return;
+    g_recs.push_back(r);
+  }
+  slot = (int)g_used++;
+  g_recs[slot].tag = t_tag ? t_tag : default_tag;
+  cudaEventRecord(g_recs[slot].e0, s);
+}
+ProfScope::~ProfScope() {
+  if (slot >= 0) cudaEventRecord(g_recs[slot].e1, s);
+}
+
+int prof_collect(char* names, int names_cap, float* ms, int* counts, int cap) {
+  cudaDeviceSynchronize();
+  std::vector<std::string> fam;
+  std::vector<float> t;
+  std::vector<int> c;
+  for (size_t i = 0; i < g_used; ++i) {
+    float e = 0.f;
+    if (cudaEventElapsedTime(&e, g_recs[i].e0, g_recs[i].e1) != cudaSuccess) continue;
+    size_t j = 0;
+    for (; j < fam.size(); ++j)
+      if (fam[j] == g_recs[i].tag) break;
+    if (j == fam.size()) {
+      fam.push_back(g_recs[i].tag);
+      t.push_back(0.f);
+      c.push_back(0);
+    }
+    t[j] += e;
+    c[j] += 1;
+  }
+  std::string joined;
+  int n = 0;
+  for (size_t j = 0; j < fam.size() && n < cap; ++j, ++n) {
+    if (!joined.empty()) joined += ",";
+    joined += fam[j];
+    ms[n] = t[j];
+    counts[n] = c[j];
+  }
+  if (names_cap > 0) {
+    strncpy(names, joined.c_str(), names_cap - 1);
+    names[names_cap - 1] = 0;
   }
   return n;
 }
@@ -101,7 +176,7 @@ int plan_gemm(GemmPlan* p, const Operand& A, const Operand* A2, long long a2_at,
   g.k_blocks = (K + kBK - 1) / kBK;
   g.splits = splits < 1 ? 1 : (splits > g.k_blocks ? g.k_blocks : splits);
   g.bn = bn;
-  g.stages = gemm_pick_stages(bn);
+  g.stages = gemm_pick_stages(bn, 0);
   g.a_mode = A.mn_major ? A_MNMAJOR : A_KMAJOR;
   g.b_mn = B.mn_major ? 1 : 0;
   g.a_switch = -1;
@@ -115,6 +190,42 @@ int plan_gemm(GemmPlan* p, const Operand& A, const Operand* A2, long long a2_at,
     VC_TRY(operand_tmap(&p->tmA2, *A2, kBM));
   }
   VC_TRY(operand_tmap(&p->tmB, B, bn));
+  return VC_OK;
+}
+
+int conv_geometry(ConvGeom* g, int W, int H, int Nimg, int Cin, int Cout) {
+  g->W = W; g->H = H; g->Nimg = Nimg; g->Cin = Cin; g->Cout = Cout;
+  if (W % 16 == 0 && H % 8 == 0) { g->pw = 16; g->ph = 2; g->pn = 1; g->tw = 1; g->th = 4; }       // 16 x 8 x 1 tiles
+  else if (W % 8 == 0 && H % 8 == 0) { g->pw = 8; g->ph = 4; g->pn = 1; g->tw = 1; g->th = 2; }    // 8 x 8 x 2
+  else if (W % 4 == 0 && H % 4 == 0) { g->pw = 4; g->ph = 4; g->pn = 2; g->tw = 1; g->th = 1; }    // 4 x 4 x 8
+  else if (W % 2 == 0 && H % 2 == 0) { g->pw = 2; g->ph = 2; g->pn = 8; g->tw = 1; g->th = 1; }    // 2 x 2 x 32
+  else return set_error(VC_E_SHAPE, "conv_geometry: %dx%d feature map has odd extent", W, H);
+  return VC_OK;
+}
+
+int plan_conv(GemmPlan* p, const void* in, const void* wt, const ConvGeom& cg, int bn) {
+  if (cg.Cin % 64 != 0) return set_error(VC_E_SHAPE, "plan_conv: Cin=%d must be a multiple of 64", cg.Cin);
+  if (bn % 64 != 0 || bn > 256) return set_error(VC_E_ARG, "plan_conv: bn=%d", bn);
+  memset(p, 0, sizeof(*p));
+  GemmCore& g = p->core;
+  const int tn = 4 / (cg.tw * cg.th);
+  g.pw = cg.pw; g.ph = cg.ph; g.pn = cg.pn; g.tw = cg.tw; g.th = cg.th;
+  g.tiles_w = (cg.W + cg.pw * cg.tw - 1) / (cg.pw * cg.tw);
+  g.tiles_h = (cg.H + cg.ph * cg.th - 1) / (cg.ph * cg.th);
+  const int tiles_n = (cg.Nimg + cg.pn * tn - 1) / (cg.pn * tn);
+  g.m_tiles = g.tiles_w * g.tiles_h * tiles_n;
+  g.n_tiles = (cg.Cout + bn - 1) / bn;
+  g.cpk = cg.Cin / 64;
+  g.k_blocks = 9 * g.cpk;
+  g.splits = 1;
+  g.bn = bn;
+  g.stages = gemm_pick_stages(bn, 0);
+  g.a_mode = A_CONV3x3;
+  g.b_mn = 0;
+  g.a_switch = -1;
+  VC_TRY(make_tmap_nhwc(&p->tmA, in, cg.Cin, cg.W, cg.H, cg.Nimg, cg.pw, cg.ph, cg.pn));
+  p->tmA2 = p->tmA;
+  VC_TRY(make_tmap_2d(&p->tmB, wt, 9ull * cg.Cin, cg.Cout, 9ull * cg.Cin, 64, bn));
   return VC_OK;
 }
 

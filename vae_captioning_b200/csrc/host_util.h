@@ -31,12 +31,39 @@ int set_error(int code, const char* fmt, ...);
 
 int num_sms();
 
+// ---- launch accounting + optional per-kernel-family CUDA-event timing (bench.py's roofline leg).
+// Every kernel launch site opens a ProfScope: it counts the launch and, while profiling is enabled,
+// brackets it with two events on the launching stream. ProfTag overrides the family name for the
+// launches made inside its lifetime (e.g. "lstm_fwd" around the generic GEMM launcher).
+unsigned long long launch_count();
+void prof_enable(bool on);                       // clears previous records when switched on
+int prof_collect(char* names, int names_cap, float* ms, int* counts, int cap);  // -> number of families
+struct ProfTag {
+  const char* prev;
+  explicit ProfTag(const char* tag);
+  ~ProfTag();
+};
+struct ProfScope {
+  cudaStream_t s;
+  int slot;
+  ProfScope(cudaStream_t stream, const char* default_tag);
+  ~ProfScope();
+};
+
 // 2-D bf16 tensor map, 128B swizzle. inner = contiguous extent (elements), outer = rows,
 // ld = row pitch in elements (ld*2 must be a multiple of 16 bytes).
 int make_tmap_2d(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner,
                  uint32_t box_outer);
 // 4-D bf16 NHWC tensor map {C, W, H, N} with box {64, bw, bh, bi}, 128B swizzle.
 int make_tmap_nhwc(CUtensorMap* out, const void* ptr, int C, int W, int H, int N, int bw, int bh, int bi);
+
+// Patch / tile geometry of a 3x3 SAME convolution over an NHWC tensor (see GemmCore).
+struct ConvGeom {
+  int W, H, Nimg, Cin, Cout;
+  int pw, ph, pn, tw, th;
+};
+// Picks the patch shape that tiles a W x H feature map exactly (224/112: 16x2x1, 56: 8x4x1, 28: 4x4x2, 14: 2x2x8).
+int conv_geometry(ConvGeom* g, int W, int H, int Nimg, int Cin, int Cout);
 
 // A GEMM operand. K-major: matrix [rows = M or N][cols = K]. MN-major: matrix [rows = K][cols = M or N].
 struct Operand {
@@ -56,6 +83,9 @@ struct GemmPlan {
 int plan_gemm(GemmPlan* p, const Operand& A, const Operand* A2, long long a2_at, const Operand& B, int M, int N, int K,
               int bn, int splits);
 
+// D = conv3x3_same(in NHWC bf16 [Nimg,H,W,Cin], Wt bf16 [Cout, 9*Cin] (tap-major, then cin)); Cin % 64 == 0.
+int plan_conv(GemmPlan* p, const void* in, const void* wt, const ConvGeom& g, int bn);
+
 template <class Epi>
 int launch_gemm(const GemmPlan& p, const Epi& epi, cudaStream_t stream) {
   static bool configured = false;
@@ -66,8 +96,14 @@ int launch_gemm(const GemmPlan& p, const Epi& epi, cudaStream_t stream) {
   const int total = p.core.m_tiles * p.core.n_tiles * p.core.splits;
   if (total <= 0) return VC_OK;
   const int grid = total < num_sms() ? total : num_sms();
-  const int smem = gemm_smem_bytes(p.core.bn, p.core.stages);
-  gemm_tc_kernel<Epi><<<grid, kGemmThreads, smem, stream>>>(p.tmA, p.tmA2, p.tmB, p.core, epi);
+  GemmCore core = p.core;
+  core.stages = gemm_pick_stages(core.bn, Epi::kSmemBytes);
+  if (core.stages < 2) return set_error(VC_E_ARG, "launch_gemm: tile too large for shared memory (bn=%d)", core.bn);
+  const int smem = gemm_smem_bytes(core.bn, core.stages, Epi::kSmemBytes);
+  {
+    ProfScope ps(stream, "gemm");
+    gemm_tc_kernel<Epi><<<grid, kGemmThreads, smem, stream>>>(p.tmA, p.tmA2, p.tmB, core, epi);
+  }
   VC_CUDA(cudaGetLastError());
   return VC_OK;
 }

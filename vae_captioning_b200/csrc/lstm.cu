@@ -28,8 +28,11 @@ struct EpiLstmFwd {
   long long out_keep_ld;
   float inv_keep;
   int t, N, H;
+  static constexpr int kSmemBytes = 0;
+  __device__ __forceinline__ void finish() const {}
 
-  __device__ __forceinline__ void operator()(uint32_t taddr, const TileCoord& tc, int row) const {
+  __device__ __forceinline__ void operator()(uint32_t taddr, const GemmCore&, const TileCoord& tc, int row, uint8_t*,
+                                             int&) const {
     const int m = tc.m_blk * kBM + row;
     const bool row_ok = m < N;
     const bool live = row_ok && (lengths == nullptr || t < lengths[m]);
@@ -133,6 +136,7 @@ int lstm_fwd_step(cudaStream_t stream, const LstmFwdArgs& a) {
   epi.t = a.t;
   epi.N = a.N;
   epi.H = a.H;
+  ProfTag tag("lstm_fwd_step");
   return launch_gemm(plan, epi, stream);
 }
 
@@ -234,7 +238,10 @@ constexpr int kBwdBN = 64;
 
 struct EpiLstmBwd {
   LstmBwdCommon c;
-  __device__ __forceinline__ void operator()(uint32_t taddr, const TileCoord& tc, int row) const {
+  static constexpr int kSmemBytes = 0;
+  __device__ __forceinline__ void finish() const {}
+  __device__ __forceinline__ void operator()(uint32_t taddr, const GemmCore&, const TileCoord& tc, int row, uint8_t*,
+                                             int&) const {
     const int m = tc.m_blk * kBM + row;
 #pragma unroll 1
     for (int col = 0; col < kBwdBN; col += 16) {
@@ -279,7 +286,10 @@ int lstm_bwd_step(cudaStream_t stream, const LstmBwdArgs& a) {
   if (a.d_gates_next == nullptr) {
     const long long chunks = (long long)a.N * (a.H / 16);
     int grid = (int)((chunks + 127) / 128);
-    k_lstm_bwd_last<<<grid, 128, 0, stream>>>(c);
+    {
+      ProfScope ps(stream, "lstm_bwd_last");
+      k_lstm_bwd_last<<<grid, 128, 0, stream>>>(c);
+    }
     VC_CUDA(cudaGetLastError());
     return VC_OK;
   }
@@ -289,6 +299,7 @@ int lstm_bwd_step(cudaStream_t stream, const LstmBwdArgs& a) {
   GemmPlan plan;
   VC_TRY(plan_gemm(&plan, A, nullptr, 0, B, a.N, a.H, 4 * a.H, kBwdBN, 1));
   EpiLstmBwd epi{c};
+  ProfTag tag("lstm_bwd_step");
   return launch_gemm(plan, epi, stream);
 }
 

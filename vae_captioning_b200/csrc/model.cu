@@ -13,18 +13,6 @@ Model::~Model() {
   if (host_scal) cudaFreeHost(host_scal);
 }
 
-template <class T>
-int Model::dalloc(T** p, size_t count, bool zero) {
-  void* q = nullptr;
-  if (count == 0) count = 1;
-  cudaError_t e = cudaMalloc(&q, count * sizeof(T));
-  if (e != cudaSuccess) return set_error(VC_E_NOMEM, "cudaMalloc(%zu bytes) failed: %s", count * sizeof(T), cudaGetErrorString(e));
-  if (zero) VC_CUDA(cudaMemset(q, 0, count * sizeof(T)));
-  allocs.push_back(q);
-  *p = reinterpret_cast<T*>(q);
-  return VC_OK;
-}
-
 int Model::add_param(const std::string& name, std::vector<int64_t> shape, int region) {
   ParamInfo pi;
   pi.name = name;
@@ -221,6 +209,7 @@ int Model::init(const vc_config& c, int dev) {
   VC_TRY(dalloc(&st_in, (size_t)N * T));
   VC_TRY(dalloc(&st_len, (size_t)N));
   VC_CUDA(cudaMallocHost((void**)&host_scal, 64 * sizeof(float)));
+  if (cfg.with_cnn || cfg.fine_tune) VC_TRY(vgg_init());
   shadows_dirty = true;
   return VC_OK;
 }
@@ -231,6 +220,7 @@ int Model::param_set(const char* name, const float* src) {
   if (i < 0) return set_error(VC_E_ARG, "unknown variable '%s'", name);
   VC_CUDA(cudaMemcpy(pp(i), src, params[i].count * sizeof(float), cudaMemcpyHostToDevice));
   shadows_dirty = true;
+  vgg_shadows_dirty = true;
   return VC_OK;
 }
 int Model::param_get(const char* name, float* dst) {
@@ -252,6 +242,7 @@ int Model::grad_get(const char* name, float* dst) {
 
 // ------------------------------------------------------------------------------------------
 int Model::refresh_shadows(cudaStream_t s) {
+  ProfTag ptag("refresh_shadows");
   const int E = cfg.embed_size, Z = cfg.latent_size, S = cfg.gen_z_samples, V = cfg.vocab_size, F = cfg.cnn_feature_size,
             K = cfg.num_clusters;
   VC_TRY(transpose_cast(s, pp(pidx("imf_emb/kernel")), imf_wt, F, E, E, F, 0, 0));
@@ -305,7 +296,7 @@ int Model::stage_inputs(const float* feats, const int32_t* lbl, const int32_t* i
     return set_error(VC_E_SHAPE, "batch %d x len %d exceeds the handle's max_batch %d / max_len %d", B, T, cfg.max_batch, maxT);
   const int N = B * cfg.num_captions;
   const size_t fe = cfg.fine_tune ? (size_t)224 * 224 * 3 : (size_t)cfg.cnn_feature_size;
-  VC_CUDA(cudaMemcpyAsync(st_feats, feats, B * fe * sizeof(float), cudaMemcpyHostToDevice, s));
+  if (feats != nullptr) VC_CUDA(cudaMemcpyAsync(st_feats, feats, B * fe * sizeof(float), cudaMemcpyHostToDevice, s));
   VC_CUDA(cudaMemcpyAsync(st_lbl, lbl, (size_t)N * T * sizeof(int32_t), cudaMemcpyHostToDevice, s));
   VC_CUDA(cudaMemcpyAsync(st_in, inp, (size_t)N * T * sizeof(int32_t), cudaMemcpyHostToDevice, s));
   VC_CUDA(cudaMemcpyAsync(st_len, len, (size_t)N * sizeof(int32_t), cudaMemcpyHostToDevice, s));
@@ -397,13 +388,16 @@ int Model::lstm_backward(LstmNet& L, int N, int T, const int32_t* len, const flo
   e.alpha = 1.f;
   const int tiles = ((L.E + L.H + 127) / 128) * ((4 * L.H + 255) / 256);
   int splits = std::max(1, num_sms() / std::max(1, tiles));
-  if (L.E % 128 == 0) {
-    VC_TRY(gemm_store(s, AX, &AH, L.E, BG, L.E + L.H, 4 * L.H, (int)rows, e, 256, splits));
-  } else {  // E not a multiple of the 128-row tile: two GEMMs
-    EpiStore e2 = e;
-    VC_TRY(gemm_store(s, AX, nullptr, 0, BG, L.E, 4 * L.H, (int)rows, e, 256, splits));
-    e2.out = gp(L.p_kernel) + (size_t)L.E * 4 * L.H;
-    VC_TRY(gemm_store(s, AH, nullptr, 0, BG, L.H, 4 * L.H, (int)rows, e2, 256, splits));
+  {
+    ProfTag ptag("lstm_wgrad");
+    if (L.E % 128 == 0) {
+      VC_TRY(gemm_store(s, AX, &AH, L.E, BG, L.E + L.H, 4 * L.H, (int)rows, e, 256, splits));
+    } else {  // E not a multiple of the 128-row tile: two GEMMs
+      EpiStore e2 = e;
+      VC_TRY(gemm_store(s, AX, nullptr, 0, BG, L.E, 4 * L.H, (int)rows, e, 256, splits));
+      e2.out = gp(L.p_kernel) + (size_t)L.E * 4 * L.H;
+      VC_TRY(gemm_store(s, AH, nullptr, 0, BG, L.H, 4 * L.H, (int)rows, e2, 256, splits));
+    }
   }
   VC_TRY(colsum_bf16(s, L.dG, rows, 4 * L.H, 4 * L.H, gp(L.p_bias)));
   // input gradient: dX[steps*N, E] = dG x W_x^T  (B = rows 0..E of the natural shadow)
@@ -413,7 +407,10 @@ int Model::lstm_backward(LstmNet& L, int N, int T, const int32_t* len, const flo
   ex.out = L.dX;
   ex.ld = L.E;
   ex.alpha = 1.f;
-  VC_TRY(gemm_store(s, AG, nullptr, 0, BW, (int)rows, L.E, 4 * L.H, ex, L.E % 256 == 0 ? 256 : 64, 1));
+  {
+    ProfTag ptag("lstm_dx");
+    VC_TRY(gemm_store(s, AG, nullptr, 0, BW, (int)rows, L.E, 4 * L.H, ex, L.E % 256 == 0 ? 256 : 64, 1));
+  }
   return VC_OK;
 }
 
@@ -448,6 +445,7 @@ int Model::forward(const StepInputs& in, bool write_grad, cudaStream_t s) {
     Operand A{feats_h, B, F, F, false}, Bw{imf_wt, E, F, F, false};
     EpiStore e{};
     e.out = imf_f; e.ld = E; e.bias = pp(pidx("imf_emb/bias")); e.atomic = 1; e.alpha = 1.f;
+    ProfTag ptag("imf_emb");
     VC_TRY(gemm_store(s, A, nullptr, 0, Bw, B, E, F, e, 64, 8));
   }
   VC_TRY(tile_cast(s, imf_f, cfg.no_encoder ? nullptr : enc.X, dec.X, B, C, E));
@@ -457,6 +455,7 @@ int Model::forward(const StepInputs& in, bool write_grad, cudaStream_t s) {
       Operand A{cv_h, N, K, KP, false}, Bw{cv_wt, E, K, KP, false};
       EpiStore e{};
       e.out = cv_f; e.ld = E; e.bias = pp(pidx("cv_emb/bias")); e.alpha = 1.f;
+      ProfTag ptag("cv_emb");
       VC_TRY(gemm_store(s, A, nullptr, 0, Bw, N, E, K, e, 64, 1));
       VC_TRY(tile_cast(s, cv_f, cfg.no_encoder ? nullptr : (uint16_t*)enc.X + (size_t)N * E,
                        (uint16_t*)dec.X + (size_t)N * E, N, 1, E));
@@ -472,6 +471,7 @@ int Model::forward(const StepInputs& in, bool write_grad, cudaStream_t s) {
       Operand A{hT, N, He, He, false}, Bw{heads_wt, heads_cols, He, He, false};
       EpiStore e{};
       e.out = heads_f; e.ld = heads_cols; e.bias = heads_bias; e.alpha = 1.f;
+      ProfTag ptag("heads");
       VC_TRY(gemm_store(s, A, nullptr, 0, Bw, N, heads_cols, He, e, 64, 1));
     }
     VC_TRY(heads_to_musd(s, heads_f, heads_cols, ZP, mu, sd, N, Z));
@@ -485,6 +485,7 @@ int Model::forward(const StepInputs& in, bool write_grad, cudaStream_t s) {
       EpiStore e{};
       e.out = zdec_f; e.ld = E; e.bias = pp(pidx("decoder/net/z_rnn/bias")); e.atomic = 1; e.alpha = 1.f;
       const int tiles = ((N + 127) / 128) * ((E + 127) / 128);
+      ProfTag ptag("z_rnn");
       VC_TRY(gemm_store(s, A, nullptr, 0, Bw, N, E, SZ, e, 128, std::max(1, num_sms() / tiles)));
     }
     VC_TRY(tile_cast(s, zdec_f, nullptr, (uint16_t*)dec.X + (size_t)(dec.pre - 1) * N * E, N, 1, E));
@@ -497,6 +498,7 @@ int Model::forward(const StepInputs& in, bool write_grad, cudaStream_t s) {
     Operand A{Out, (long long)T * N, Hd, Hd, false}, Bw{wo_t, V, Hd, Hd, false};
     EpiStore e{};
     e.out = logits; e.ld = VP; e.bias = pp(pidx("decoder/rnn_logits/bias")); e.out_bf16 = 1; e.alpha = 1.f;
+    ProfTag ptag("logits_fwd");
     VC_TRY(gemm_store(s, A, nullptr, 0, Bw, T * N, V, Hd, e, 256, 1));
   }
   // masked cross-entropy (main.py:152-158); AG differentiates the sum of an [N] lower bound (Q2)
@@ -522,11 +524,17 @@ int Model::backward(const StepInputs& in, cudaStream_t s) {
     Operand A{logits, rows, V, VP, false}, Bw{wo_nat, Hd, V, VP, false};
     EpiStore e{};
     e.out = dOut; e.ld = Hd; e.alpha = 1.f;
-    VC_TRY(gemm_store(s, A, nullptr, 0, Bw, (int)rows, Hd, V, e, Hd % 256 == 0 ? 256 : 64, 1));
+    {
+      ProfTag ptag("logits_dgrad");
+      VC_TRY(gemm_store(s, A, nullptr, 0, Bw, (int)rows, Hd, V, e, Hd % 256 == 0 ? 256 : 64, 1));
+    }
     Operand A2{Out, rows, Hd, Hd, true}, B2{logits, rows, V, VP, true};
     EpiStore e2{};
     e2.out = gp(pidx("decoder/rnn_logits/kernel")); e2.ld = V; e2.alpha = 1.f;
-    VC_TRY(gemm_store(s, A2, nullptr, 0, B2, Hd, V, (int)rows, e2, 256, 1));
+    {
+      ProfTag ptag("logits_wgrad");
+      VC_TRY(gemm_store(s, A2, nullptr, 0, B2, Hd, V, (int)rows, e2, 256, 1));
+    }
     VC_TRY(colsum_bf16(s, logits, rows, V, VP, gp(pidx("decoder/rnn_logits/bias"))));
   }
   // decoder BPTT
@@ -546,11 +554,17 @@ int Model::backward(const StepInputs& in, cudaStream_t s) {
       Operand A{dzdec_h, N, E, E, false}, Bw{z_nat, SZ, E, E, false};
       EpiStore e{};
       e.out = dz; e.ld = SZ; e.alpha = 1.f;
-      VC_TRY(gemm_store(s, A, nullptr, 0, Bw, N, SZ, E, e, 256, 1));
+      {
+        ProfTag ptag("z_rnn_dgrad");
+        VC_TRY(gemm_store(s, A, nullptr, 0, Bw, N, SZ, E, e, 256, 1));
+      }
       Operand A2{z, N, SZ, SZ, true}, B2{dzdec_h, N, E, E, true};
       EpiStore e2{};
       e2.out = gp(pidx("decoder/net/z_rnn/kernel")); e2.ld = E; e2.alpha = 1.f;
-      VC_TRY(gemm_store(s, A2, nullptr, 0, B2, SZ, E, N, e2, E % 256 == 0 ? 256 : 64, 1));
+      {
+        ProfTag ptag("z_rnn_wgrad");
+        VC_TRY(gemm_store(s, A2, nullptr, 0, B2, SZ, E, N, e2, E % 256 == 0 ? 256 : 64, 1));
+      }
       VC_TRY(colsum_bf16(s, dzdec_h, N, E, E, gp(pidx("decoder/net/z_rnn/bias"))));
     }
     // reparameterisation + KL -> head gradients. lower_bound = rec + ann * KL / 10 (main.py:172-174);
@@ -564,7 +578,10 @@ int Model::backward(const StepInputs& in, cudaStream_t s) {
       Operand A{dheads, N, heads_cols, heads_cols, false}, Bw{heads_nat, He, heads_cols, heads_cols, false};
       EpiStore e{};
       e.out = enc.dh_carry; e.ld = He; e.alpha = 1.f;
-      VC_TRY(gemm_store(s, A, nullptr, 0, Bw, N, He, heads_cols, e, 64, 1));
+      {
+        ProfTag ptag("heads_bwd");
+        VC_TRY(gemm_store(s, A, nullptr, 0, Bw, N, He, heads_cols, e, 64, 1));
+      }
       VC_CUDA(cudaMemsetAsync(tmp_bias, 0, (size_t)heads_cols * sizeof(float), s));
       VC_TRY(colsum_bf16(s, dheads, N, heads_cols, heads_cols, tmp_bias));
       const int pk[2] = {pidx("encoder/dense/kernel"), pidx("encoder/dense_1/kernel")};
@@ -573,6 +590,7 @@ int Model::backward(const StepInputs& in, cudaStream_t s) {
         Operand A2{hT, N, He, He, true}, B2{(uint16_t*)dheads + (size_t)w * ZP, N, Z, heads_cols, true};
         EpiStore e2{};
         e2.out = gp(pk[w]); e2.ld = Z; e2.alpha = 1.f;
+        ProfTag ptag("heads_bwd");
         VC_TRY(gemm_store(s, A2, nullptr, 0, B2, He, Z, N, e2, 64, 1));
         VC_CUDA(cudaMemcpyAsync(gp(pb[w]), tmp_bias + (size_t)w * ZP, Z * sizeof(float), cudaMemcpyDeviceToDevice, s));
       }
@@ -588,6 +606,7 @@ int Model::backward(const StepInputs& in, cudaStream_t s) {
     Operand A{feats_h, B, F, F, true}, Bw{dimf_h, B, E, E, true};
     EpiStore e{};
     e.out = gp(pidx("imf_emb/kernel")); e.ld = E; e.alpha = 1.f;
+    ProfTag ptag("imf_emb_bwd");
     VC_TRY(gemm_store(s, A, nullptr, 0, Bw, F, E, B, e, E % 256 == 0 ? 256 : 64, 1));
     VC_TRY(colsum_bf16(s, dimf_h, B, E, E, gp(pidx("imf_emb/bias"))));
   }
@@ -596,6 +615,7 @@ int Model::backward(const StepInputs& in, cudaStream_t s) {
     Operand A{cv_h, N, K, KP, true}, Bw{dcv_h, N, E, E, true};
     EpiStore e{};
     e.out = gp(pidx("cv_emb/kernel")); e.ld = E; e.alpha = 1.f;
+    ProfTag ptag("cv_emb_bwd");
     VC_TRY(gemm_store(s, A, nullptr, 0, Bw, K, E, N, e, E % 256 == 0 ? 256 : 64, 1));
     VC_TRY(colsum_bf16(s, dcv_h, N, E, E, gp(pidx("cv_emb/bias"))));
   }

@@ -34,6 +34,15 @@ struct LstmNet {
   float* dc_carry = nullptr;
 };
 
+struct VggLayer {
+  int cin = 0, cout = 0, hw = 0, kpad = 0;
+  bool pool = false;
+  int p_w = -1, p_b = -1;
+  void* wt = nullptr;      // bf16 [cout, kpad] (tap-major, then cin)
+  void* out = nullptr;     // bf16 NHWC [B, hw, hw, cout] (post-ReLU, un-pooled)
+  void* pooled = nullptr;  // bf16 NHWC [B, hw/2, hw/2, cout] when pool
+};
+
 struct StepInputs {
   const float* feats;     // device fp32 [B, F] (or images when fine_tune)
   const int32_t* cap_lbl; // device [N, T]
@@ -80,6 +89,18 @@ class Model {
   int32_t *st_lbl = nullptr, *st_in = nullptr, *st_len = nullptr;
   float* host_scal = nullptr;  // pinned
 
+  // --- VGG16 (vgg.cu)
+  std::vector<VggLayer> vgg;
+  void *vgg_im2col = nullptr, *fc1_w = nullptr, *fc2_w = nullptr, *fc1_h = nullptr;
+  float *fc_acc = nullptr, *fc2_f = nullptr, *st_images = nullptr;
+  bool vgg_shadows_dirty = true, vgg_keep = false, vgg_have_unpooled = false;
+  int vgg_last_B = 0;
+  int vgg_init();
+  int vgg_refresh_shadows(cudaStream_t s);
+  int vgg_conv_layer(int l, const void* in, int B, bool fuse_pool, cudaStream_t s);
+  int vgg_forward(const float* images, float* fc2_out, int B, bool keep_unpooled, const float* fc_keep, cudaStream_t s);
+  int vgg_activation(const char* layer, float* dst_host);
+
   std::vector<void*> allocs;
 
   ~Model();
@@ -100,7 +121,17 @@ class Model {
 
  private:
   template <class T>
-  int dalloc(T** p, size_t count, bool zero = true);
+  int dalloc(T** p, size_t count, bool zero = true) {
+    void* q = nullptr;
+    if (count == 0) count = 1;
+    cudaError_t e = cudaMalloc(&q, count * sizeof(T));
+    if (e != cudaSuccess)
+      return set_error(VC_E_NOMEM, "cudaMalloc(%zu bytes) failed: %s", count * sizeof(T), cudaGetErrorString(e));
+    if (zero) VC_CUDA(cudaMemset(q, 0, count * sizeof(T)));
+    allocs.push_back(q);
+    *p = reinterpret_cast<T*>(q);
+    return VC_OK;
+  }
   int add_param(const std::string& name, std::vector<int64_t> shape, int region);
   int lstm_forward(LstmNet& L, int N, int T, const int32_t* len, void* out, const float* out_keep, cudaStream_t s);
   int lstm_backward(LstmNet& L, int N, int T, const int32_t* len, const float* d_out, const float* out_keep,

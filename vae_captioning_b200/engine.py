@@ -113,11 +113,16 @@ class Engine(object):
         step_args = [vp, vp, vp, vp, vp, vp, ci, ci, cll, ctypes.POINTER(VcRng)]
         lib.vc_train_step.argtypes = step_args + [ctypes.POINTER(VcStepOut), vp]
         lib.vc_train_step_dev.argtypes = step_args + [ctypes.POINTER(VcStepOut), vp]
+        lib.vc_train_step_images.argtypes = step_args + [ctypes.POINTER(VcStepOut), vp]
         lib.vc_forward_backward_dev.argtypes = step_args + [vp]
         lib.vc_eval_step.argtypes = [vp, vp, vp, vp, vp, vp, ci, ci, ctypes.POINTER(VcRng), ctypes.POINTER(VcStepOut), vp]
         lib.vc_grad_buffer.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(ctypes.c_int64)]
         lib.vc_apply_gradients.argtypes = [vp, ctypes.c_float, ctypes.POINTER(VcStepOut), vp]
         lib.vc_forward_debug.argtypes = [vp] * 7
+        lib.vc_vgg_forward.argtypes = [vp, vp, vp, ci, vp]
+        lib.vc_vgg_forward_dev.argtypes = [vp, vp, vp, ci, vp]
+        lib.vc_vgg_activation.argtypes = [vp, ctypes.c_char_p, vp]
+        lib.vc_vgg_keep_activations.argtypes = [vp, ci]
         lib._vc_declared = True
 
     # ------------------------------------------------------------------ lifetime
@@ -201,7 +206,7 @@ class Engine(object):
         return L.stream_ptr()
 
     def train_step(self, image_f_inputs, ann_inputs_enc, ann_inputs_dec, ann_lengths, anneal, c_i=None, rng=None,
-                   fetch=True):
+                   fetch=True, images=False):
         """sess.run([kld, rec_loss, lower_bound, optimize, optimize_cnn, annealing], feed) (main.py:229-244).
 
         Host (numpy) inputs: copied to the device inside the call. Returns dict(kld, rec_loss, lower_bound,
@@ -211,11 +216,12 @@ class Engine(object):
         ln = _i32(np.asarray(ann_lengths).ravel())
         cv = _f32(c_i) if c_i is not None else None
         B, T = feats.shape[0], lbl.shape[1]
-        self._check_feed(feats, lbl, inp, ln, cv, B, T)
+        self._check_feed(feats, lbl, inp, ln, cv, B, T, images)
         r, keep = self._rng(rng)
         out = VcStepOut()
         self._keep = [feats, lbl, inp, ln, cv, keep]
-        L.check(self.lib.vc_train_step(self._h, _np_ptr(feats), _np_ptr(lbl), _np_ptr(inp), _np_ptr(ln), _np_ptr(cv), B, T,
+        fn = self.lib.vc_train_step_images if images else self.lib.vc_train_step
+        L.check(fn(self._h, _np_ptr(feats), _np_ptr(lbl), _np_ptr(inp), _np_ptr(ln), _np_ptr(cv), B, T,
                                        int(anneal), ctypes.byref(r), ctypes.byref(out) if fetch else None, self._stream()))
         return out.as_dict() if fetch else None
 
@@ -264,7 +270,7 @@ class Engine(object):
                                       ctypes.byref(r), ctypes.byref(out), self._stream()))
         return out.as_dict()
 
-    def _check_feed(self, feats, lbl, inp, ln, cv, B, T):
+    def _check_feed(self, feats, lbl, inp, ln, cv, B, T, images=False):
         N = B * self.cfg.num_captions
         if lbl.shape != (N, T) or inp.shape != (N, T):
             raise ValueError("captions must be [B*num_captions=%d, T] (got %s and %s)" % (N, lbl.shape, inp.shape))
@@ -272,9 +278,45 @@ class Engine(object):
             raise ValueError("ann_lengths must have %d entries, got %s" % (N, ln.shape))
         if cv is not None and cv.shape != (N, self.cfg.num_clusters):
             raise ValueError("c_i must be [%d, %d], got %s" % (N, self.cfg.num_clusters, cv.shape))
-        per_image = 224 * 224 * 3 if self.cfg.fine_tune else self.cfg.cnn_feature_size
+        per_image = 224 * 224 * 3 if (self.cfg.fine_tune or images) else self.cfg.cnn_feature_size
         if feats.size != B * per_image:
             raise ValueError("image_f_inputs has %d values per row, expected %d" % (feats.size // max(B, 1), per_image))
+
+    # ------------------------------------------------------------------ VGG16 feature extractor
+    def vgg_forward(self, images):
+        """sess.run(features, {input_img: images}) of Data.extract_features_from_dir (utils/data.py:120-125), batched:
+        images [B,224,224,3] RGB 0..255 (host) -> fc2 features fp32 [B,4096] (host)."""
+        img = _f32(images)
+        if img.ndim != 4 or img.shape[1:] != (224, 224, 3):
+            raise ValueError("images must be [B,224,224,3], got %s" % (img.shape,))
+        out = np.empty((img.shape[0], 4096), np.float32)
+        L.check(self.lib.vc_vgg_forward(self._h, _np_ptr(img), _np_ptr(out), img.shape[0], self._stream()))
+        return out
+
+    def vgg_forward_device(self, images):
+        """Device-resident form: images is a CUDA float32 tensor [B,224,224,3]; returns a CUDA tensor [B,4096]."""
+        import torch
+        B = images.shape[0]
+        out = torch.empty((B, 4096), dtype=torch.float32, device=images.device)
+        self._keep_vgg = (images, out)
+        L.check(self.lib.vc_vgg_forward_dev(self._h, L.ptr(images), L.ptr(out), B, self._stream()))
+        return out
+
+    def vgg_keep_activations(self, on=True):
+        L.check(self.lib.vc_vgg_keep_activations(self._h, int(bool(on))))
+
+    def vgg_activation(self, layer, B):
+        shapes = {"conv1_1": (224, 64), "conv1_2": (224, 64), "pool1": (112, 64), "conv2_1": (112, 128),
+                  "conv2_2": (112, 128), "pool2": (56, 128), "conv3_1": (56, 256), "conv3_2": (56, 256),
+                  "conv3_3": (56, 256), "pool3": (28, 256), "conv4_1": (28, 512), "conv4_2": (28, 512),
+                  "conv4_3": (28, 512), "pool4": (14, 512), "conv5_1": (14, 512), "conv5_2": (14, 512),
+                  "conv5_3": (14, 512), "pool5": (7, 512)}
+        if layer not in shapes:
+            raise ValueError("unknown VGG layer %r" % layer)
+        hw, c = shapes[layer]
+        a = np.empty((B, hw, hw, c), np.float32)
+        L.check(self.lib.vc_vgg_activation(self._h, layer.encode(), _np_ptr(a)))
+        return a
 
     def debug_taps(self, N, T, logits=True, z=False):
         """x_logits (main.py:150), qz mean/std (main.py:122-124), per-row KL and CE of the last forward-only pass."""

@@ -57,3 +57,22 @@ def ptr(t):
 def stream_ptr():
     import torch
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class _RawCudaBuffer(object):
+    """Exposes a library-owned device allocation through __cuda_array_interface__ so torch can alias it."""
+
+    def __init__(self, ptr, count, typestr):
+        self.__cuda_array_interface__ = {"shape": (int(count),), "typestr": typestr, "data": (int(ptr), False),
+                                         "version": 2, "strides": None}
+
+
+def alias_tensor(ptr, count, dtype, device_index):
+    """A torch tensor (container only) aliasing `count` elements at device pointer `ptr`; used to hand the
+    library's flat gradient buffer to torch.distributed's NCCL all-reduce without a copy."""
+    import torch
+    typestr = {torch.float32: "<f4", torch.int32: "<i4", torch.bfloat16: "<u2"}[dtype]
+    t = torch.as_tensor(_RawCudaBuffer(ptr, count, typestr), device=torch.device("cuda", device_index))
+    if dtype == torch.bfloat16:
+        t = t.view(torch.bfloat16)
+    return t
