@@ -104,6 +104,9 @@ int vc_param_info(vc_handle* h, int index, const char** name, int32_t* ndim, int
 int vc_param_get(vc_handle* h, const char* name, float* dst_host);
 int vc_param_set(vc_handle* h, const char* name, const float* src_host);
 int vc_grad_get(vc_handle* h, const char* name, float* dst_host); /* tf.gradients of the last step (debug tap) */
+/* init_clusters (utils/vae_utils.py:6-31, main.py:127/137): the [num_clusters, latent] constant cluster means of the
+ * AG prior (the reference persists them in ./pickles/cluster_means.pickle). Zero until set. */
+int vc_set_cluster_means(vc_handle* h, const float* src_host);
 
 /* One training sess.run (main.py:229-244): feed {image_f_inputs, ann_inputs_enc, ann_inputs_dec, ann_lengths,
  * anneal, c_i} -> fetch [kld, rec_loss, lower_bound, optimize, optimize_cnn, annealing].

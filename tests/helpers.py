@@ -35,6 +35,8 @@ def engine_for(cfg, params, B, T, **kw):
     from vae_captioning_b200.engine import Engine
     eng = Engine(cfg, vocab_size=cfg.vocab_size, max_batch=B, max_len=T, **kw)
     eng.load_state({n: v.to(torch.float32).numpy() for n, v in params.items()})
+    if cfg.prior == "AG" and not cfg.no_encoder:
+        eng.set_cluster_means(O.init_clusters(cfg.num_clusters, cfg.latent_size).numpy())  # the oracle's default (seed 2)
     return eng
 
 

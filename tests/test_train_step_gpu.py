@@ -48,6 +48,24 @@ def test_forward_normal_prior(sizes, B, T, ragged):
     assert out["n_tokens"] == ref_x["n_tokens"]
 
 
+@pytest.mark.parametrize("prior,use_c_v,sizes,B,T", [("GMM", True, TINY, 3, 5), ("AG", True, TINY, 3, 5), ("AG", False, SMALL, 4, 6),
+                                                     ("GMM", False, SMALL, 4, 6), ("AG", True, SMALL, 30, 7)])
+def test_forward_gmm_ag_priors(prior, use_c_v, sizes, B, T):
+    """90 (mu_k, logstd_k) heads; GMM gathers the drawn cluster, AG mixes with the cluster vector (encoder.py:71-107);
+    AG's KL is a per-row vector against N(c_v @ c_means, 0.1) (main.py:136-145, Q2)."""
+    cfg, out, taps, ref_e, ref_x = run_forward(sizes, B, T, True, prior=prior, use_c_v=use_c_v)
+    assert rel_err(taps["mu"], ref_e["mu"].numpy()) <= 5e-3
+    assert rel_err(taps["std"], ref_e["std"].numpy()) <= 5e-3
+    assert rel_err(taps["logits"], ref_e["logits"].numpy()) <= 1.5e-2
+    kl_ref = ref_x["kld"].numpy()
+    if prior == "AG":
+        assert rel_err(taps["kl_rows"], kl_ref) <= 1e-2
+    assert abs(out["kld"] - float(kl_ref.mean())) <= 1e-2 * abs(float(kl_ref.mean())) + 1e-6
+    assert abs(out["rec_loss"] - float(ref_x["rec_loss"])) <= 5e-3 * abs(float(ref_x["rec_loss"]))
+    lb = float(ref_x["lower_bound"].mean())
+    assert abs(out["lower_bound"] - lb) <= 5e-3 * abs(lb)
+
+
 def test_padding_semantics():
     """dynamic_rnn(sequence_length): logits past the caption end equal the logits bias exactly."""
     cfg, params, batch = make_case(TINY, 3, 6, seed=5, ragged=True)
@@ -86,7 +104,9 @@ def grads_case(sizes, B, T, ragged, **kw):
 @pytest.mark.parametrize("sizes,B,T,ragged,kw", [
     (TINY, 2, 5, False, {}), (SMALL, 4, 7, True, {}), (SMALL, 3, 6, True, dict(use_c_v=True)),
     (SMALL, 3, 5, True, dict(no_encoder=True)), (SMALL, 3, 5, True, dict(dec_keep_rate=0.7, dec_lstm_drop=0.8)),
-    (SMALL, 4, 6, False, dict(ann_param=3.0))])
+    (SMALL, 4, 6, False, dict(ann_param=3.0)), (TINY, 3, 5, True, dict(prior="GMM", use_c_v=True)),
+    (TINY, 3, 5, True, dict(prior="AG", use_c_v=True)), (SMALL, 4, 6, True, dict(prior="AG")),
+    (SMALL, 6, 6, False, dict(prior="GMM", use_c_v=True, ann_param=2.0))])
 def test_gradients(sizes, B, T, ragged, kw):
     cfg, eng, grads, gnorm = grads_case(sizes, B, T, ragged, **kw)
     worst = {}

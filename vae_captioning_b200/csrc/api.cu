@@ -60,12 +60,12 @@ int vc_destroy(vc_handle* h) {
   return VC_OK;
 }
 
-int vc_num_params(vc_handle* h) { return h ? (int)h->m.params.size() : set_error(VC_E_ARG, "null handle"); }
+int vc_num_params(vc_handle* h) { return h ? (int)h->m.visible.size() : set_error(VC_E_ARG, "null handle"); }
 
 int vc_param_info(vc_handle* h, int index, const char** name, int32_t* ndim, int64_t* shape, int32_t* trainable) {
   if (h == nullptr) return set_error(VC_E_ARG, "null handle");
-  if (index < 0 || index >= (int)h->m.params.size()) return set_error(VC_E_ARG, "parameter index %d out of range", index);
-  const ParamInfo& p = h->m.params[index];
+  if (index < 0 || index >= (int)h->m.visible.size()) return set_error(VC_E_ARG, "parameter index %d out of range", index);
+  const ParamInfo& p = h->m.params[h->m.visible[index]];
   if (name) *name = p.name.c_str();
   if (ndim) *ndim = p.ndim;
   if (shape) for (int i = 0; i < 4; ++i) shape[i] = p.shape[i];
@@ -87,6 +87,12 @@ int vc_grad_get(vc_handle* h, const char* name, float* dst) {
   if (!h || !name || !dst) return set_error(VC_E_ARG, "vc_grad_get: null argument");
   cudaSetDevice(h->m.device);
   return h->m.grad_get(name, dst);
+}
+
+int vc_set_cluster_means(vc_handle* h, const float* src) {
+  if (!h || !src) return set_error(VC_E_ARG, "vc_set_cluster_means: null argument");
+  cudaSetDevice(h->m.device);
+  return h->m.set_cluster_means(src);
 }
 
 static StepInputs make_inputs(const float* feats, const int32_t* lbl, const int32_t* inp, const int32_t* len,

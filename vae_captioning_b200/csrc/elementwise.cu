@@ -198,20 +198,116 @@ __device__ __forceinline__ float4 philox_normal4(unsigned long long seed, unsign
   return curand_normal4(&st);
 }
 
-__global__ void k_heads_to_musd(const float* __restrict__ heads, long long ld, int zp, float* __restrict__ mu,
-                                float* __restrict__ sd, int N, int Z) {
+// Posterior parameters from the packed head outputs (encoder.py:59-107). heads [N, ld] fp32: head k has its mean at
+// columns [2k*zp, 2k*zp+Z) and its log-std at [(2k+1)*zp, ...).
+//   Normal: mu = mean_0, sd = exp(logstd_0)
+//   GMM   : k = pick[n] (tf.multinomial draw, encoder.py:72-88): mu = mean_k, sd = exp(logstd_k)
+//   AG    : mu = sum_k c_v[n,k] mean_k, sd = sum_k c_v[n,k] exp(logstd_k) (encoder.py:105-107); zero weights are
+//           skipped (exactly equivalent, Q17). Also cm[n,:] = c_v[n,:] @ c_means for the AG KL (main.py:142-143).
+__global__ void k_heads_mix(const float* __restrict__ heads, long long ld, int zp, int prior, const float* __restrict__ c_v,
+                            int K, const int* __restrict__ pick, const float* __restrict__ c_means, float* __restrict__ mu,
+                            float* __restrict__ sd, float* __restrict__ cm, int N, int Z) {
   const long long total = (long long)N * Z;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const long long n = i / Z;
-    const int k = (int)(i - n * Z);
-    mu[i] = heads[n * ld + k];
-    sd[i] = __expf(heads[n * ld + zp + k]);
+    const int z = (int)(i - n * Z);
+    const float* hr = heads + n * ld;
+    if (prior == 2) {
+      float m = 0.f, s = 0.f, c = 0.f;
+      const float* w = c_v + n * K;
+      for (int k = 0; k < K; ++k) {
+        const float wk = w[k];
+        if (wk != 0.f) {
+          m = fmaf(wk, hr[(2 * k) * zp + z], m);
+          s = fmaf(wk, __expf(hr[(2 * k + 1) * zp + z]), s);
+          c = fmaf(wk, c_means[(long long)k * Z + z], c);
+        }
+      }
+      mu[i] = m; sd[i] = s; cm[i] = c;
+    } else {
+      int k = 0;
+      if (prior == 1) { k = pick[n]; k = k < 0 ? 0 : (k >= K ? K - 1 : k); }
+      mu[i] = hr[(2 * k) * zp + z];
+      sd[i] = __expf(hr[(2 * k + 1) * zp + z]);
+    }
   }
 }
-int heads_to_musd(cudaStream_t s, const float* heads, long long ld, int zp, float* mu, float* sd, int N, int Z) {
+int heads_mix(cudaStream_t s, const float* heads, long long ld, int zp, int prior, const float* c_v, int K, const int* pick,
+              const float* c_means, float* mu, float* sd, float* cm, int N, int Z) {
   {
-    ProfScope ps(s, "heads_to_musd");
-    k_heads_to_musd<<<grid_for((long long)N * Z, 256), 256, 0, s>>>(heads, ld, zp, mu, sd, N, Z);
+    ProfScope ps(s, "heads_mix");
+    k_heads_mix<<<grid_for((long long)N * Z, 256), 256, 0, s>>>(heads, ld, zp, prior, c_v, K, pick, c_means, mu, sd, cm, N, Z);
+  }
+  VC_CUDA(cudaGetLastError());
+  return VC_OK;
+}
+
+// Backward of heads_mix: dmu/dsd fp32 [N, Z] -> bf16 gradient of the packed head outputs (pre-zeroed for GMM/AG).
+__global__ void k_heads_mix_bwd(const float* __restrict__ dmu, const float* __restrict__ dsd, const float* __restrict__ heads,
+                                long long ld, int zp, int prior, const float* __restrict__ c_v, int K,
+                                const int* __restrict__ pick, const float* __restrict__ sd,
+                                __nv_bfloat16* __restrict__ dheads, int N, int Z) {
+  const long long total = (long long)N * Z;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long n = i / Z;
+    const int z = (int)(i - n * Z);
+    __nv_bfloat16* dr = dheads + n * ld;
+    const float gm = dmu[i], gs = dsd[i];
+    if (prior == 2) {
+      const float* hr = heads + n * ld;
+      const float* w = c_v + n * K;
+      for (int k = 0; k < K; ++k) {
+        const float wk = w[k];
+        if (wk != 0.f) {
+          dr[(2 * k) * zp + z] = __float2bfloat16(wk * gm);
+          dr[(2 * k + 1) * zp + z] = __float2bfloat16(wk * gs * __expf(hr[(2 * k + 1) * zp + z]));
+        }
+      }
+    } else {
+      int k = 0;
+      if (prior == 1) { k = pick[n]; k = k < 0 ? 0 : (k >= K ? K - 1 : k); }
+      dr[(2 * k) * zp + z] = __float2bfloat16(gm);
+      dr[(2 * k + 1) * zp + z] = __float2bfloat16(gs * sd[i]);  // d/dlogstd = d/dsd * sd
+    }
+  }
+}
+int heads_mix_bwd(cudaStream_t s, const float* dmu, const float* dsd, const float* heads, long long ld, int zp, int prior,
+                  const float* c_v, int K, const int* pick, const float* sd, void* dheads, int N, int Z) {
+  {
+    ProfScope ps(s, "heads_mix_bwd");
+    k_heads_mix_bwd<<<grid_for((long long)N * Z, 256), 256, 0, s>>>(dmu, dsd, heads, ld, zp, prior, c_v, K, pick, sd,
+                                                                   (__nv_bfloat16*)dheads, N, Z);
+  }
+  VC_CUDA(cudaGetLastError());
+  return VC_OK;
+}
+
+// tf.multinomial(logits = c_v, 1) (encoder.py:72, Q3: the cluster *probabilities* are used as logits): one draw per
+// row from softmax(c_v[n, :]) by inverse CDF on a Philox uniform.
+__global__ void k_gmm_pick(const float* __restrict__ c_v, int K, unsigned long long seed, unsigned long long offset,
+                           int* __restrict__ pick, int N) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  curandStatePhilox4_32_10_t st;
+  curand_init(seed ^ 0x9E3779B97F4A7C15ull, (unsigned long long)n, offset, &st);
+  const float u = curand_uniform(&st);  // (0, 1]
+  const float* w = c_v + (long long)n * K;
+  float mx = -INFINITY, tot = 0.f;
+  for (int k = 0; k < K; ++k) mx = fmaxf(mx, w[k]);
+  for (int k = 0; k < K; ++k) tot += __expf(w[k] - mx);
+  float acc = 0.f;
+  int sel = K - 1;
+  for (int k = 0; k < K; ++k) {
+    acc += __expf(w[k] - mx);
+    if (u * tot <= acc) { sel = k; break; }
+  }
+  pick[n] = sel;
+}
+int gmm_pick_clusters(cudaStream_t s, const float* c_v, int K, unsigned long long seed, unsigned long long offset, int* pick,
+                      int N) {
+  {
+    ProfScope ps(s, "gmm_pick");
+    k_gmm_pick<<<(N + 127) / 128, 128, 0, s>>>(c_v, K, seed, offset, pick, N);
   }
   VC_CUDA(cudaGetLastError());
   return VC_OK;

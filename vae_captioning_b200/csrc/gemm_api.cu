@@ -17,6 +17,24 @@ int gemm_store(cudaStream_t stream, const Operand& A, const Operand* A2, long lo
   return launch_gemm(plan, epi, stream);
 }
 
+// out[M, N] (bf16, row pitch ldo) = act(A x B + bias) through the TMA-store epilogue: full 128-byte row segments
+// leave the SM as bulk tensor stores instead of per-thread 64-byte pieces (used for the [T*N, V] logits).
+int gemm_tma_rows(cudaStream_t stream, const Operand& A, const Operand& B, int M, int N, int K, void* out, long long ldo,
+                  const float* bias, int relu, int bn) {
+  if (bn % 64 != 0) return set_error(VC_E_ARG, "gemm_tma_rows: bn=%d must be a multiple of 64", bn);
+  GemmPlan plan;
+  VC_TRY(plan_gemm(&plan, A, nullptr, 0, B, M, N, K, bn, 1));
+  EpiTma epi{};
+  epi.bias = bias;
+  epi.N = N;
+  epi.bn = bn;
+  epi.relu = relu;
+  epi.mode = kRows;
+  epi.alpha = 1.f;
+  VC_TRY(make_tmap_2d(&epi.tm, out, (uint64_t)ldo, (uint64_t)M, (uint64_t)ldo, 64, 32));
+  return launch_gemm(plan, epi, stream);
+}
+
 }  // namespace vc
 
 extern "C" int vc_gemm_bf16(const void* A, int a_mn, long long lda, const void* B, int b_mn, long long ldb, void* out,

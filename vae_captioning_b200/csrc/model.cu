@@ -13,7 +13,7 @@ Model::~Model() {
   if (host_scal) cudaFreeHost(host_scal);
 }
 
-int Model::add_param(const std::string& name, std::vector<int64_t> shape, int region) {
+int Model::add_param(const std::string& name, std::vector<int64_t> shape, int region, bool hidden) {
   ParamInfo pi;
   pi.name = name;
   pi.ndim = (int)shape.size();
@@ -23,8 +23,19 @@ int Model::add_param(const std::string& name, std::vector<int64_t> shape, int re
   pi.region = region;
   pi.trainable = region != 1;
   pi.offset = -1;
+  pi.hidden = hidden;
   index[name] = (int)params.size();
+  if (!hidden) visible.push_back((int)params.size());
   params.push_back(pi);
+  return VC_OK;
+}
+
+int Model::add_view(const std::string& name, std::vector<int64_t> shape, int parent, int64_t parent_off, int64_t ld) {
+  VC_TRY(add_param(name, shape, params[parent].region, false));
+  ParamInfo& pi = params.back();
+  pi.parent = parent;
+  pi.parent_off = parent_off;
+  pi.ld = ld;
   return VC_OK;
 }
 
@@ -64,23 +75,22 @@ int Model::init(const vc_config& c, int dev) {
   if (!cfg.no_encoder) {
     add_param("encoder/multi_rnn_cell/cell_0/lstm_cell/kernel", {E + He, 4 * He}, 0);
     add_param("encoder/multi_rnn_cell/cell_0/lstm_cell/bias", {4 * He}, 0);
-    if (cfg.prior == VC_PRIOR_NORMAL) {
-      add_param("encoder/dense/kernel", {He, Z}, 0);
-      add_param("encoder/dense/bias", {Z}, 0);
-      add_param("encoder/dense_1/kernel", {He, Z}, 0);
-      add_param("encoder/dense_1/bias", {Z}, 0);
-    } else {
-      const char* tag = cfg.prior == VC_PRIOR_GMM ? "gmm_ll" : "ag_ll";
-      char buf[128];
-      for (int k = 0; k < K; ++k) {
-        snprintf(buf, sizeof(buf), "encoder/%s_%d/dense/kernel", tag, k);
-        add_param(buf, {He, Z}, 0);
-        snprintf(buf, sizeof(buf), "encoder/%s_%d/dense/bias", tag, k);
-        add_param(buf, {Z}, 0);
-        snprintf(buf, sizeof(buf), "encoder/%s_%d/dense_1/kernel", tag, k);
-        add_param(buf, {He, Z}, 0);
-        snprintf(buf, sizeof(buf), "encoder/%s_%d/dense_1/bias", tag, k);
-        add_param(buf, {Z}, 0);
+    // posterior heads: two packed blocks + one strided view per TF variable
+    heads_nh = cfg.prior == VC_PRIOR_NORMAL ? 1 : K;
+    heads_cols = heads_nh * 2 * ZP;
+    add_param("__heads/kernel", {He, heads_cols}, 0, true);
+    p_heads_w = (int)params.size() - 1;
+    add_param("__heads/bias", {heads_cols}, 0, true);
+    p_heads_b = (int)params.size() - 1;
+    for (int k = 0; k < heads_nh; ++k) {
+      char scope[64] = "encoder";
+      if (cfg.prior != VC_PRIOR_NORMAL)
+        snprintf(scope, sizeof(scope), "encoder/%s_%d", cfg.prior == VC_PRIOR_GMM ? "gmm_ll" : "ag_ll", k);
+      for (int w = 0; w < 2; ++w) {
+        const int64_t col = ((int64_t)k * 2 + w) * ZP;
+        const std::string layer = std::string(scope) + (w == 0 ? "/dense" : "/dense_1");
+        add_view(layer + "/kernel", {He, Z}, p_heads_w, col, heads_cols);
+        add_view(layer + "/bias", {Z}, p_heads_b, col, 0);
       }
     }
   }
@@ -107,22 +117,24 @@ int Model::init(const vc_config& c, int dev) {
     add_param("cnn/fc2/weights", {4096, 4096}, r);
     add_param("cnn/fc2/biases", {4096}, r);
   }
-  // offsets: region 0 (dense, then embeddings), 64-float tail, region 1, region 2
+  // offsets: region 0 (dense, then embeddings), 64-float tail, region 1, region 2; views resolve to their parent
   int64_t off = 0;
   for (int i = 0; i < (int)params.size(); ++i)
-    if (params[i].region == 0 && i < first_emb) { params[i].offset = off; off += round_up(params[i].count, 64); }
+    if (params[i].region == 0 && i < first_emb && params[i].parent < 0) { params[i].offset = off; off += round_up(params[i].count, 64); }
   n_dense = off;
   for (int i = first_emb; i < (int)params.size(); ++i)
-    if (params[i].region == 0) { params[i].offset = off; off += round_up(params[i].count, 64); }
+    if (params[i].region == 0 && params[i].parent < 0) { params[i].offset = off; off += round_up(params[i].count, 64); }
   n_adam = off;
   off += 64;
   for (auto& p : params)
-    if (p.region == 1) { p.offset = off; off += round_up(p.count, 64); }
+    if (p.region == 1 && p.parent < 0) { p.offset = off; off += round_up(p.count, 64); }
   n_frozen = off - n_adam - 64;
   for (auto& p : params)
-    if (p.region == 2) { p.offset = off; off += round_up(p.count, 64); }
+    if (p.region == 2 && p.parent < 0) { p.offset = off; off += round_up(p.count, 64); }
   n_cnn = off - n_adam - 64 - n_frozen;
   n_total = off;
+  for (auto& p : params)
+    if (p.parent >= 0) p.offset = params[p.parent].offset + p.parent_off;
   VC_TRY(dalloc(&Pf, n_total));
   const int64_t n_opt = cfg.fine_tune ? n_total : n_adam + 64;
   VC_TRY(dalloc(&Gf, n_opt));
@@ -160,10 +172,9 @@ int Model::init(const vc_config& c, int dev) {
   VC_TRY(setup_lstm(dec, "decoder/net/multi_rnn_cell/cell_0/lstm_cell/kernel",
                     "decoder/net/multi_rnn_cell/cell_0/lstm_cell/bias", Hd, 1 + cvstep + (cfg.no_encoder ? 0 : 1)));
   if (!cfg.no_encoder) {
-    heads_cols = (cfg.prior == VC_PRIOR_NORMAL ? 1 : K) * 2 * ZP;
     VC_TRY(dalloc((uint16_t**)&heads_wt, (size_t)heads_cols * He));
     VC_TRY(dalloc((uint16_t**)&heads_nat, (size_t)He * heads_cols));
-    VC_TRY(dalloc(&heads_bias, (size_t)heads_cols));
+    heads_bias = pp(p_heads_b);
     VC_TRY(dalloc((uint16_t**)&z_wt, (size_t)E * S * Z));
     VC_TRY(dalloc((uint16_t**)&z_nat, (size_t)E * S * Z));
     VC_TRY(dalloc((uint16_t**)&enc_emb_h, (size_t)V * E));
@@ -194,6 +205,10 @@ int Model::init(const vc_config& c, int dev) {
     VC_TRY(dalloc(&dkl_dmu, (size_t)N * Z));
     VC_TRY(dalloc(&dkl_dsd, (size_t)N * Z));
     VC_TRY(dalloc(&cm, (size_t)N * Z));
+    VC_TRY(dalloc(&dmu_t, (size_t)N * Z));
+    VC_TRY(dalloc(&dsd_t, (size_t)N * Z));
+    VC_TRY(dalloc(&c_means, (size_t)K * Z));
+    VC_TRY(dalloc(&gmm_pick, (size_t)N));
     VC_TRY(dalloc((uint16_t**)&z, (size_t)S * N * Z));
     VC_TRY(dalloc(&zdec_f, (size_t)N * E));
     VC_TRY(dalloc((uint16_t**)&dzdec_h, (size_t)N * E));
@@ -201,7 +216,6 @@ int Model::init(const vc_config& c, int dev) {
     VC_TRY(dalloc((uint16_t**)&dheads, (size_t)N * heads_cols));
   }
   VC_TRY(dalloc(&scal, 64));
-  VC_TRY(dalloc(&tmp_bias, (size_t)std::max(heads_cols, 4 * std::max(He, Hd)) + 64));
   const size_t img_elems = cfg.fine_tune ? (size_t)224 * 224 * 3 : (size_t)F;
   VC_TRY(dalloc(&st_feats, (size_t)B * img_elems));
   VC_TRY(dalloc(&st_cv, (size_t)N * K));
@@ -215,28 +229,52 @@ int Model::init(const vc_config& c, int dev) {
 }
 
 // ------------------------------------------------------------------------------------------
+// Copies variable i between the flat device buffer `base` (Pf or Gf) and a dense host array; strided for views.
+int Model::copy_var(int i, float* base, float* host_dst, const float* host_src) {
+  const ParamInfo& p = params[i];
+  float* dev = base + p.offset;
+  if (p.ld > 0 && p.ndim == 2) {
+    const size_t w = (size_t)p.shape[1] * sizeof(float);
+    if (host_src)
+      VC_CUDA(cudaMemcpy2D(dev, (size_t)p.ld * sizeof(float), host_src, w, w, (size_t)p.shape[0], cudaMemcpyHostToDevice));
+    else
+      VC_CUDA(cudaMemcpy2D(host_dst, w, dev, (size_t)p.ld * sizeof(float), w, (size_t)p.shape[0], cudaMemcpyDeviceToHost));
+  } else {
+    if (host_src)
+      VC_CUDA(cudaMemcpy(dev, host_src, p.count * sizeof(float), cudaMemcpyHostToDevice));
+    else
+      VC_CUDA(cudaMemcpy(host_dst, dev, p.count * sizeof(float), cudaMemcpyDeviceToHost));
+  }
+  return VC_OK;
+}
+
 int Model::param_set(const char* name, const float* src) {
   const int i = pidx(name);
-  if (i < 0) return set_error(VC_E_ARG, "unknown variable '%s'", name);
-  VC_CUDA(cudaMemcpy(pp(i), src, params[i].count * sizeof(float), cudaMemcpyHostToDevice));
+  if (i < 0 || params[i].hidden) return set_error(VC_E_ARG, "unknown variable '%s'", name);
+  VC_CUDA(cudaDeviceSynchronize());
+  VC_TRY(copy_var(i, Pf, nullptr, src));
   shadows_dirty = true;
   vgg_shadows_dirty = true;
   return VC_OK;
 }
 int Model::param_get(const char* name, float* dst) {
   const int i = pidx(name);
-  if (i < 0) return set_error(VC_E_ARG, "unknown variable '%s'", name);
+  if (i < 0 || params[i].hidden) return set_error(VC_E_ARG, "unknown variable '%s'", name);
   VC_CUDA(cudaDeviceSynchronize());
-  VC_CUDA(cudaMemcpy(dst, pp(i), params[i].count * sizeof(float), cudaMemcpyDeviceToHost));
-  return VC_OK;
+  return copy_var(i, Pf, dst, nullptr);
 }
 int Model::grad_get(const char* name, float* dst) {
   const int i = pidx(name);
-  if (i < 0) return set_error(VC_E_ARG, "unknown variable '%s'", name);
+  if (i < 0 || params[i].hidden) return set_error(VC_E_ARG, "unknown variable '%s'", name);
   if (params[i].region == 1 || (params[i].region == 2 && !cfg.fine_tune))
     return set_error(VC_E_STATE, "variable '%s' has no gradient in this configuration", name);
   VC_CUDA(cudaDeviceSynchronize());
-  VC_CUDA(cudaMemcpy(dst, gp(i), params[i].count * sizeof(float), cudaMemcpyDeviceToHost));
+  return copy_var(i, Gf, dst, nullptr);
+}
+int Model::set_cluster_means(const float* src) {
+  if (c_means == nullptr) return set_error(VC_E_STATE, "this configuration has no encoder (no cluster means)");
+  VC_CUDA(cudaDeviceSynchronize());
+  VC_CUDA(cudaMemcpy(c_means, src, (size_t)cfg.num_clusters * cfg.latent_size * sizeof(float), cudaMemcpyHostToDevice));
   return VC_OK;
 }
 
@@ -255,26 +293,8 @@ int Model::refresh_shadows(cudaStream_t s) {
   if (!cfg.no_encoder) {
     VC_TRY(lstm(enc));
     const int He = cfg.encoder_hidden;
-    const int nh = cfg.prior == VC_PRIOR_NORMAL ? 1 : K;
-    for (int k = 0; k < nh; ++k) {
-      int pk[2], pb[2];
-      if (cfg.prior == VC_PRIOR_NORMAL) {
-        pk[0] = pidx("encoder/dense/kernel"); pb[0] = pidx("encoder/dense/bias");
-        pk[1] = pidx("encoder/dense_1/kernel"); pb[1] = pidx("encoder/dense_1/bias");
-      } else {
-        // the four variables of head k were registered consecutively
-        const char* tag = cfg.prior == VC_PRIOR_GMM ? "gmm_ll" : "ag_ll";
-        char buf[128];
-        snprintf(buf, sizeof(buf), "encoder/%s_%d/dense/kernel", tag, k);
-        pk[0] = pidx(buf); pb[0] = pk[0] + 1; pk[1] = pk[0] + 2; pb[1] = pk[0] + 3;
-      }
-      for (int w = 0; w < 2; ++w) {
-        const int64_t col = ((int64_t)k * 2 + w) * ZP;
-        VC_TRY(transpose_cast(s, pp(pk[w]), (uint16_t*)heads_wt + col * He, He, Z, Z, He, 0, 0));
-        VC_TRY(cast_f32_bf16(s, pp(pk[w]), (uint16_t*)heads_nat + col, He, Z, Z, heads_cols));
-        VC_CUDA(cudaMemcpyAsync(heads_bias + col, pp(pb[w]), Z * sizeof(float), cudaMemcpyDeviceToDevice, s));
-      }
-    }
+    VC_TRY(transpose_cast(s, pp(p_heads_w), heads_wt, He, heads_cols, heads_cols, He, 0, 0));
+    VC_TRY(cast_f32_bf16(s, pp(p_heads_w), heads_nat, He, heads_cols, heads_cols, heads_cols));
     const int pz = pidx("decoder/net/z_rnn/kernel");
     VC_TRY(transpose_cast(s, pp(pz), z_wt, S * Z, E, E, (int64_t)S * Z, 0, 0));
     VC_TRY(cast_f32_bf16(s, pp(pz), z_nat, (int64_t)S * Z, E, E, E));
@@ -428,7 +448,6 @@ int Model::forward(const StepInputs& in, bool write_grad, cudaStream_t s) {
             F = cfg.cnn_feature_size, K = cfg.num_clusters;
   if (B < 1 || B > cfg.max_batch || T < 1 || T > maxT) return set_error(VC_E_SHAPE, "batch/len out of range");
   if (cfg.fine_tune) return set_error(VC_E_STATE, "fine_tune training is not implemented in this build");
-  if (cfg.prior != VC_PRIOR_NORMAL) return set_error(VC_E_STATE, "GMM/AG priors are not implemented in this build");
   const bool has_cv = cfg.use_c_v || cfg.prior != VC_PRIOR_NORMAL;
   if (has_cv && in.c_v == nullptr) return set_error(VC_E_ARG, "this configuration needs cluster vectors (c_v)");
   if (cfg.dec_keep_rate < 1.f && in.rng.emb_keep_dev == nullptr)
@@ -472,9 +491,17 @@ int Model::forward(const StepInputs& in, bool write_grad, cudaStream_t s) {
       EpiStore e{};
       e.out = heads_f; e.ld = heads_cols; e.bias = heads_bias; e.alpha = 1.f;
       ProfTag ptag("heads");
-      VC_TRY(gemm_store(s, A, nullptr, 0, Bw, N, heads_cols, He, e, 64, 1));
+      VC_TRY(gemm_store(s, A, nullptr, 0, Bw, N, heads_cols, He, e, heads_cols >= 1024 ? 256 : 64, 1));
     }
-    VC_TRY(heads_to_musd(s, heads_f, heads_cols, ZP, mu, sd, N, Z));
+    last_pick = nullptr;
+    if (cfg.prior == VC_PRIOR_GMM) {  // encoder.py:72: explicit draw (parity mode) or in-kernel Philox
+      last_pick = in.rng.gmm_cluster_dev;
+      if (last_pick == nullptr) {
+        VC_TRY(gmm_pick_clusters(s, in.c_v, K, in.rng.seed, (unsigned long long)in.global_step, gmm_pick, N));
+        last_pick = gmm_pick;
+      }
+    }
+    VC_TRY(heads_mix(s, heads_f, heads_cols, ZP, cfg.prior, in.c_v, K, last_pick, c_means, mu, sd, cm, N, Z));
     VC_TRY(kl_rows(s, mu, sd, cm, cfg.prior, kl_row, dkl_dmu, dkl_dsd, scal + 3, N, Z));
     VC_TRY(sample_z(s, mu, sd, in.rng.eps_dev, in.rng.seed, (unsigned long long)in.global_step, z, nullptr, S, (long long)N * Z));
     // p(x | z, I): z reshaped row-major [S,N,Z] -> [N, S*Z] (Q1), decoder.py:109-113
@@ -496,10 +523,8 @@ int Model::forward(const StepInputs& in, bool write_grad, cudaStream_t s) {
   VC_TRY(lstm_forward(dec, N, T, in.len, Out, cfg.dec_lstm_drop < 1.f ? in.rng.out_keep_dev : nullptr, s));
   {
     Operand A{Out, (long long)T * N, Hd, Hd, false}, Bw{wo_t, V, Hd, Hd, false};
-    EpiStore e{};
-    e.out = logits; e.ld = VP; e.bias = pp(pidx("decoder/rnn_logits/bias")); e.out_bf16 = 1; e.alpha = 1.f;
     ProfTag ptag("logits_fwd");
-    VC_TRY(gemm_store(s, A, nullptr, 0, Bw, T * N, V, Hd, e, 256, 1));
+    VC_TRY(gemm_tma_rows(s, A, Bw, T * N, V, Hd, logits, VP, pp(pidx("decoder/rnn_logits/bias")), 0, 256));
   }
   // masked cross-entropy (main.py:152-158); AG differentiates the sum of an [N] lower bound (Q2)
   VC_TRY(count_mask(s, in.cap_lbl, (long long)N * T, scal + 2));
@@ -572,28 +597,29 @@ int Model::backward(const StepInputs& in, cudaStream_t s) {
     const float ann = annealing_coeff(cfg, in.global_step);
     const float kl_scale = cfg.prior == VC_PRIOR_AG ? ann / 10.f : ann / (10.f * N);
     VC_TRY(dz_reduce(s, dz, in.rng.eps_dev, in.rng.seed, (unsigned long long)in.global_step, sd, dkl_dmu, dkl_dsd, kl_scale,
-                     dheads, heads_cols, ZP, nullptr, nullptr, S, N, Z));
+                     nullptr, heads_cols, ZP, dmu_t, dsd_t, S, N, Z));
+    if (cfg.prior != VC_PRIOR_NORMAL) VC_CUDA(cudaMemsetAsync(dheads, 0, (size_t)N * heads_cols * 2, s));
+    VC_TRY(heads_mix_bwd(s, dmu_t, dsd_t, heads_f, heads_cols, ZP, cfg.prior, in.c_v, K, last_pick, sd, dheads, N, Z));
     const uint16_t* hT = (uint16_t*)enc.Hs + (size_t)(enc.pre + T) * N * He;
     {
+      ProfTag ptag("heads_bwd");
       Operand A{dheads, N, heads_cols, heads_cols, false}, Bw{heads_nat, He, heads_cols, heads_cols, false};
       EpiStore e{};
       e.out = enc.dh_carry; e.ld = He; e.alpha = 1.f;
-      {
-        ProfTag ptag("heads_bwd");
+      if (heads_cols > 4096) {  // long contraction, few output tiles: split-K
+        VC_CUDA(cudaMemsetAsync(enc.dh_carry, 0, (size_t)N * He * sizeof(float), s));
+        e.atomic = 1;
+        const int tiles = ((N + 127) / 128) * ((He + 63) / 64);
+        VC_TRY(gemm_store(s, A, nullptr, 0, Bw, N, He, heads_cols, e, 64, std::max(1, num_sms() / tiles)));
+      } else {
         VC_TRY(gemm_store(s, A, nullptr, 0, Bw, N, He, heads_cols, e, 64, 1));
       }
-      VC_CUDA(cudaMemsetAsync(tmp_bias, 0, (size_t)heads_cols * sizeof(float), s));
-      VC_TRY(colsum_bf16(s, dheads, N, heads_cols, heads_cols, tmp_bias));
-      const int pk[2] = {pidx("encoder/dense/kernel"), pidx("encoder/dense_1/kernel")};
-      const int pb[2] = {pidx("encoder/dense/bias"), pidx("encoder/dense_1/bias")};
-      for (int w = 0; w < 2; ++w) {
-        Operand A2{hT, N, He, He, true}, B2{(uint16_t*)dheads + (size_t)w * ZP, N, Z, heads_cols, true};
-        EpiStore e2{};
-        e2.out = gp(pk[w]); e2.ld = Z; e2.alpha = 1.f;
-        ProfTag ptag("heads_bwd");
-        VC_TRY(gemm_store(s, A2, nullptr, 0, B2, He, Z, N, e2, 64, 1));
-        VC_CUDA(cudaMemcpyAsync(gp(pb[w]), tmp_bias + (size_t)w * ZP, Z * sizeof(float), cudaMemcpyDeviceToDevice, s));
-      }
+      // dW[He, heads_cols] = h_T^T x dheads, written straight into the packed gradient block
+      Operand A2{hT, N, He, He, true}, B2{dheads, N, heads_cols, heads_cols, true};
+      EpiStore e2{};
+      e2.out = gp(p_heads_w); e2.ld = heads_cols; e2.alpha = 1.f;
+      VC_TRY(gemm_store(s, A2, nullptr, 0, B2, He, heads_cols, N, e2, heads_cols >= 1024 ? 256 : 64, 1));
+      VC_TRY(colsum_bf16(s, dheads, N, heads_cols, heads_cols, gp(p_heads_b)));
     }
     VC_CUDA(cudaMemsetAsync(enc.dc_carry, 0, (size_t)N * He * sizeof(float), s));
     VC_TRY(lstm_backward(enc, N, T, in.len, nullptr, nullptr, s));

@@ -17,6 +17,10 @@ struct ParamInfo {
   int64_t offset;  // element offset into the flat fp32 buffers
   int region;      // 0: clipped Adam (non-CNN), 1: frozen (created but never updated), 2: CNN
   bool trainable;
+  bool hidden = false;     // packed block that backs several variables (not listed by vc_param_info)
+  int parent = -1;         // >= 0: this variable is a view into params[parent] ...
+  int64_t parent_off = 0;  // ... starting at this element offset ...
+  int64_t ld = 0;          // ... with this row pitch (0 = contiguous)
 };
 
 struct LstmNet {
@@ -60,6 +64,7 @@ class Model {
   int device = 0;
   int maxN = 0, maxT = 0;
   std::vector<ParamInfo> params;
+  std::vector<int> visible;  // indices of the variables the Saver surface lists (creation order)
   std::map<std::string, int> index;
   int64_t n_adam = 0, n_dense = 0, n_frozen = 0, n_cnn = 0, n_total = 0;  // element counts (padded)
   float *Pf = nullptr, *Gf = nullptr, *Mf = nullptr, *Vf = nullptr;  // flat fp32: params, grads, Adam m, v
@@ -73,7 +78,14 @@ class Model {
   // --- shadows (bf16 unless noted)
   void *imf_wt = nullptr, *cv_wt = nullptr, *heads_wt = nullptr, *heads_nat = nullptr, *z_wt = nullptr, *z_nat = nullptr,
        *wo_t = nullptr, *wo_nat = nullptr, *enc_emb_h = nullptr, *dec_emb_h = nullptr;
-  float* heads_bias = nullptr;  // fp32 [2*ZP]
+  // The posterior heads (encoder.py:59-107) are packed: kernel block [He, heads_cols] and bias block [heads_cols],
+  // head k's mean at columns [2k*ZP, 2k*ZP+Z), its log-std at [(2k+1)*ZP, ...). The TF variables
+  // encoder/{dense,dense_1,gmm_ll_k/...,ag_ll_k/...} are strided views into the two blocks.
+  int p_heads_w = -1, p_heads_b = -1, heads_nh = 0;
+  float* heads_bias = nullptr;  // = pp(p_heads_b)
+  float* c_means = nullptr;     // fp32 [K, Z] cluster means (utils/vae_utils.py:20-30), AG prior
+  int32_t* gmm_pick = nullptr;  // [N] cluster drawn per row (encoder.py:72) when not given explicitly
+  const int32_t* last_pick = nullptr;
   int ZP = 0, VP = 0, KP = 0, heads_cols = 0;
 
   LstmNet enc, dec;
@@ -83,7 +95,7 @@ class Model {
        *dzdec_h = nullptr, *dimf_h = nullptr, *dcv_h = nullptr;
   float *imf_f = nullptr, *cv_f = nullptr, *heads_f = nullptr, *mu = nullptr, *sd = nullptr, *kl_row = nullptr,
         *dkl_dmu = nullptr, *dkl_dsd = nullptr, *zdec_f = nullptr, *dOut = nullptr, *dz = nullptr, *ce_row = nullptr,
-        *scal = nullptr, *tmp_bias = nullptr, *cm = nullptr;
+        *scal = nullptr, *cm = nullptr, *dmu_t = nullptr, *dsd_t = nullptr;
   // staging for host-pointer entry points
   float *st_feats = nullptr, *st_cv = nullptr;
   int32_t *st_lbl = nullptr, *st_in = nullptr, *st_len = nullptr;
@@ -109,6 +121,8 @@ class Model {
   int param_set(const char* name, const float* src);
   int param_get(const char* name, float* dst);
   int grad_get(const char* name, float* dst);
+  int copy_var(int i, float* base, float* host_dst, const float* host_src);
+  int set_cluster_means(const float* src_host);
 
   int refresh_shadows(cudaStream_t s);
   int forward(const StepInputs& in, bool write_grad, cudaStream_t s);
@@ -132,7 +146,8 @@ class Model {
     *p = reinterpret_cast<T*>(q);
     return VC_OK;
   }
-  int add_param(const std::string& name, std::vector<int64_t> shape, int region);
+  int add_param(const std::string& name, std::vector<int64_t> shape, int region, bool hidden = false);
+  int add_view(const std::string& name, std::vector<int64_t> shape, int parent, int64_t parent_off, int64_t ld);
   int lstm_forward(LstmNet& L, int N, int T, const int32_t* len, void* out, const float* out_keep, cudaStream_t s);
   int lstm_backward(LstmNet& L, int N, int T, const int32_t* len, const float* d_out, const float* out_keep,
                     cudaStream_t s);

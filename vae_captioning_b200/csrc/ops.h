@@ -8,6 +8,9 @@ namespace vc {
 int gemm_store(cudaStream_t stream, const Operand& A, const Operand* A2, long long a2_at, const Operand& B, int M,
                int N, int K, const EpiStore& epi, int bn, int splits);
 
+int gemm_tma_rows(cudaStream_t stream, const Operand& A, const Operand& B, int M, int N, int K, void* out, long long ldo,
+                  const float* bias, int relu, int bn);
+
 // lstm.cu ----------------------------------------------------------------------------------
 struct LstmFwdArgs {
   const void* x;         // bf16 [N, E] input of this step
@@ -57,7 +60,12 @@ int embed_gather(cudaStream_t s, const void* table, const int* tok, void* X, con
                  int N, int T, int E, int V);
 int embed_scatter(cudaStream_t s, const float* dX, const int* tok, float* gtable, const float* keep_mask, float inv_keep,
                   float* normsq, int N, int T, int E, int V);
-int heads_to_musd(cudaStream_t s, const float* heads, long long ld, int zp, float* mu, float* sd, int N, int Z);
+int heads_mix(cudaStream_t s, const float* heads, long long ld, int zp, int prior, const float* c_v, int K, const int* pick,
+              const float* c_means, float* mu, float* sd, float* cm, int N, int Z);
+int heads_mix_bwd(cudaStream_t s, const float* dmu, const float* dsd, const float* heads, long long ld, int zp, int prior,
+                  const float* c_v, int K, const int* pick, const float* sd, void* dheads, int N, int Z);
+int gmm_pick_clusters(cudaStream_t s, const float* c_v, int K, unsigned long long seed, unsigned long long offset, int* pick,
+                      int N);
 int kl_rows(cudaStream_t s, const float* mu, const float* sd, const float* cm, int prior, float* kl_row, float* dkl_dmu,
             float* dkl_dsd, float* kl_sum, int N, int Z);
 int sample_z(cudaStream_t s, const float* mu, const float* sd, const float* eps, unsigned long long seed,

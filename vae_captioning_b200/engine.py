@@ -116,6 +116,7 @@ class Engine(object):
         lib.vc_train_step_images.argtypes = step_args + [ctypes.POINTER(VcStepOut), vp]
         lib.vc_forward_backward_dev.argtypes = step_args + [vp]
         lib.vc_eval_step.argtypes = [vp, vp, vp, vp, vp, vp, ci, ci, ctypes.POINTER(VcRng), ctypes.POINTER(VcStepOut), vp]
+        lib.vc_set_cluster_means.argtypes = [vp, vp]
         lib.vc_grad_buffer.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(ctypes.c_int64)]
         lib.vc_apply_gradients.argtypes = [vp, ctypes.c_float, ctypes.POINTER(VcStepOut), vp]
         lib.vc_forward_debug.argtypes = [vp] * 7
@@ -175,6 +176,13 @@ class Engine(object):
         a = np.empty(self._shape(name), dtype=np.float32)
         L.check(self.lib.vc_grad_get(self._h, name.encode(), _np_ptr(a)))
         return a
+
+    def set_cluster_means(self, c_means):
+        """c_means [num_clusters, latent_size]: init_clusters() of the reference (utils/vae_utils.py:6-31), AG prior."""
+        a = _f32(c_means)
+        if a.shape != (self.cfg.num_clusters, self.cfg.latent_size):
+            raise ValueError("cluster means must be [%d, %d], got %s" % (self.cfg.num_clusters, self.cfg.latent_size, a.shape))
+        L.check(self.lib.vc_set_cluster_means(self._h, _np_ptr(a)))
 
     def load_state(self, state):
         """state: {tf_name: array}. Unknown names are rejected, missing names keep their value."""
