@@ -154,6 +154,41 @@ int vc_vgg_forward_dev(vc_handle* h, const float* images_dev, float* fc2_dev, in
 int vc_vgg_keep_activations(vc_handle* h, int on);
 int vc_vgg_activation(vc_handle* h, const char* layer, float* dst_host);
 
+/* ---- generation (vae_model/decoder.py:145-320, ops/inference.py:16-50). The reference issues one
+ * sess.run([sample, out_state], feed) per token per beam at batch 1; these calls run the whole loop for a batch of B
+ * images on the device. feats_host fp32 [B, 4096] (features are NOT tiled in generation, main.py:84), c_v_host fp32
+ * [B, 90] or NULL. rng->eps_dev (optional, device) fp32 [B, S, Z]: the N(0,1) draws of zs.Normal('z', z_mean, std)
+ * (decoder.py:72-74); NULL -> Philox(rng->seed). bos / eos: data_dict.word2idx['<BOS>'] / ['<EOS>'].
+ *
+ * vc_decode_greedy = Decoder.online_inference (decoder.py:145-201): mode 0 'greedy' (argmax; temperature is a no-op,
+ * SURVEY Q10), mode 1 'sample' (tf.multinomial(logits / temperature)). out_tokens_host int32 [B, max_len] (zero
+ * padded, the generated ids = cap_raw), out_len_host [B].
+ * vc_decode_beam = Decoder.beam_search (decoder.py:203-320) with utils/top_n.py container semantics (heap order,
+ * tie handling), <BOS> fed twice (Q9), p < 1e-12 skipped, score / len^len_norm only for completed captions, never
+ * mixing complete and partial. Per image the beams sorted by score: out_tokens_host int32 [B, beam, max_len]
+ * (sentence incl. <BOS>/<EOS>, zero padded), out_len_host / out_score_host [B, beam], out_n_host [B] beams returned
+ * (beams[0] is the caption; all of them = ret_beams). */
+int vc_decode_greedy(vc_handle* h, const float* feats_host, const float* c_v_host, int B, int max_len, int mode,
+                     const vc_rng* rng, int bos, int eos, int32_t* out_tokens_host, int32_t* out_len_host, void* stream);
+int vc_decode_beam(vc_handle* h, const float* feats_host, const float* c_v_host, int B, int beam, int max_len, float len_norm,
+                   const vc_rng* rng, int bos, int eos, int32_t* out_tokens_host, int32_t* out_len_host,
+                   float* out_score_host, int32_t* out_n_host, void* stream);
+/* The reference's own granularity for callers that keep their Python loop: vc_decode_begin computes the state the graph
+ * uses when `initial_state` is left at its placeholder default (utils/rnn_model.py:7-21, decoder.py:96-114);
+ * vc_decode_step is one sess.run([sample, out_state], {captions: tokens[M,1], in_state: current}) for the M rows:
+ * probs_host fp32 [M, V] = tf.nn.softmax(x_logits) (nullable), state advanced in place;
+ * vc_decode_state_get / _set read or feed (c, h) fp32 [M, H] each. */
+int vc_decode_begin(vc_handle* h, const float* feats_host, const float* c_v_host, int B, const vc_rng* rng, void* stream);
+int vc_decode_step(vc_handle* h, const int32_t* tokens_host, int M, float* probs_host, void* stream);
+int vc_decode_state_get(vc_handle* h, float* c_host, float* h_host, void* stream);
+int vc_decode_state_set(vc_handle* h, const float* c_host, const float* h_host, void* stream);
+/* Host-only (no GPU): the beam bookkeeping above driven by a callback `step(user, token, state_in (-1 = initial),
+ * probs_out[V]) -> state id`; pins the container semantics against the reference's Decoder.beam_search. Outputs as
+ * vc_decode_beam for one image. */
+int vc_beam_search_host(int (*step)(void* user, int token, int state_in, float* probs_out), void* user, int V, int beam,
+                        int max_len, int bos, int eos, float len_norm, int32_t* out_tokens, int32_t* out_len,
+                        float* out_score, int32_t* out_n);
+
 #ifdef __cplusplus
 }
 #endif

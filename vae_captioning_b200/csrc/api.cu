@@ -234,6 +234,72 @@ int vc_vgg_forward(vc_handle* h, const float* images_host, float* fc2_host, int 
   VC_GUARD_END
 }
 
+int vc_decode_greedy(vc_handle* h, const float* feats_host, const float* c_v_host, int B, int max_len, int mode,
+                     const vc_rng* rng, int bos, int eos, int32_t* out_tokens_host, int32_t* out_len_host, void* stream) {
+  VC_GUARD_BEGIN
+  if (!h || !feats_host || !out_tokens_host || !out_len_host) return set_error(VC_E_ARG, "vc_decode_greedy: null argument");
+  if (mode != 0 && mode != 1) return set_error(VC_E_ARG, "vc_decode_greedy: mode must be 0 (greedy) or 1 (sample)");
+  Model& m = h->m;
+  cudaSetDevice(m.device);
+  cudaStream_t s = (cudaStream_t)stream;
+  const float *fd = nullptr, *cd = nullptr;
+  VC_TRY(m.decode_stage(feats_host, c_v_host, B, 1, &fd, &cd, s));
+  return m.decode_greedy(fd, cd, B, max_len, mode, rng, bos, eos, out_tokens_host, out_len_host, s);
+  VC_GUARD_END
+}
+
+int vc_decode_beam(vc_handle* h, const float* feats_host, const float* c_v_host, int B, int beam, int max_len, float len_norm,
+                   const vc_rng* rng, int bos, int eos, int32_t* out_tokens_host, int32_t* out_len_host,
+                   float* out_score_host, int32_t* out_n_host, void* stream) {
+  VC_GUARD_BEGIN
+  if (!h || !feats_host || !out_tokens_host || !out_len_host || !out_score_host || !out_n_host)
+    return set_error(VC_E_ARG, "vc_decode_beam: null argument");
+  Model& m = h->m;
+  cudaSetDevice(m.device);
+  cudaStream_t s = (cudaStream_t)stream;
+  const float *fd = nullptr, *cd = nullptr;
+  VC_TRY(m.decode_stage(feats_host, c_v_host, B, beam, &fd, &cd, s));
+  return m.decode_beam(fd, cd, B, beam, max_len, len_norm, rng, bos, eos, out_tokens_host, out_len_host, out_score_host,
+                       out_n_host, s);
+  VC_GUARD_END
+}
+
+int vc_decode_begin(vc_handle* h, const float* feats_host, const float* c_v_host, int B, const vc_rng* rng, void* stream) {
+  VC_GUARD_BEGIN
+  if (!h || !feats_host) return set_error(VC_E_ARG, "vc_decode_begin: null argument");
+  Model& m = h->m;
+  cudaSetDevice(m.device);
+  cudaStream_t s = (cudaStream_t)stream;
+  const float *fd = nullptr, *cd = nullptr;
+  VC_TRY(m.decode_stage(feats_host, c_v_host, B, 1, &fd, &cd, s));
+  return m.decode_open(fd, cd, B, rng, s);
+  VC_GUARD_END
+}
+
+int vc_decode_step(vc_handle* h, const int32_t* tokens_host, int M, float* probs_host, void* stream) {
+  VC_GUARD_BEGIN
+  if (!h || !tokens_host) return set_error(VC_E_ARG, "vc_decode_step: null argument");
+  cudaSetDevice(h->m.device);
+  return h->m.decode_step(tokens_host, M, probs_host, (cudaStream_t)stream);
+  VC_GUARD_END
+}
+
+int vc_decode_state_get(vc_handle* h, float* c_host, float* h_host, void* stream) {
+  VC_GUARD_BEGIN
+  if (!h || !c_host || !h_host) return set_error(VC_E_ARG, "vc_decode_state_get: null argument");
+  cudaSetDevice(h->m.device);
+  return h->m.decode_state(c_host, h_host, nullptr, nullptr, (cudaStream_t)stream);
+  VC_GUARD_END
+}
+
+int vc_decode_state_set(vc_handle* h, const float* c_host, const float* h_host, void* stream) {
+  VC_GUARD_BEGIN
+  if (!h || !c_host || !h_host) return set_error(VC_E_ARG, "vc_decode_state_set: null argument");
+  cudaSetDevice(h->m.device);
+  return h->m.decode_state(nullptr, nullptr, c_host, h_host, (cudaStream_t)stream);
+  VC_GUARD_END
+}
+
 int vc_vgg_activation(vc_handle* h, const char* layer, float* dst_host) {
   VC_GUARD_BEGIN
   if (!h || !layer || !dst_host) return set_error(VC_E_ARG, "vc_vgg_activation: null argument");

@@ -412,4 +412,154 @@ struct EpiTma {
   }
 };
 
+// ------------------------------------------------------------------------------------------
+// 3x3 SAME convolution for Cin == 64 with the input patch staged ONCE per tile ("halo" form).
+//
+// gemm_tc_kernel's A_CONV3x3 mode re-reads the 128-pixel input patch from L2 for each of the 9 filter taps
+// (9 x 16 KB per tile) and the [bn, 576] filter slice for every tile; at Cout <= 128 that operand traffic, not the
+// tensor pipe, bounds the layer (conv1_2 / conv2_1: ~7 TB/s of L2->SM traffic). Here a tile is 8 (w) x 16 (h) output
+// pixels; one 4-D TMA box {64 ch, 16 w, 18 h} brings the patch plus its halo into shared memory with a 16-row line
+// pitch (128-byte swizzled rows, OOB zero fill = SAME padding), and the 9 taps are 9 shifted UMMA descriptors into
+// that buffer: start = base + (fr*16 + fs)*128 B, 8-row groups (one image row of 8 pixels) SBO = 2048 B apart, so
+// every group has the same swizzle phase (fs), which goes into the descriptor's base-offset field. The 64-output-
+// channel filter slice (9 x 8 KB) is loaded once per CTA and stays resident. Epilogue: EpiTma (bias + ReLU + pool).
+constexpr int kHaloLineRows = 16;                               // halo rows (pixels) per image line in smem
+constexpr int kHaloLines = 18;                                  // 16 output lines + 2
+constexpr int kHaloBytes = kHaloLineRows * kHaloLines * 128;    // 36,864
+constexpr int kHaloWBytes = 9 * 64 * 128;                       // resident filter slice: 9 taps x [64 x 64] bf16
+constexpr int kHaloStages = 3;
+
+__host__ inline int conv_halo_smem_bytes(int epi_bytes) {
+  return kHaloWBytes + kHaloStages * kHaloBytes + epi_bytes + 1024 + 256;
+}
+
+template <class Epi>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmCore g,
+                 const __grid_constant__ Epi epi, const int use_base_offset) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* wres = smem;
+  uint8_t* halo = smem + kHaloWBytes;
+  uint8_t* epi_smem = halo + kHaloStages * kHaloBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_smem + Epi::kSmemBytes);
+  uint64_t* hfull = bars;
+  uint64_t* hempty = bars + kHaloStages;
+  uint64_t* tfull = bars + 2 * kHaloStages;
+  uint64_t* tempty = bars + 2 * kHaloStages + 2;
+  uint64_t* wfull = bars + 2 * kHaloStages + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kHaloStages + 5);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  // static schedule: a CTA keeps one n-tile (its resident filter slice) and strides over the m-tiles
+  const int n_blk = blockIdx.x % g.n_tiles;
+  const int m_first = blockIdx.x / g.n_tiles;
+  const int m_step = gridDim.x / g.n_tiles;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < kHaloStages; ++i) {
+      mbar_init(&hfull[i], 1);
+      mbar_init(&hempty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 4);
+    }
+    mbar_init(wfull, 1);
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(wfull, kHaloWBytes);
+      for (int tap = 0; tap < 9; ++tap) tma_load_2d(wres + tap * 8192, &tmB, wfull, tap * 64, n_blk * 64);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int m_blk = m_first; m_blk < g.m_tiles; m_blk += m_step) {
+        const PatchOrigin po = conv_patch_origin(g, m_blk, 0);
+        mbar_wait(&hempty[stage], phase ^ 1);
+        mbar_expect_tx(&hfull[stage], kHaloBytes);
+        tma_load_4d(halo + stage * kHaloBytes, &tmA, &hfull[stage], 0, po.w - 1, po.h - 1, po.n);
+        if (++stage == kHaloStages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(kBM, 64, false, false);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      mbar_wait(wfull, 0);
+      tc_fence_after();
+      const uint32_t wbase = smem_u32(wres);
+      for (int m_blk = m_first; m_blk < g.m_tiles; m_blk += m_step) {
+        mbar_wait(&tempty[acc], acc_phase ^ 1);
+        mbar_wait(&hfull[stage], phase);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * kAccStride;
+        const uint32_t hbase = smem_u32(halo + stage * kHaloBytes);
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+          const int fr = tap / 3, fs = tap - fr * 3;
+          uint64_t adesc = make_smem_desc(hbase + (fr * kHaloLineRows + fs) * 128, 16u, kHaloLineRows * 128);
+          if (use_base_offset) adesc |= static_cast<uint64_t>(fs) << 49;
+          const uint64_t bdesc = make_smem_desc(wbase + tap * 8192, 16u, 1024);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(d_tmem, adesc + uint64_t(k * 2), bdesc + uint64_t(k * 2), idesc, (tap > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(&hempty[stage]);
+        umma_commit(&tfull[acc]);
+        if (++stage == kHaloStages) {
+          stage = 0;
+          phase ^= 1;
+        }
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    const int q = warp & 3;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    int epi_phase = 0;
+    uint8_t* warp_smem = epi_smem + q * (Epi::kSmemBytes / 4);
+    for (int m_blk = m_first; m_blk < g.m_tiles; m_blk += m_step) {
+      TileCoord t;
+      t.m_blk = m_blk; t.n_blk = n_blk; t.split = 0; t.kb_begin = 0; t.kb_end = 9;
+      mbar_wait(&tfull[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + acc * kAccStride + (uint32_t(q * 32) << 16);
+      epi(taddr, g, t, q * 32 + lane, warp_smem, epi_phase);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+    epi.finish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<512>(tmem_base);
+}
+
 }  // namespace vc

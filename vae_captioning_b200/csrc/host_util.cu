@@ -1,5 +1,6 @@
 #include "host_util.h"
 #include <cstdarg>
+#include <cstdlib>
 #include <atomic>
 #include <mutex>
 #include <vector>
@@ -200,6 +201,53 @@ int conv_geometry(ConvGeom* g, int W, int H, int Nimg, int Cin, int Cout) {
   else if (W % 4 == 0 && H % 4 == 0) { g->pw = 4; g->ph = 4; g->pn = 2; g->tw = 1; g->th = 1; }    // 4 x 4 x 8
   else if (W % 2 == 0 && H % 2 == 0) { g->pw = 2; g->ph = 2; g->pn = 8; g->tw = 1; g->th = 1; }    // 2 x 2 x 32
   else return set_error(VC_E_SHAPE, "conv_geometry: %dx%d feature map has odd extent", W, H);
+  return VC_OK;
+}
+
+bool conv_halo_applicable(int W, int H, int Cin, int Cout) {
+  static int enabled = -1;
+  if (enabled < 0) {
+    const char* e = getenv("VC_CONV_HALO");
+    enabled = (e == nullptr) ? 0 : atoi(e);
+  }
+  return enabled && Cin == 64 && Cout % 64 == 0 && W % 8 == 0 && H % 16 == 0;
+}
+
+int halo_base_offset_mode() {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("VC_HALO_BASE_OFFSET");
+    mode = (e == nullptr) ? 1 : atoi(e);
+  }
+  return mode;
+}
+
+int conv_halo_geometry(ConvGeom* g, int W, int H, int Nimg, int Cin, int Cout) {
+  g->W = W; g->H = H; g->Nimg = Nimg; g->Cin = Cin; g->Cout = Cout;
+  g->pw = 8; g->ph = 4; g->pn = 1; g->tw = 1; g->th = 4;  // 8 x 16 x 1 tiles, one 8 x 4 patch per epilogue warp
+  return VC_OK;
+}
+
+int plan_conv_halo(GemmPlan* p, const void* in, const void* wt, const ConvGeom& cg) {
+  if (cg.Cin != 64 || cg.Cout % 64 != 0 || cg.W % 8 != 0 || cg.H % 16 != 0)
+    return set_error(VC_E_SHAPE, "plan_conv_halo: unsupported layer %dx%d Cin=%d Cout=%d", cg.W, cg.H, cg.Cin, cg.Cout);
+  memset(p, 0, sizeof(*p));
+  GemmCore& g = p->core;
+  g.pw = cg.pw; g.ph = cg.ph; g.pn = cg.pn; g.tw = cg.tw; g.th = cg.th;
+  g.tiles_w = cg.W / 8;
+  g.tiles_h = cg.H / 16;
+  g.m_tiles = g.tiles_w * g.tiles_h * cg.Nimg;
+  g.n_tiles = cg.Cout / 64;
+  g.cpk = 1;
+  g.k_blocks = 9;
+  g.splits = 1;
+  g.bn = 64;
+  g.stages = kHaloStages;
+  g.a_mode = A_CONV3x3;
+  g.a_switch = -1;
+  VC_TRY(make_tmap_nhwc(&p->tmA, in, cg.Cin, cg.W, cg.H, cg.Nimg, kHaloLineRows, kHaloLines, 1));
+  p->tmA2 = p->tmA;
+  VC_TRY(make_tmap_2d(&p->tmB, wt, 9ull * cg.Cin, cg.Cout, 9ull * cg.Cin, 64, 64));
   return VC_OK;
 }
 

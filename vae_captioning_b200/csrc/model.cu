@@ -9,6 +9,7 @@ namespace vc {
 static inline int64_t round_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
 
 Model::~Model() {
+  decode_release();
   for (void* p : allocs) cudaFree(p);
   if (host_scal) cudaFreeHost(host_scal);
 }

@@ -47,6 +47,8 @@ struct VggLayer {
   void* pooled = nullptr;  // bf16 NHWC [B, hw/2, hw/2, cout] when pool
 };
 
+struct DecodeWs;  // decode.cu
+
 struct StepInputs {
   const float* feats;     // device fp32 [B, F] (or images when fine_tune)
   const int32_t* cap_lbl; // device [N, T]
@@ -112,6 +114,23 @@ class Model {
   int vgg_conv_layer(int l, const void* in, int B, bool fuse_pool, cudaStream_t s);
   int vgg_forward(const float* images, float* fc2_out, int B, bool keep_unpooled, const float* fc_keep, cudaStream_t s);
   int vgg_activation(const char* layer, float* dst_host);
+
+  // --- generation (decode.cu)
+  DecodeWs* dws = nullptr;
+  int decode_reserve(int B, int beam);
+  void decode_release();
+  int decode_stage(const float* feats_host, const float* c_v_host, int B, int beam, const float** feats_dev,
+                   const float** c_v_dev, cudaStream_t s);
+  int decode_begin(const float* feats_dev, const float* c_v_dev, int B, const vc_rng* rng, cudaStream_t s);
+  int decode_advance(int M, cudaStream_t s);
+  int decode_greedy(const float* feats_dev, const float* c_v_dev, int B, int max_len, int mode, const vc_rng* rng, int bos,
+                    int eos, int32_t* out_tokens_host, int32_t* out_len_host, cudaStream_t s);
+  int decode_beam(const float* feats_dev, const float* c_v_dev, int B, int beam, int max_len, float len_norm,
+                  const vc_rng* rng, int bos, int eos, int32_t* out_tokens_host, int32_t* out_len_host,
+                  float* out_score_host, int32_t* out_n_host, cudaStream_t s);
+  int decode_open(const float* feats_dev, const float* c_v_dev, int B, const vc_rng* rng, cudaStream_t s);
+  int decode_step(const int32_t* tok_host, int M, float* probs_host, cudaStream_t s);
+  int decode_state(float* c_host, float* h_host, const float* c_in, const float* h_in, cudaStream_t s);
 
   std::vector<void*> allocs;
 

@@ -165,8 +165,15 @@ int Model::vgg_conv_layer(int l, const void* in, int B, bool fuse_pool, cudaStre
     return launch_gemm(plan, epi, s);
   }
   ConvGeom g;
-  VC_TRY(conv_geometry(&g, L.hw, L.hw, B, L.cin, L.cout));
-  VC_TRY(plan_conv(&plan, in, L.wt, g, bn));
+  const bool halo = conv_halo_applicable(L.hw, L.hw, L.cin, L.cout);
+  if (halo) {
+    VC_TRY(conv_halo_geometry(&g, L.hw, L.hw, B, L.cin, L.cout));
+    VC_TRY(plan_conv_halo(&plan, in, L.wt, g));
+    epi.bn = 64;
+  } else {
+    VC_TRY(conv_geometry(&g, L.hw, L.hw, B, L.cin, L.cout));
+    VC_TRY(plan_conv(&plan, in, L.wt, g, bn));
+  }
   if (fuse_pool && L.pool) {
     epi.mode = kConvPool;
     VC_TRY(make_tmap_nhwc(&epi.tm, L.pooled, L.cout, L.hw / 2, L.hw / 2, B, g.pw / 2, g.ph / 2, g.pn));
@@ -174,6 +181,7 @@ int Model::vgg_conv_layer(int l, const void* in, int B, bool fuse_pool, cudaStre
     epi.mode = kConv;
     VC_TRY(make_tmap_nhwc(&epi.tm, L.out, L.cout, L.hw, L.hw, B, g.pw, g.ph, g.pn));
   }
+  if (halo) return launch_conv_halo(plan, epi, s);
   return launch_gemm(plan, epi, s);
 }
 
