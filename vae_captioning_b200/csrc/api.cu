@@ -119,7 +119,8 @@ int vc_forward_backward_dev(vc_handle* h, const float* feats, const int32_t* lbl
 int vc_grad_buffer(vc_handle* h, float** dev_ptr, int64_t* count) {
   if (!h || !dev_ptr || !count) return set_error(VC_E_ARG, "vc_grad_buffer: null argument");
   *dev_ptr = h->m.Gf;
-  *count = h->m.n_adam + 64;  // gradients + the 64-float tail carrying the embedding-slice squared norms
+  // gradients + the 64-float tail carrying the embedding-slice squared norms (+ frozen gap and cnn/ region when fine-tuning)
+  *count = h->m.cfg.fine_tune ? h->m.n_total : h->m.n_adam + 64;
   return VC_OK;
 }
 

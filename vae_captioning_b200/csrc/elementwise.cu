@@ -639,7 +639,7 @@ int sumsq(cudaStream_t s, const float* g, long long n, float* out) {
 // normsq_parts: the squared norm is the sum of up to 4 device scalars (dense grads + per-token embedding slices).
 __global__ void k_adam(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                        long long n, const float* __restrict__ normsq_parts, int n_parts, float clip, float gscale,
-                       float lr_t, float b1, float b2, float eps, float* __restrict__ norm_out) {
+                       float lr_t, float b1, float b2, float eps, float* __restrict__ norm_out, float wd) {
   float scale = gscale;
   if (clip > 0.f) {
     float ns = 0.f;
@@ -657,7 +657,7 @@ __global__ void k_adam(float* __restrict__ p, const float* __restrict__ g, float
     float4 pp = p4[i], gg = g4[i], mm = m4[i], vv = v4[i];
 #define VC_ADAM1(c)                                 \
   {                                                 \
-    const float gs = gg.c * scale;                  \
+    const float gs = gg.c * scale + wd * pp.c;      \
     mm.c = b1 * mm.c + (1.f - b1) * gs;             \
     vv.c = b2 * vv.c + (1.f - b2) * gs * gs;        \
     pp.c -= lr_t * mm.c / (sqrtf(vv.c) + eps);      \
@@ -670,12 +670,12 @@ __global__ void k_adam(float* __restrict__ p, const float* __restrict__ g, float
   }
 }
 int adam_step(cudaStream_t s, float* p, const float* g, float* m, float* v, long long n, const float* normsq_parts,
-              int n_parts, float clip, float gscale, float lr_t, float b1, float b2, float eps, float* norm_out) {
+              int n_parts, float clip, float gscale, float lr_t, float b1, float b2, float eps, float* norm_out, float weight_decay) {
   if (n <= 0) return VC_OK;
   if (n % 4 != 0) return set_error(VC_E_ARG, "adam_step: length must be a multiple of 4 (padded flat buffer)");
   {
     ProfScope ps(s, "adam");
-    k_adam<<<grid_for(n / 4, 256, 2), 256, 0, s>>>(p, g, m, v, n, normsq_parts, n_parts, clip, gscale, lr_t, b1, b2, eps, norm_out);
+    k_adam<<<grid_for(n / 4, 256, 2), 256, 0, s>>>(p, g, m, v, n, normsq_parts, n_parts, clip, gscale, lr_t, b1, b2, eps, norm_out, weight_decay);
   }
   VC_CUDA(cudaGetLastError());
   return VC_OK;

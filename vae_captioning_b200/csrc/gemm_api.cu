@@ -53,3 +53,25 @@ extern "C" int vc_gemm_bf16(const void* A, int a_mn, long long lda, const void* 
   epi.alpha = 1.f;
   return gemm_store(static_cast<cudaStream_t>(stream), a, nullptr, 0, b, M, N, K, epi, bn, splits);
 }
+
+// Test entries for the convolution backward kernels (parity against torch conv2d gradients on the same bf16 inputs):
+// x, dy bf16 NHWC; w fp32 HWIO; dw fp32 [9*Cin, Cout] (zeroed here); dx bf16 NHWC. All device pointers.
+extern "C" int vc_conv3x3_bwd(const void* x, const void* dy, const float* w, float* dw, void* dx, int B, int hw, int cin,
+                              int cout, void* stream) {
+  using namespace vc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  void* wt_d = nullptr;
+  VC_CUDA(cudaMalloc(&wt_d, (size_t)9 * cin * cout * 2));
+  int st = dgrad_shadow(s, w, wt_d, cin, cout);
+  if (st == VC_OK && cudaMemsetAsync(dw, 0, (size_t)9 * cin * cout * sizeof(float), s) != cudaSuccess)
+    st = set_error(VC_E_CUDA, "memset failed");
+  if (st == VC_OK) st = conv3x3_wgrad(s, x, dy, dw, B, hw, cin, cout);
+  if (st == VC_OK) st = conv3x3_dgrad(s, dy, wt_d, dx, B, hw, cin, cout);
+  cudaStreamSynchronize(s);
+  cudaFree(wt_d);
+  return st;
+}
+
+extern "C" int vc_relu_pool_bwd(const void* dA, const void* out, void* dY, int B, int hw, int C, int pooled, void* stream) {
+  return vc::relu_pool_bwd(static_cast<cudaStream_t>(stream), dA, out, dY, B, hw, C, pooled != 0);
+}

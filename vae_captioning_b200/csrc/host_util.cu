@@ -205,21 +205,7 @@ int conv_geometry(ConvGeom* g, int W, int H, int Nimg, int Cin, int Cout) {
 }
 
 bool conv_halo_applicable(int W, int H, int Cin, int Cout) {
-  static int enabled = -1;
-  if (enabled < 0) {
-    const char* e = getenv("VC_CONV_HALO");
-    enabled = (e == nullptr) ? 0 : atoi(e);
-  }
-  return enabled && Cin == 64 && Cout % 64 == 0 && W % 8 == 0 && H % 16 == 0;
-}
-
-int halo_base_offset_mode() {
-  static int mode = -1;
-  if (mode < 0) {
-    const char* e = getenv("VC_HALO_BASE_OFFSET");
-    mode = (e == nullptr) ? 1 : atoi(e);
-  }
-  return mode;
+  return Cin == 64 && Cout % 64 == 0 && W % 8 == 0 && H % 16 == 0;
 }
 
 int conv_halo_geometry(ConvGeom* g, int W, int H, int Nimg, int Cin, int Cout) {
@@ -274,6 +260,38 @@ int plan_conv(GemmPlan* p, const void* in, const void* wt, const ConvGeom& cg, i
   VC_TRY(make_tmap_nhwc(&p->tmA, in, cg.Cin, cg.W, cg.H, cg.Nimg, cg.pw, cg.ph, cg.pn));
   p->tmA2 = p->tmA;
   VC_TRY(make_tmap_2d(&p->tmB, wt, 9ull * cg.Cin, cg.Cout, 9ull * cg.Cin, 64, bn));
+  return VC_OK;
+}
+
+int plan_conv_wgrad(GemmPlan* p, const void* in, const void* dy, int W, int H, int Nimg, int Cin, int Cout, int bn,
+                    int splits) {
+  if (Cin % 64 != 0 || Cout % 64 != 0) return set_error(VC_E_SHAPE, "plan_conv_wgrad: Cin=%d Cout=%d must be multiples of 64", Cin, Cout);
+  if (bn % 64 != 0 || bn > 256 || Cout % bn != 0) return set_error(VC_E_ARG, "plan_conv_wgrad: bn=%d", bn);
+  memset(p, 0, sizeof(*p));
+  GemmCore& g = p->core;
+  // 64-pixel contraction patches that tile the feature map exactly
+  if (W % 16 == 0 && H % 4 == 0) { g.pw = 16; g.ph = 4; g.pn = 1; }
+  else if (W % 8 == 0 && H % 8 == 0) { g.pw = 8; g.ph = 8; g.pn = 1; }
+  else if (W % 4 == 0 && H % 4 == 0) { g.pw = 4; g.ph = 4; g.pn = 4; }
+  else if (W % 2 == 0 && H % 2 == 0) { g.pw = 2; g.ph = 2; g.pn = 16; }
+  else return set_error(VC_E_SHAPE, "plan_conv_wgrad: %dx%d feature map has odd extent", W, H);
+  g.tw = g.th = 1;
+  g.tiles_w = W / g.pw;
+  g.tiles_h = H / g.ph;
+  g.k_blocks = g.tiles_w * g.tiles_h * ((Nimg + g.pn - 1) / g.pn);
+  g.cpk = Cin / 64;
+  g.m_tiles = (9 * Cin + kBM - 1) / kBM;
+  g.n_tiles = Cout / bn;
+  g.splits = splits < 1 ? 1 : (splits > g.k_blocks ? g.k_blocks : splits);
+  g.bn = bn;
+  g.stages = gemm_pick_stages(bn, 0);
+  g.a_mode = A_WGRAD3x3;
+  g.b_mn = 2;
+  g.a_switch = -1;
+  g.n_img = Nimg;
+  VC_TRY(make_tmap_nhwc(&p->tmA, in, Cin, W, H, Nimg, g.pw, g.ph, g.pn));
+  p->tmA2 = p->tmA;
+  VC_TRY(make_tmap_nhwc(&p->tmB, dy, Cout, W, H, Nimg, g.pw, g.ph, g.pn));
   return VC_OK;
 }
 

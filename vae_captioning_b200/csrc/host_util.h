@@ -86,11 +86,16 @@ int plan_gemm(GemmPlan* p, const Operand& A, const Operand* A2, long long a2_at,
 // D = conv3x3_same(in NHWC bf16 [Nimg,H,W,Cin], Wt bf16 [Cout, 9*Cin] (tap-major, then cin)); Cin % 64 == 0.
 int plan_conv(GemmPlan* p, const void* in, const void* wt, const ConvGeom& g, int bn);
 
+// Filter gradient of the same convolution: dW[9*Cin, Cout] (HWIO row-major) += patches(in)^T x dY, contraction over
+// the Nimg*H*W pixels in 64-pixel patches, split-K over `splits` CTAs per output tile (fp32 atomic epilogue).
+// in: NHWC bf16 [Nimg,H,W,Cin]; dy: NHWC bf16 [Nimg,H,W,Cout]; Cin, Cout multiples of 64; bn divides Cout.
+int plan_conv_wgrad(GemmPlan* p, const void* in, const void* dy, int W, int H, int Nimg, int Cin, int Cout, int bn,
+                    int splits);
+
 // Halo form for Cin == 64 layers whose feature map tiles into 8 x 16 pixel blocks (see conv_halo_kernel).
 bool conv_halo_applicable(int W, int H, int Cin, int Cout);
 int conv_halo_geometry(ConvGeom* g, int W, int H, int Nimg, int Cin, int Cout);
 int plan_conv_halo(GemmPlan* p, const void* in, const void* wt, const ConvGeom& g);
-int halo_base_offset_mode();  // env VC_HALO_BASE_OFFSET (default 1)
 
 template <class Epi>
 int launch_conv_halo(const GemmPlan& p, const Epi& epi, cudaStream_t stream) {
@@ -106,7 +111,7 @@ int launch_conv_halo(const GemmPlan& p, const Epi& epi, cudaStream_t stream) {
   const int smem = conv_halo_smem_bytes(Epi::kSmemBytes);
   {
     ProfScope ps(stream, "conv_halo");
-    conv_halo_kernel<Epi><<<grid, kGemmThreads, smem, stream>>>(p.tmA, p.tmB, p.core, epi, halo_base_offset_mode());
+    conv_halo_kernel<Epi><<<grid, kGemmThreads, smem, stream>>>(p.tmA, p.tmB, p.core, epi);
   }
   VC_CUDA(cudaGetLastError());
   return VC_OK;

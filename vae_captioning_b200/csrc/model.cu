@@ -270,7 +270,13 @@ int Model::grad_get(const char* name, float* dst) {
   if (params[i].region == 1 || (params[i].region == 2 && !cfg.fine_tune))
     return set_error(VC_E_STATE, "variable '%s' has no gradient in this configuration", name);
   VC_CUDA(cudaDeviceSynchronize());
-  return copy_var(i, Gf, dst, nullptr);
+  VC_TRY(copy_var(i, Gf, dst, nullptr));
+  if (params[i].region == 2 && cfg.weight_decay != 0.f) {  // + d(weight_decay * sum(w^2) / 2)/dw, Q11
+    std::vector<float> w((size_t)params[i].count);
+    VC_TRY(copy_var(i, Pf, w.data(), nullptr));
+    for (int64_t k = 0; k < params[i].count; ++k) dst[k] += cfg.weight_decay * w[(size_t)k];
+  }
+  return VC_OK;
 }
 int Model::set_cluster_means(const float* src) {
   if (c_means == nullptr) return set_error(VC_E_STATE, "this configuration has no encoder (no cluster means)");
@@ -285,6 +291,7 @@ int Model::refresh_shadows(cudaStream_t s) {
   const int E = cfg.embed_size, Z = cfg.latent_size, S = cfg.gen_z_samples, V = cfg.vocab_size, F = cfg.cnn_feature_size,
             K = cfg.num_clusters;
   VC_TRY(transpose_cast(s, pp(pidx("imf_emb/kernel")), imf_wt, F, E, E, F, 0, 0));
+  if (imf_nat) VC_TRY(cast_f32_bf16(s, pp(pidx("imf_emb/kernel")), imf_nat, F, E, E, E));
   if (cv_wt) VC_TRY(transpose_cast(s, pp(pidx("cv_emb/kernel")), cv_wt, K, E, E, KP, 0, 0));
   auto lstm = [&](LstmNet& L) -> int {
     VC_TRY(transpose_cast(s, pp(L.p_kernel), L.w_t_perm, L.E + L.H, 4 * L.H, 4 * L.H, L.E + L.H, L.H, 64));
@@ -442,13 +449,12 @@ static float annealing_coeff(const vc_config& c, int64_t gs) {  // main.py:162-1
 }
 
 // ------------------------------------------------------------------------------------------
-// scal layout: 0 ce_sum, 1 mask_sum, 2 mask count (pre-pass), 3 kl_sum, 7 global norm
+// scal layout: 0 ce_sum, 1 mask_sum, 2 mask count (pre-pass), 3 kl_sum, 7 global norm, 8 sum(w^2) over cnn/ (fine_tune)
 int Model::forward(const StepInputs& in, bool write_grad, cudaStream_t s) {
   const int B = in.B, T = in.T, C = cfg.num_captions, N = B * C;
   const int E = cfg.embed_size, Hd = cfg.decoder_hidden, Z = cfg.latent_size, S = cfg.gen_z_samples, V = cfg.vocab_size,
             F = cfg.cnn_feature_size, K = cfg.num_clusters;
   if (B < 1 || B > cfg.max_batch || T < 1 || T > maxT) return set_error(VC_E_SHAPE, "batch/len out of range");
-  if (cfg.fine_tune) return set_error(VC_E_STATE, "fine_tune training is not implemented in this build");
   const bool has_cv = cfg.use_c_v || cfg.prior != VC_PRIOR_NORMAL;
   if (has_cv && in.c_v == nullptr) return set_error(VC_E_ARG, "this configuration needs cluster vectors (c_v)");
   if (cfg.dec_keep_rate < 1.f && in.rng.emb_keep_dev == nullptr)
@@ -458,8 +464,20 @@ int Model::forward(const StepInputs& in, bool write_grad, cudaStream_t s) {
   if (shadows_dirty) VC_TRY(refresh_shadows(s));
   VC_CUDA(cudaMemsetAsync(scal, 0, 64 * sizeof(float), s));
 
+  // --fine_tune: the feed is the image batch and fc2 of the trainable VGG16 is the feature (main.py:65-82);
+  // un-pooled activations are kept for the backward pass
+  const float* feats = in.feats;
+  if (cfg.fine_tune) {
+    vgg_drop_seed = in.rng.seed;
+    vgg_drop_step = (unsigned long long)in.global_step;
+    VC_TRY(vgg_forward(in.feats, nullptr, B, true, in.rng.cnn_keep_dev, s));
+    feats = fc2_f;
+    // l2_regularizer(weight_decay) on every cnn/ variable joins rec_loss through get_total_loss (main.py:67-74,
+    // 159-160; Q11): scal[8] = sum of squares of the cnn/ region (its padding is zero)
+    VC_TRY(sumsq(s, Pf + (n_total - n_cnn), n_cnn, scal + 8));
+  }
   // image features -> embedding space (main.py:84-94; projection before tiling, Q7)
-  VC_TRY(cast_f32_bf16(s, in.feats, feats_h, B, F, F, F));
+  VC_TRY(cast_f32_bf16(s, feats, feats_h, B, F, F, F));
   VC_CUDA(cudaMemsetAsync(imf_f, 0, (size_t)B * E * sizeof(float), s));
   {
     Operand A{feats_h, B, F, F, false}, Bw{imf_wt, E, F, F, false};
@@ -646,6 +664,17 @@ int Model::backward(const StepInputs& in, cudaStream_t s) {
     VC_TRY(gemm_store(s, A, nullptr, 0, Bw, K, E, N, e, E % 256 == 0 ? 256 : 64, 1));
     VC_TRY(colsum_bf16(s, dcv_h, N, E, E, gp(pidx("cv_emb/bias"))));
   }
+  if (cfg.fine_tune) {
+    // d lower_bound / d fc2 = dimf x W_imf^T, then down the VGG16 (ops/optimizers.py:49-52)
+    Operand A{dimf_h, B, E, E, false}, Bw{imf_nat, F, E, E, false};
+    EpiStore e{};
+    e.out = dfeats_f; e.ld = F; e.alpha = 1.f;
+    {
+      ProfTag ptag("imf_emb_dgrad");
+      VC_TRY(gemm_store(s, A, nullptr, 0, Bw, B, F, E, e, 128, 1));
+    }
+    VC_TRY(vgg_backward(dfeats_f, B, s));
+  }
   // squared norm of the dense (non-embedding) gradients -> tail[2]; embedding slices are in tail[0..1] (Q4)
   return VC_OK;
 }
@@ -658,6 +687,15 @@ int Model::apply(float grad_scale, cudaStream_t s) {
   const double b1 = 0.8, b2 = 0.999;
   const float lr_t = (float)(cfg.learning_rate * std::sqrt(1.0 - std::pow(b2, (double)adam_t)) / (1.0 - std::pow(b1, (double)adam_t)));
   VC_TRY(adam_step(s, Pf, Gf, Mf, Vf, n_adam, g_tail, 3, cfg.clip_norm, grad_scale, lr_t, (float)b1, (float)b2, 1e-8f, scal + 7));
+  if (cfg.fine_tune) {
+    // ops/optimizers.py:49-82: Adam(cnn_lr, beta1=0.8) on the 30 cnn/ variables, no clipping; the regulariser
+    // gradient weight_decay * w (Q11) is added inside the update
+    const float lr_c = (float)(cfg.cnn_lr * std::sqrt(1.0 - std::pow(b2, (double)adam_t)) / (1.0 - std::pow(b1, (double)adam_t)));
+    const int64_t c0 = n_total - n_cnn;
+    VC_TRY(adam_step(s, Pf + c0, Gf + c0, Mf + c0, Vf + c0, n_cnn, nullptr, 0, 0.f, grad_scale, lr_c, (float)b1, (float)b2,
+                     1e-8f, nullptr, cfg.weight_decay));
+    vgg_shadows_dirty = true;
+  }
   shadows_dirty = true;
   VC_TRY(refresh_shadows(s));
   return VC_OK;
@@ -669,6 +707,7 @@ int Model::fetch(vc_step_out* out, cudaStream_t s) {
   VC_CUDA(cudaStreamSynchronize(s));
   const float cnt = host_scal[1] > 0.f ? host_scal[1] : 1.f;
   out->rec_loss = host_scal[0] / cnt;
+  if (cfg.fine_tune) out->rec_loss += 0.5f * cfg.weight_decay * host_scal[8];
   out->n_tokens = host_scal[1];
   out->kld = cfg.no_encoder ? 0.f : host_scal[3] / (float)lastN;
   out->global_norm = host_scal[7];

@@ -43,6 +43,7 @@ struct VggLayer {
   bool pool = false;
   int p_w = -1, p_b = -1;
   void* wt = nullptr;      // bf16 [cout, kpad] (tap-major, then cin)
+  void* wt_d = nullptr;    // bf16 [cin, 9*cout] tap-reversed (dgrad B operand; fine_tune only)
   void* out = nullptr;     // bf16 NHWC [B, hw, hw, cout] (post-ReLU, un-pooled)
   void* pooled = nullptr;  // bf16 NHWC [B, hw/2, hw/2, cout] when pool
 };
@@ -109,6 +110,13 @@ class Model {
   float *fc_acc = nullptr, *fc2_f = nullptr, *st_images = nullptr;
   bool vgg_shadows_dirty = true, vgg_keep = false, vgg_have_unpooled = false;
   int vgg_last_B = 0;
+  // fine-tune backward (vgg_bwd.cu)
+  void *vgg_bwd_a = nullptr, *vgg_bwd_b = nullptr, *imf_nat = nullptr, *dfc2_pre = nullptr, *dfc1_pre = nullptr;
+  float* dfeats_f = nullptr;
+  unsigned long long vgg_drop_seed = 0, vgg_drop_step = 0;  // Philox stream of the fc dropout masks (explicit masks win)
+  int vgg_bwd_init();
+  int vgg_refresh_bwd_shadows(cudaStream_t s);
+  int vgg_backward(const float* dfeats, int B, cudaStream_t s);
   int vgg_init();
   int vgg_refresh_shadows(cudaStream_t s);
   int vgg_conv_layer(int l, const void* in, int B, bool fuse_pool, cudaStream_t s);

@@ -48,6 +48,12 @@ struct LstmBwdArgs {
 };
 int lstm_bwd_step(cudaStream_t stream, const LstmBwdArgs& a);
 
+// vgg_bwd.cu -------------------------------------------------------------------------------
+int conv3x3_wgrad(cudaStream_t s, const void* x, const void* dy, float* dw, int B, int hw, int cin, int cout);
+int conv3x3_dgrad(cudaStream_t s, const void* dy, const void* wt_d, void* dx, int B, int hw, int cin, int cout);
+int dgrad_shadow(cudaStream_t s, const float* w_hwio, void* wt_d, int cin, int cout);
+int relu_pool_bwd(cudaStream_t s, const void* dA, const void* out, void* dY, int B, int hw, int C, bool pooled);
+
 // elementwise.cu ---------------------------------------------------------------------------
 int cast_f32_bf16(cudaStream_t s, const float* src, void* dst, long long rows, int cols, long long ld_src,
                   long long ld_dst);
@@ -79,7 +85,7 @@ int count_mask(cudaStream_t s, const int* lbl, long long n, float* count);
 int colsum_bf16(cudaStream_t s, const void* x, long long rows, int cols, long long ld, float* out);
 int sumsq(cudaStream_t s, const float* g, long long n, float* out);
 int adam_step(cudaStream_t s, float* p, const float* g, float* m, float* v, long long n, const float* normsq_parts,
-              int n_parts, float clip, float gscale, float lr_t, float b1, float b2, float eps, float* norm_out);
+              int n_parts, float clip, float gscale, float lr_t, float b1, float b2, float eps, float* norm_out, float weight_decay = 0.f);
 int logits_to_ref(cudaStream_t s, const void* src, long long ld, float* dst, int N, int T, int V);
 
 }  // namespace vc

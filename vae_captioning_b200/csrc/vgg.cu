@@ -6,6 +6,7 @@
 // zero fill = SAME padding), the B operand is the [Cout, 9*Cin] weight shadow, and bias + ReLU
 // (+ the 2x2 max-pool of the following layer) run in the epilogue, which stores bf16 NHWC through TMA.
 // conv1_1 (Cin = 3) goes through a tiny im2col (27 -> 32 columns) fused with the mean subtraction.
+#include <curand_kernel.h>
 #include "model.h"
 
 namespace vc {
@@ -88,13 +89,21 @@ __global__ void k_maxpool2(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* 
   }
 }
 
-// y = relu(x + bias) (* keep / keep_prob) -> fp32 and/or bf16 (fc layers after the split-K accumulation)
+// y = relu(x + bias) (* keep / keep_prob) -> fp32 and/or bf16 (fc layers after the split-K accumulation).
+// tf.nn.dropout (image_embeddings.py:225-226, 236-237): explicit 0/1 mask `keep`, or, when philox != 0, a
+// Philox4x32-10 uniform per element (subsequence = element index, offset = stream) kept if u < keep_prob.
 __global__ void k_bias_relu(const float* __restrict__ x, const float* __restrict__ bias, const float* __restrict__ keep,
-                            float inv_keep, float* __restrict__ yf, __nv_bfloat16* __restrict__ yh, long long rows, int cols) {
+                            float inv_keep, float* __restrict__ yf, __nv_bfloat16* __restrict__ yh, long long rows, int cols,
+                            int philox, unsigned long long seed, unsigned long long stream) {
   const long long total = rows * cols;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     float v = fmaxf(x[i] + bias[i % cols], 0.f);
     if (keep) v *= keep[i] * inv_keep;
+    else if (philox) {
+      curandStatePhilox4_32_10_t st;
+      curand_init(seed, (unsigned long long)i, stream, &st);
+      v = (curand_uniform(&st) * inv_keep <= 1.f) ? v * inv_keep : 0.f;  // u <= keep_prob
+    }
     if (yf) yf[i] = v;
     if (yh) yh[i] = __float2bfloat16(v);
   }
@@ -129,6 +138,7 @@ int Model::vgg_init() {
   VC_TRY(dalloc(&fc2_f, (size_t)B * 4096));
   VC_TRY(dalloc(&st_images, (size_t)B * 224 * 224 * 3));
   vgg_shadows_dirty = true;
+  if (cfg.fine_tune) VC_TRY(vgg_bwd_init());
   return VC_OK;
 }
 
@@ -141,6 +151,7 @@ int Model::vgg_refresh_shadows(cudaStream_t s) {
   }
   VC_TRY(cast_f32_bf16(s, pp(pidx("cnn/fc1/weights")), fc1_w, 25088, 4096, 4096, 4096));
   VC_TRY(cast_f32_bf16(s, pp(pidx("cnn/fc2/weights")), fc2_w, 4096, 4096, 4096, 4096));
+  if (cfg.fine_tune) VC_TRY(vgg_refresh_bwd_shadows(s));
   vgg_shadows_dirty = false;
   return VC_OK;
 }
@@ -155,7 +166,7 @@ int Model::vgg_conv_layer(int l, const void* in, int B, bool fuse_pool, cudaStre
   epi.relu = 1;
   epi.alpha = 1.f;
   GemmPlan plan;
-  ProfTag ptag("conv");
+  ProfTag ptag(kVggNames[l]);
   if (l == 0) {
     const long long M = (long long)B * L.hw * L.hw;
     Operand A{in, M, 27, 32, false}, Bw{L.wt, L.cout, 27, 32, false};
@@ -218,7 +229,12 @@ int Model::vgg_forward(const float* images, float* fc2_out, int B, bool keep_unp
   vgg_last_B = B;
   vgg_have_unpooled = keep_unpooled;
   // fc1 / fc2 (image_embeddings.py:214-238): NHWC flatten of pool5 is the row-major [B, 25088] view
-  const float inv_keep = 1.f / cfg.cnn_dropout;
+  // dropout only exists in the fine-tune training graph (main.py:67-72); explicit masks (parity) win over Philox
+  const bool drop = cfg.fine_tune && cfg.cnn_dropout < 1.f;
+  const float inv_keep = drop ? 1.f / cfg.cnn_dropout : 1.f;
+  if (!drop) fc_keep = nullptr;
+  const int philox = (drop && fc_keep == nullptr) ? 1 : 0;
+  int fc_no = 0;
   auto fc = [&](const void* a, int K, const void* w, const char* bias_name, const float* keep, float* yf, void* yh) -> int {
     VC_CUDA(cudaMemsetAsync(fc_acc, 0, (size_t)B * 4096 * sizeof(float), s));
     Operand A{a, B, K, K, false}, Bw{w, K, 4096, 4096, true};
@@ -231,7 +247,9 @@ int Model::vgg_forward(const float* images, float* fc2_out, int B, bool keep_unp
     }
     ProfScope ps(s, "bias_relu");
     k_bias_relu<<<ew_grid((long long)B * 4096, 256), 256, 0, s>>>(fc_acc, pp(pidx(bias_name)), keep, inv_keep, yf,
-                                                                 (__nv_bfloat16*)yh, B, 4096);
+                                                                 (__nv_bfloat16*)yh, B, 4096, philox, vgg_drop_seed,
+                                                                 vgg_drop_step * 2 + fc_no);
+    ++fc_no;
     return VC_OK;
   };
   VC_TRY(fc(vgg[12].pooled, 25088, fc1_w, "cnn/fc1/biases", fc_keep, nullptr, fc1_h));
