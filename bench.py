@@ -94,7 +94,9 @@ def family_work(p, B, has_enc=True):
 
 def total_flops(p, B, vgg):
     w = family_work(p, B)
-    tot = sum(v for k, (kind, v) in w.items() if kind == "tensor" and k not in ("conv", "fc"))
+    cvae = ("lstm_fwd_step", "lstm_bwd_step", "lstm_wgrad", "lstm_dx", "logits_fwd", "logits_dgrad", "logits_wgrad", "z_rnn",
+            "z_rnn_dgrad", "z_rnn_wgrad", "imf_emb", "imf_emb_bwd")
+    tot = sum(w[k][1] for k in cvae)
     heads = 1 if p.prior == "Normal" else 3  # minimum-algorithmic (active heads only)
     tot += 3 * 2.0 * B * C * p.encoder_hidden * 2 * p.latent_size * heads
     if vgg:

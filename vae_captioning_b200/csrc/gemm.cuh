@@ -4,8 +4,10 @@
 //
 //   D[128 x BN] (fp32, TMEM) = sum_k A[128 x 64] (bf16, smem) * B[BN x 64] (bf16, smem)
 //
-// Roles (256 threads): warp 0 = TMA producer, warp 1 = tcgen05.mma issuer (one elected lane),
-// warp 2 = TMEM allocator, warps 4..7 = epilogue (one TMEM lane quarter each).
+// Roles (384 threads): warp 0 = TMA producer, warp 1 = tcgen05.mma issuer (one elected lane),
+// warp 2 = TMEM allocator, warps 4..7 and 8..11 = two epilogue groups (one TMEM lane quarter per
+// warp). Group g drains accumulator buffer g, i.e. every second tile of the CTA, so two tile
+// epilogues run concurrently (a lone warp per SM sub-partition cannot hide its own latencies).
 // Three pipelines: smem full/empty ring (TMA <-> MMA), TMEM full/empty double buffer
 // (MMA <-> epilogue), and a static persistent tile schedule (tile += gridDim.x).
 //
@@ -22,9 +24,11 @@ namespace vc {
 constexpr int kBM = 128;        // tile rows (UMMA M)
 constexpr int kBK = 64;         // k-block: 64 bf16 = one 128-byte swizzle row
 constexpr int kABytes = kBM * kBK * 2;
-constexpr int kGemmThreads = 256;
+constexpr int kGemmThreads = 384;
 constexpr int kMaxStages = 8;
-constexpr int kAccStride = 256;  // TMEM columns between the two accumulator buffers
+constexpr int kMaxAcc = 8;       // accumulator buffers in TMEM: 512 columns / tile width (2 at bn = 256 ... 8 at bn <= 64)
+__host__ __device__ inline int gemm_acc_buffers(int bn) { return bn > 128 ? 2 : (bn > 64 ? 4 : 8); }
+__host__ __device__ inline int gemm_acc_stride(int bn) { return bn > 128 ? 256 : (bn > 64 ? 128 : 64); }
 
 enum AMode : int { A_KMAJOR = 0, A_MNMAJOR = 1, A_CONV3x3 = 2, A_WGRAD3x3 = 3 };
 
@@ -66,13 +70,13 @@ __device__ __forceinline__ PatchOrigin conv_patch_origin(const GemmCore& g, int 
 }
 
 __host__ __device__ inline int gemm_stage_bytes(int bn) { return kABytes + bn * kBK * 2; }
-// dynamic smem = [1024-align slack][stages x (A tile + B tile)][epilogue staging][barriers, 256 B]
+// dynamic smem = [1024-align slack][stages x (A tile + B tile)][epilogue staging][barriers, 512 B]
 __host__ inline int gemm_pick_stages(int bn, int epi_bytes) {
-  int s = (227 * 1024 - 1024 - 256 - epi_bytes) / gemm_stage_bytes(bn);
+  int s = (227 * 1024 - 1024 - 512 - epi_bytes) / gemm_stage_bytes(bn);
   return s > kMaxStages ? kMaxStages : s;
 }
 __host__ inline int gemm_smem_bytes(int bn, int stages, int epi_bytes) {
-  return stages * gemm_stage_bytes(bn) + epi_bytes + 1024 + 256;
+  return stages * gemm_stage_bytes(bn) + epi_bytes + 1024 + 512;
 }
 
 struct TileCoord {
@@ -93,7 +97,7 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmCore& g, int tile) {
 }
 
 // Epi must provide:
-//   static constexpr int kSmemBytes;   // epilogue staging (multiple of 1024), split evenly over the 4 warps
+//   static constexpr int kSmemBytes;   // epilogue staging (multiple of 1024), split evenly over the 8 warps
 //   __device__ void operator()(uint32_t tmem_row_addr, const GemmCore& g, const TileCoord& t, int row,
 //                              uint8_t* warp_smem, int& phase) const
 // called by each of the 128 epilogue threads (row = 0..127 = TMEM lane = tile row) once the
@@ -112,8 +116,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* full = bars;
   uint64_t* empty = bars + kMaxStages;
   uint64_t* tfull = bars + 2 * kMaxStages;
-  uint64_t* tempty = bars + 2 * kMaxStages + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 4);
+  uint64_t* tempty = bars + 2 * kMaxStages + kMaxAcc;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 2 * kMaxAcc);
+  const int nacc = gemm_acc_buffers(g.bn);
+  const int acc_stride = gemm_acc_stride(g.bn);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -129,7 +135,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_init(&full[i], 1);
       mbar_init(&empty[i], 1);
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < kMaxAcc; ++i) {
       mbar_init(&tfull[i], 1);
       mbar_init(&tempty[i], 4);
     }
@@ -224,7 +230,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const TileCoord t = decode_tile(g, tile);
         mbar_wait(&tempty[acc], acc_phase ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * kAccStride;
+        const uint32_t d_tmem = tmem_base + acc * acc_stride;
         for (int kb = t.kb_begin; kb < t.kb_end; ++kb) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
@@ -243,7 +249,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         }
         umma_commit(&tfull[acc]);
-        if (++acc == 2) {
+        if (++acc == nacc) {
           acc = 0;
           acc_phase ^= 1;
         }
@@ -251,26 +257,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------ epilogue
+    // tile ordinal `ord` of this CTA lives in accumulator buffer ord % nacc; group (warp - 4) / 4 drains the
+    // ordinals of its own parity (nacc is even, so a buffer always belongs to the same group)
     const int q = warp & 3;
-    int acc = 0;
-    uint32_t acc_phase = 0;
+    const int grp = (warp - 4) >> 2;
     int epi_phase = 0;
-    uint8_t* warp_smem = epi_smem + q * (Epi::kSmemBytes / 4);
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    uint8_t* warp_smem = epi_smem + (warp - 4) * (Epi::kSmemBytes / 8);
+    int ord = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ord) {
+      if ((ord & 1) != grp) continue;
+      const int acc = ord % nacc;
+      const uint32_t acc_phase = (ord / nacc) & 1;
       const TileCoord t = decode_tile(g, tile);
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
       if (t.kb_end > t.kb_begin) {
-        const uint32_t taddr = tmem_base + acc * kAccStride + (uint32_t(q * 32) << 16);
+        const uint32_t taddr = tmem_base + acc * acc_stride + (uint32_t(q * 32) << 16);
         epi(taddr, g, t, q * 32 + lane, warp_smem, epi_phase);
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[acc]);
-      if (++acc == 2) {
-        acc = 0;
-        acc_phase ^= 1;
-      }
     }
     epi.finish();
   }
@@ -360,15 +367,18 @@ enum TmaOutMode : int { kRows = 0, kConv = 1, kConvPool = 2 };
 
 struct EpiTma {
   CUtensorMap tm;
-  const float* bias;  // nullable, indexed by n
+  const float* bias;  // nullable, indexed by n (16-byte aligned)
   int N, bn, relu, mode;
   float alpha;
-  static constexpr int kSmemBytes = 32 * 1024;  // 4 warps x 2 buffers x (32 rows x 128 B)
+  static constexpr int kSmemBytes = 32 * 1024;  // 8 warps x (32 rows x 128 B)
 
   __device__ __forceinline__ void finish() const {
     if ((threadIdx.x & 31) == 0) bulk_wait_all();
   }
 
+  // The accumulator row is rounded to packed bf16 pairs right after the bias add; ReLU and the 2x2 max-pool then run
+  // on the pairs (max commutes with the monotone rounding, so the result equals pooling / clamping in fp32 first)
+  // with half the instructions and half the shuffles.
   __device__ __forceinline__ void operator()(uint32_t taddr, const GemmCore& g, const TileCoord& t, int row,
                                              uint8_t* warp_smem, int& phase) const {
     const int lane = row & 31, q = row >> 5;
@@ -384,40 +394,56 @@ struct EpiTma {
       tmem_ld32(taddr + c, v);
       tmem_ld32(taddr + c + 32, v + 32);  // bn is a multiple of 64 for this epilogue
       tmem_ld_wait();
+      uint32_t p[32];
+      if (bias != nullptr && n0 + 64 <= N) {
+        const float4* b4 = reinterpret_cast<const float4*>(bias + n0);
 #pragma unroll
-      for (int j = 0; j < 64; ++j) {
-        float x = v[j] * alpha;
-        if (bias != nullptr && n0 + j < N) x += bias[n0 + j];
-        if (relu) x = fmaxf(x, 0.f);
-        v[j] = x;
+        for (int j = 0; j < 16; ++j) {
+          const float4 b = __ldg(b4 + j);
+          p[2 * j] = pack_bf16(fmaf(v[4 * j], alpha, b.x), fmaf(v[4 * j + 1], alpha, b.y));
+          p[2 * j + 1] = pack_bf16(fmaf(v[4 * j + 2], alpha, b.z), fmaf(v[4 * j + 3], alpha, b.w));
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float b0 = (bias != nullptr && n0 + 2 * j < N) ? bias[n0 + 2 * j] : 0.f;
+          const float b1 = (bias != nullptr && n0 + 2 * j + 1 < N) ? bias[n0 + 2 * j + 1] : 0.f;
+          p[j] = pack_bf16(fmaf(v[2 * j], alpha, b0), fmaf(v[2 * j + 1], alpha, b1));
+        }
+      }
+      if (relu) {
+        const __nv_bfloat162 zero = __floats2bfloat162_rn(0.f, 0.f);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const __nv_bfloat162 x = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&p[j]), zero);
+          p[j] = *reinterpret_cast<const uint32_t*>(&x);
+        }
       }
       int srow = lane;
       bool writer = true;
       if (mode == kConvPool) {
 #pragma unroll
-        for (int j = 0; j < 64; ++j) {
-          float x = fmaxf(v[j], __shfl_xor_sync(0xffffffffu, v[j], 1));
-          v[j] = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, g.pw));
+        for (int j = 0; j < 32; ++j) {
+          uint32_t o = __shfl_xor_sync(0xffffffffu, p[j], 1);
+          __nv_bfloat162 x = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&p[j]), *reinterpret_cast<__nv_bfloat162*>(&o));
+          uint32_t xu = *reinterpret_cast<const uint32_t*>(&x);
+          o = __shfl_xor_sync(0xffffffffu, xu, g.pw);
+          x = __hmax2(x, *reinterpret_cast<__nv_bfloat162*>(&o));
+          p[j] = *reinterpret_cast<const uint32_t*>(&x);
         }
         const int w = lane % g.pw, h = (lane / g.pw) % g.ph, n = lane / (g.pw * g.ph);
         writer = ((w | h) & 1) == 0;
         srow = (w >> 1) + (g.pw >> 1) * ((h >> 1) + (g.ph >> 1) * n);
       }
-      // the buffer we are about to fill was handed to a bulk store two chunks ago
-      if (lane == 0) bulk_wait_read<1>();
+      // the staging buffer was handed to a bulk store one chunk ago: wait until the TMA engine has read it
+      if (lane == 0) bulk_wait_read<0>();
       __syncwarp();
-      uint8_t* buf = warp_smem + (phase & 1) * 4096;
+      uint8_t* buf = warp_smem;
       if (writer) {
         uint8_t* rp = buf + srow * 128;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          uint4 u;
-          u.x = pack_bf16(v[8 * j + 0], v[8 * j + 1]);
-          u.y = pack_bf16(v[8 * j + 2], v[8 * j + 3]);
-          u.z = pack_bf16(v[8 * j + 4], v[8 * j + 5]);
-          u.w = pack_bf16(v[8 * j + 6], v[8 * j + 7]);
-          *reinterpret_cast<uint4*>(rp + ((j ^ (srow & 7)) << 4)) = u;
-        }
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<uint4*>(rp + ((j ^ (srow & 7)) << 4)) = make_uint4(p[4 * j], p[4 * j + 1], p[4 * j + 2], p[4 * j + 3]);
       }
       fence_proxy_async();
       __syncwarp();
@@ -454,7 +480,7 @@ constexpr int kHaloWBytes = 9 * 64 * 128;                       // resident filt
 constexpr int kHaloStages = 3;
 
 __host__ inline int conv_halo_smem_bytes(int epi_bytes) {
-  return kHaloWBytes + kHaloStages * kHaloBytes + epi_bytes + 1024 + 256;
+  return kHaloWBytes + kHaloStages * kHaloBytes + epi_bytes + 1024 + 512;
 }
 
 template <class Epi>
@@ -470,9 +496,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* hfull = bars;
   uint64_t* hempty = bars + kHaloStages;
   uint64_t* tfull = bars + 2 * kHaloStages;
-  uint64_t* tempty = bars + 2 * kHaloStages + 2;
-  uint64_t* wfull = bars + 2 * kHaloStages + 4;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kHaloStages + 5);
+  uint64_t* tempty = bars + 2 * kHaloStages + kMaxAcc;
+  uint64_t* wfull = bars + 2 * kHaloStages + 2 * kMaxAcc;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kHaloStages + 2 * kMaxAcc + 1);
+  constexpr int nacc = kMaxAcc, acc_stride = 64;  // bn = 64
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -490,7 +517,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_init(&hfull[i], 1);
       mbar_init(&hempty[i], 1);
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < kMaxAcc; ++i) {
       mbar_init(&tfull[i], 1);
       mbar_init(&tempty[i], 4);
     }
@@ -534,7 +561,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         mbar_wait(&tempty[acc], acc_phase ^ 1);
         mbar_wait(&hfull[stage], phase);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * kAccStride;
+        const uint32_t d_tmem = tmem_base + acc * acc_stride;
         const uint32_t hbase = smem_u32(halo + stage * kHaloBytes);
 #pragma unroll
         for (int tap = 0; tap < 9; ++tap) {
@@ -551,7 +578,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           stage = 0;
           phase ^= 1;
         }
-        if (++acc == 2) {
+        if (++acc == nacc) {
           acc = 0;
           acc_phase ^= 1;
         }
@@ -559,24 +586,23 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else if (warp >= 4) {
     const int q = warp & 3;
-    int acc = 0;
-    uint32_t acc_phase = 0;
+    const int grp = (warp - 4) >> 2;
     int epi_phase = 0;
-    uint8_t* warp_smem = epi_smem + q * (Epi::kSmemBytes / 4);
-    for (int m_blk = m_first; m_blk < g.m_tiles; m_blk += m_step) {
+    uint8_t* warp_smem = epi_smem + (warp - 4) * (Epi::kSmemBytes / 8);
+    int ord = 0;
+    for (int m_blk = m_first; m_blk < g.m_tiles; m_blk += m_step, ++ord) {
+      if ((ord & 1) != grp) continue;
+      const int acc = ord % nacc;
+      const uint32_t acc_phase = (ord / nacc) & 1;
       TileCoord t;
       t.m_blk = m_blk; t.n_blk = n_blk; t.split = 0; t.kb_begin = 0; t.kb_end = 9;
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + acc * kAccStride + (uint32_t(q * 32) << 16);
+      const uint32_t taddr = tmem_base + acc * acc_stride + (uint32_t(q * 32) << 16);
       epi(taddr, g, t, q * 32 + lane, warp_smem, epi_phase);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[acc]);
-      if (++acc == 2) {
-        acc = 0;
-        acc_phase ^= 1;
-      }
     }
     epi.finish();
   }
