@@ -130,11 +130,12 @@ def test_finetune_philox_dropout_and_eval():
     r["seed"] = 77
     a = eng.eval_step(rng=r, **feed(batch))
     b = eng.eval_step(rng=r, **feed(batch))
-    assert a["rec_loss"] == b["rec_loss"]
+    # same masks; split-K fp32 atomics make the sum order (not the masks) vary between runs
+    assert abs(a["rec_loss"] - b["rec_loss"]) <= 1e-5 * abs(a["rec_loss"])
     r2 = dict(r)
     r2["seed"] = 78
     c = eng.eval_step(rng=r2, **feed(batch))
-    assert c["rec_loss"] != a["rec_loss"]
+    assert abs(c["rec_loss"] - a["rec_loss"]) > 1e-4 * abs(a["rec_loss"])
     with torch.no_grad():
         ref = O.forward(params, cfg, batch, emulate=True)  # explicit masks: a different draw, same distribution
     assert abs(a["rec_loss"] - float(ref["rec_loss"])) <= 0.1 * abs(float(ref["rec_loss"]))

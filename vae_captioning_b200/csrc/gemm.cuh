@@ -97,12 +97,12 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmCore& g, int tile) {
 }
 
 // Epi must provide:
-//   static constexpr int kSmemBytes;   // epilogue staging (multiple of 1024), split evenly over the 8 warps
+//   static constexpr int kSmemBytes;   // epilogue staging (multiple of 2048), split evenly over the 2 groups
 //   __device__ void operator()(uint32_t tmem_row_addr, const GemmCore& g, const TileCoord& t, int row,
-//                              uint8_t* warp_smem, int& phase) const
-// called by each of the 128 epilogue threads (row = 0..127 = TMEM lane = tile row) once the
+//                              uint8_t* grp_smem, int grp, int& phase) const
+// called by each of the 128 threads of epilogue group `grp` (row = 0..127 = TMEM lane = tile row) once the
 // accumulator is complete. tmem_row_addr addresses column 0 of this thread's warp lane quarter;
-// warp_smem is this warp's quarter of the staging area; phase is per-thread state carried across tiles.
+// grp_smem is the group's half of the staging area; phase is per-thread state carried across tiles.
 //   __device__ void finish() const     // called once per epilogue thread after the last tile
 template <class Epi>
 __global__ void __launch_bounds__(kGemmThreads, 1)
@@ -262,7 +262,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int q = warp & 3;
     const int grp = (warp - 4) >> 2;
     int epi_phase = 0;
-    uint8_t* warp_smem = epi_smem + (warp - 4) * (Epi::kSmemBytes / 8);
+    uint8_t* grp_smem = epi_smem + grp * (Epi::kSmemBytes / 2);
     int ord = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ord) {
       if ((ord & 1) != grp) continue;
@@ -273,7 +273,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tc_fence_after();
       if (t.kb_end > t.kb_begin) {
         const uint32_t taddr = tmem_base + acc * acc_stride + (uint32_t(q * 32) << 16);
-        epi(taddr, g, t, q * 32 + lane, warp_smem, epi_phase);
+        epi(taddr, g, t, q * 32 + lane, grp_smem, grp, epi_phase);
       }
       tc_fence_before();
       __syncwarp();
@@ -302,7 +302,7 @@ struct EpiStore {
   __device__ __forceinline__ void finish() const {}
 
   __device__ __forceinline__ void operator()(uint32_t taddr, const GemmCore&, const TileCoord& t, int row, uint8_t*,
-                                             int&) const {
+                                             int, int&) const {
     const int m = t.m_blk * kBM + row;
     const int n_base = t.n_blk * bn;
     const bool row_ok = m < M;
@@ -357,12 +357,13 @@ struct EpiStore {
 
 // ------------------------------------------------------------------------------------------
 // bf16 tile store through shared memory + TMA: out = act(acc * alpha + bias[n]) written as 64-column
-// (128-byte) swizzled rows into a per-warp staging buffer, then one bulk tensor store per warp per
-// chunk. TMA clips rows/columns/pixels that fall outside the tensor, so ragged M, N and image
-// borders need no predicates. Three output geometries:
-//   kRows   : plain [M, N] matrix, box {64, 32}
-//   kConv   : NHWC conv output, one box {64, pw, ph, pn} per patch (warp)
-//   kConvPool: same with a fused 2x2/2 max-pool (partners are lanes of the warp), box {64, pw/2, ph/2, pn}
+// (128-byte) swizzled rows into the group's staging buffer, then ONE bulk tensor store per 128-row x 64-column
+// chunk (the TMA unit's cost is per instruction, so four 4 KB stores per chunk throttled the 64-channel layers).
+// TMA clips rows/columns/pixels that fall outside the tensor, so ragged M, N and image borders need no predicates.
+// Three output geometries (the 4 patches of a tile stack into one box, see conv_patch_origin):
+//   kRows   : plain [M, N] matrix, box {64, 128}
+//   kConv   : NHWC conv output, box {64, pw, ph*th, pn*tn}
+//   kConvPool: same with a fused 2x2/2 max-pool (partners are lanes of a warp), box {64, pw/2, ph*th/2, pn*tn}
 enum TmaOutMode : int { kRows = 0, kConv = 1, kConvPool = 2 };
 
 struct EpiTma {
@@ -370,21 +371,21 @@ struct EpiTma {
   const float* bias;  // nullable, indexed by n (16-byte aligned)
   int N, bn, relu, mode;
   float alpha;
-  static constexpr int kSmemBytes = 32 * 1024;  // 8 warps x (32 rows x 128 B)
+  static constexpr int kSmemBytes = 32 * 1024;  // 2 groups x (128 rows x 128 B)
 
   __device__ __forceinline__ void finish() const {
-    if ((threadIdx.x & 31) == 0) bulk_wait_all();
+    if ((threadIdx.x & 127) == 0) bulk_wait_all();  // the issuing thread of each group
   }
 
   // The accumulator row is rounded to packed bf16 pairs right after the bias add; ReLU and the 2x2 max-pool then run
   // on the pairs (max commutes with the monotone rounding, so the result equals pooling / clamping in fp32 first)
   // with half the instructions and half the shuffles.
   __device__ __forceinline__ void operator()(uint32_t taddr, const GemmCore& g, const TileCoord& t, int row,
-                                             uint8_t* warp_smem, int& phase) const {
+                                             uint8_t* buf, int grp, int& phase) const {
     const int lane = row & 31, q = row >> 5;
     const int n_base = t.n_blk * bn;
     PatchOrigin po{0, 0, 0};
-    if (mode != kRows) po = conv_patch_origin(g, t.m_blk, q);
+    if (mode != kRows) po = conv_patch_origin(g, t.m_blk, 0);
 #pragma unroll 1
     for (int c = 0; c < bn; c += 64) {
       const int n0 = n_base + c;
@@ -419,7 +420,7 @@ struct EpiTma {
           p[j] = *reinterpret_cast<const uint32_t*>(&x);
         }
       }
-      int srow = lane;
+      int srow = row;
       bool writer = true;
       if (mode == kConvPool) {
 #pragma unroll
@@ -433,12 +434,11 @@ struct EpiTma {
         }
         const int w = lane % g.pw, h = (lane / g.pw) % g.ph, n = lane / (g.pw * g.ph);
         writer = ((w | h) & 1) == 0;
-        srow = (w >> 1) + (g.pw >> 1) * ((h >> 1) + (g.ph >> 1) * n);
+        srow = q * 8 + (w >> 1) + (g.pw >> 1) * ((h >> 1) + (g.ph >> 1) * n);
       }
       // the staging buffer was handed to a bulk store one chunk ago: wait until the TMA engine has read it
-      if (lane == 0) bulk_wait_read<0>();
-      __syncwarp();
-      uint8_t* buf = warp_smem;
+      if (row == 0) bulk_wait_read<0>();
+      named_bar_sync(1 + grp, 128);
       if (writer) {
         uint8_t* rp = buf + srow * 128;
 #pragma unroll
@@ -446,10 +446,10 @@ struct EpiTma {
           *reinterpret_cast<uint4*>(rp + ((j ^ (srow & 7)) << 4)) = make_uint4(p[4 * j], p[4 * j + 1], p[4 * j + 2], p[4 * j + 3]);
       }
       fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) {
+      named_bar_sync(1 + grp, 128);
+      if (row == 0) {
         if (mode == kRows)
-          tma_store_2d(&tm, buf, n0, t.m_blk * kBM + q * 32);
+          tma_store_2d(&tm, buf, n0, t.m_blk * kBM);
         else if (mode == kConv)
           tma_store_4d(&tm, buf, n0, po.w, po.h, po.n);
         else
@@ -588,7 +588,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int q = warp & 3;
     const int grp = (warp - 4) >> 2;
     int epi_phase = 0;
-    uint8_t* warp_smem = epi_smem + (warp - 4) * (Epi::kSmemBytes / 8);
+    uint8_t* grp_smem = epi_smem + grp * (Epi::kSmemBytes / 2);
     int ord = 0;
     for (int m_blk = m_first; m_blk < g.m_tiles; m_blk += m_step, ++ord) {
       if ((ord & 1) != grp) continue;
@@ -599,7 +599,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + acc * acc_stride + (uint32_t(q * 32) << 16);
-      epi(taddr, g, t, q * 32 + lane, warp_smem, epi_phase);
+      epi(taddr, g, t, q * 32 + lane, grp_smem, grp, epi_phase);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[acc]);

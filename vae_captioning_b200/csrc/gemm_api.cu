@@ -31,7 +31,7 @@ int gemm_tma_rows(cudaStream_t stream, const Operand& A, const Operand& B, int M
   epi.relu = relu;
   epi.mode = kRows;
   epi.alpha = 1.f;
-  VC_TRY(make_tmap_2d(&epi.tm, out, (uint64_t)ldo, (uint64_t)M, (uint64_t)ldo, 64, 32));
+  VC_TRY(make_tmap_2d(&epi.tm, out, (uint64_t)ldo, (uint64_t)M, (uint64_t)ldo, 64, 128));
   return launch_gemm(plan, epi, stream);
 }
 

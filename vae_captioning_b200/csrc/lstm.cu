@@ -32,7 +32,7 @@ struct EpiLstmFwd {
   __device__ __forceinline__ void finish() const {}
 
   __device__ __forceinline__ void operator()(uint32_t taddr, const GemmCore&, const TileCoord& tc, int row, uint8_t*,
-                                             int&) const {
+                                             int, int&) const {
     const int m = tc.m_blk * kBM + row;
     const bool row_ok = m < N;
     const bool live = row_ok && (lengths == nullptr || t < lengths[m]);
@@ -241,7 +241,7 @@ struct EpiLstmBwd {
   static constexpr int kSmemBytes = 0;
   __device__ __forceinline__ void finish() const {}
   __device__ __forceinline__ void operator()(uint32_t taddr, const GemmCore&, const TileCoord& tc, int row, uint8_t*,
-                                             int&) const {
+                                             int, int&) const {
     const int m = tc.m_blk * kBM + row;
 #pragma unroll 1
     for (int col = 0; col < kBwdBN; col += 16) {

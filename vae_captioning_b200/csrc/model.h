@@ -107,12 +107,12 @@ class Model {
   // --- VGG16 (vgg.cu)
   std::vector<VggLayer> vgg;
   void *vgg_im2col = nullptr, *fc1_w = nullptr, *fc2_w = nullptr, *fc1_h = nullptr;
-  float *fc_acc = nullptr, *fc2_f = nullptr, *st_images = nullptr;
+  float *fc_acc = nullptr, *fc2_f = nullptr, *st_images = nullptr, *conv1_bias2 = nullptr;
   bool vgg_shadows_dirty = true, vgg_keep = false, vgg_have_unpooled = false;
   int vgg_last_B = 0;
   // fine-tune backward (vgg_bwd.cu)
   void *vgg_bwd_a = nullptr, *vgg_bwd_b = nullptr, *imf_nat = nullptr, *dfc2_pre = nullptr, *dfc1_pre = nullptr;
-  float* dfeats_f = nullptr;
+  float *dfeats_f = nullptr, *conv1_wg = nullptr;
   unsigned long long vgg_drop_seed = 0, vgg_drop_step = 0;  // Philox stream of the fc dropout masks (explicit masks win)
   int vgg_bwd_init();
   int vgg_refresh_bwd_shadows(cudaStream_t s);

@@ -109,6 +109,21 @@ __global__ void k_bias_relu(const float* __restrict__ x, const float* __restrict
   }
 }
 
+// conv1_1 runs as a [pixels/2, 64] x [64, 128] GEMM: one A row holds the 32-column im2col patches of TWO adjacent pixels
+// (a full 128-byte TMA row, no out-of-bounds half), B is the block-diagonal [[W, 0], [0, W]] so the 128 output columns
+// are the 64 channels of pixel 2i followed by those of pixel 2i+1 -- exactly the NHWC layout of the output.
+// wt bf16 [128, 64] (K-major rows n = pixel*64 + cout), bias2 fp32 [128].
+__global__ void k_conv1_shadow(const float* __restrict__ w, const float* __restrict__ bias, __nv_bfloat16* __restrict__ wt,
+                               float* __restrict__ bias2) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < 128 * 64) {
+    const int n = i / 64, k = i % 64;
+    const int pix = n / 64, co = n % 64, kk = k - pix * 32;
+    wt[i] = __float2bfloat16((kk >= 0 && kk < 27) ? w[kk * 64 + co] : 0.f);
+  }
+  if (i < 128) bias2[i] = bias[i % 64];
+}
+
 static inline int ew_grid(long long n, int block) {
   long long g = (n + block - 1) / block;
   const long long cap = (long long)num_sms() * 16;
@@ -125,7 +140,7 @@ int Model::vgg_init() {
     const bool c5 = l >= 10;
     L.p_w = pidx(std::string("cnn/") + kVggNames[l] + (c5 ? "/weights_conv" : "/weights"));
     L.p_b = pidx(std::string("cnn/") + kVggNames[l] + (c5 ? "/biases_conv" : "/biases"));
-    L.kpad = l == 0 ? 32 : 9 * L.cin;
+    L.kpad = l == 0 ? 128 : 9 * L.cin;  // conv1_1: block-diagonal [128, 64] (see k_conv1_shadow)
     VC_TRY(dalloc((uint16_t**)&L.wt, (size_t)L.cout * L.kpad));
     VC_TRY(dalloc((uint16_t**)&L.out, (size_t)B * L.hw * L.hw * L.cout));
     if (L.pool) VC_TRY(dalloc((uint16_t**)&L.pooled, (size_t)B * (L.hw / 2) * (L.hw / 2) * L.cout));
@@ -133,6 +148,7 @@ int Model::vgg_init() {
   VC_TRY(dalloc((uint16_t**)&vgg_im2col, (size_t)B * 224 * 224 * 32));
   VC_TRY(dalloc((uint16_t**)&fc1_w, (size_t)25088 * 4096));
   VC_TRY(dalloc((uint16_t**)&fc2_w, (size_t)4096 * 4096));
+  VC_TRY(dalloc(&conv1_bias2, 128));
   VC_TRY(dalloc(&fc_acc, (size_t)B * 4096));
   VC_TRY(dalloc((uint16_t**)&fc1_h, (size_t)B * 4096));
   VC_TRY(dalloc(&fc2_f, (size_t)B * 4096));
@@ -144,7 +160,11 @@ int Model::vgg_init() {
 
 int Model::vgg_refresh_shadows(cudaStream_t s) {
   ProfTag ptag("refresh_shadows");
-  for (int l = 0; l < 13; ++l) {
+  {
+    ProfScope ps(s, "refresh_shadows");
+    k_conv1_shadow<<<32, 256, 0, s>>>(pp(vgg[0].p_w), pp(vgg[0].p_b), (__nv_bfloat16*)vgg[0].wt, conv1_bias2);
+  }
+  for (int l = 1; l < 13; ++l) {
     VggLayer& L = vgg[l];
     // HWIO [3,3,Cin,Cout] == [9*Cin, Cout] row-major -> [Cout, kpad] (K-major B operand)
     VC_TRY(transpose_cast(s, pp(L.p_w), L.wt, 9 * L.cin, L.cout, L.cout, L.kpad, 0, 0));
@@ -168,11 +188,14 @@ int Model::vgg_conv_layer(int l, const void* in, int B, bool fuse_pool, cudaStre
   GemmPlan plan;
   ProfTag ptag(kVggNames[l]);
   if (l == 0) {
-    const long long M = (long long)B * L.hw * L.hw;
-    Operand A{in, M, 27, 32, false}, Bw{L.wt, L.cout, 27, 32, false};
-    VC_TRY(plan_gemm(&plan, A, nullptr, 0, Bw, (int)M, L.cout, 27, bn, 1));
+    const long long M = (long long)B * L.hw * L.hw / 2;  // two pixels per GEMM row
+    Operand A{in, M, 64, 64, false}, Bw{L.wt, 128, 64, 64, false};
+    VC_TRY(plan_gemm(&plan, A, nullptr, 0, Bw, (int)M, 128, 64, 128, 1));
     epi.mode = kRows;
-    VC_TRY(make_tmap_2d(&epi.tm, L.out, L.cout, M, L.cout, 64, 32));
+    epi.bias = conv1_bias2;
+    epi.N = 128;
+    epi.bn = 128;
+    VC_TRY(make_tmap_2d(&epi.tm, L.out, 128, M, 128, 64, 128));
     return launch_gemm(plan, epi, s);
   }
   ConvGeom g;
@@ -187,10 +210,10 @@ int Model::vgg_conv_layer(int l, const void* in, int B, bool fuse_pool, cudaStre
   }
   if (fuse_pool && L.pool) {
     epi.mode = kConvPool;
-    VC_TRY(make_tmap_nhwc(&epi.tm, L.pooled, L.cout, L.hw / 2, L.hw / 2, B, g.pw / 2, g.ph / 2, g.pn));
+    VC_TRY(make_tmap_nhwc(&epi.tm, L.pooled, L.cout, L.hw / 2, L.hw / 2, B, g.pw * g.tw / 2, g.ph * g.th / 2, g.pn * (4 / (g.tw * g.th))));
   } else {
     epi.mode = kConv;
-    VC_TRY(make_tmap_nhwc(&epi.tm, L.out, L.cout, L.hw, L.hw, B, g.pw, g.ph, g.pn));
+    VC_TRY(make_tmap_nhwc(&epi.tm, L.out, L.cout, L.hw, L.hw, B, g.pw * g.tw, g.ph * g.th, g.pn * (4 / (g.tw * g.th))));
   }
   if (halo) return launch_conv_halo(plan, epi, s);
   return launch_gemm(plan, epi, s);

@@ -139,7 +139,7 @@ int conv3x3_dgrad(cudaStream_t s, const void* dy, const void* wt_d, void* dx, in
     VC_TRY(conv_geometry(&g, hw, hw, B, cout, cin));
     VC_TRY(plan_conv(&plan, dy, wt_d, g, bnd));
   }
-  VC_TRY(make_tmap_nhwc(&epi.tm, dx, cin, hw, hw, B, g.pw, g.ph, g.pn));
+  VC_TRY(make_tmap_nhwc(&epi.tm, dx, cin, hw, hw, B, g.pw * g.tw, g.ph * g.th, g.pn * (4 / (g.tw * g.th))));
   if (halo) return launch_conv_halo(plan, epi, s);
   return launch_gemm(plan, epi, s);
 }
@@ -168,6 +168,15 @@ int relu_pool_bwd(cudaStream_t s, const void* dA, const void* out, void* dY, int
   return VC_OK;
 }
 
+// dW[k, co] = D[co, k] + D[64 + co, 32 + k] for the two-pixel-row conv1_1 filter gradient (D is 128 x 64 fp32)
+__global__ void k_conv1_fold(const float* __restrict__ D, float* __restrict__ dw) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < 27 * 64) {
+    const int k = i / 64, co = i % 64;
+    dw[i] = D[co * 64 + k] + D[(64 + co) * 64 + 32 + k];
+  }
+}
+
 int Model::vgg_bwd_init() {
   const int B = cfg.max_batch;
   for (int l = 1; l < 13; ++l) VC_TRY(dalloc((uint16_t**)&vgg[l].wt_d, (size_t)9 * vgg[l].cin * vgg[l].cout));
@@ -178,6 +187,7 @@ int Model::vgg_bwd_init() {
   VC_TRY(dalloc((uint16_t**)&dfc2_pre, (size_t)B * 4096));
   VC_TRY(dalloc((uint16_t**)&dfc1_pre, (size_t)B * 4096));
   VC_TRY(dalloc(&dfeats_f, (size_t)B * cfg.cnn_feature_size));
+  VC_TRY(dalloc(&conv1_wg, 128 * 64));
   return VC_OK;
 }
 
@@ -252,12 +262,20 @@ int Model::vgg_backward(const float* dfeats, int B, cudaStream_t s) {
     VC_TRY(relu_pool_bwd(s, dA, L.out, dY, B, L.hw, L.cout, L.pool));
     VC_TRY(colsum_bf16(s, dY, pix, L.cout, L.cout, gp(L.p_b)));
     if (l == 0) {
-      // conv1_1: dW[27, 64] = im2col[pixels, 27]^T x dY[pixels, 64] (columns 27..31 of the padded im2col are zero)
+      // conv1_1: dW[27, 64] = im2col[pixels, 27]^T x dY[pixels, 64]. Both operands are read as two-pixel rows
+      // ([pixels/2, 128] and [pixels/2, 64]: full 128-byte TMA rows, see k_conv1_shadow), which yields the 128 x 64
+      // matrix D[par*64 + co, par'*32 + k]; the filter gradient is the sum of its two parity-diagonal blocks.
       ProfTag pt("conv_wgrad");
-      Operand A{vgg_im2col, pix, 32, 32, true}, Bm{dY, pix, L.cout, L.cout, true};
+      VC_CUDA(cudaMemsetAsync(conv1_wg, 0, 128 * 64 * sizeof(float), s));
+      Operand A{dY, pix / 2, 128, 128, true}, Bm{vgg_im2col, pix / 2, 64, 64, true};
       EpiStore e{};
-      e.out = gp(L.p_w); e.ld = L.cout; e.alpha = 1.f; e.atomic = 1;
-      VC_TRY(gemm_store(s, A, nullptr, 0, Bm, 27, L.cout, (int)pix, e, 64, num_sms()));
+      e.out = conv1_wg; e.ld = 64; e.alpha = 1.f; e.atomic = 1;
+      VC_TRY(gemm_store(s, A, nullptr, 0, Bm, 128, 64, (int)(pix / 2), e, 64, num_sms()));
+      {
+        ProfScope ps(s, "conv1_fold");
+        k_conv1_fold<<<7, 256, 0, s>>>(conv1_wg, gp(L.p_w));
+      }
+      VC_CUDA(cudaGetLastError());
       break;
     }
     const void* x_in = vgg[l - 1].pool ? vgg[l - 1].pooled : vgg[l - 1].out;
