@@ -31,6 +31,9 @@ WORKLOADS = {
     "cfg3_feats_gmm_cv_b128": dict(B=128, vgg=False, prior="GMM", c_v=True),
     "cfg4_finetune_ag_cv_b256": dict(B=256, vgg=True, prior="AG", c_v=True, fine_tune=True),
     "finetune_ag_cv_b64": dict(B=64, vgg=True, prior="AG", c_v=True, fine_tune=True),
+    # BASELINE configs[4]: inference path -- greedy + beam-5 decode over 40k synthetic val images (one step = both
+    # decodes of one batch of B feature rows; metric images/s)
+    "cfg5_decode_greedy_beam5": dict(B=1024, vgg=False, prior="Normal", c_v=False, decode=True, images=40000),
 }
 DEFAULT_WORKLOAD = "cfg2_vgg_normal_b256"
 C, T, V = 5, 20, 11313
@@ -188,6 +191,129 @@ def run_reference(args, w, name):
 
 
 # ------------------------------------------------------------------------------------------------
+class _SynthDict(object):
+    """Stand-in for utils/captions.py Dictionary: ids only (<PAD>=0, <BOS>=1, <EOS>=2)."""
+
+    def __init__(self, vocab):
+        self.idx2word = {i: "w%d" % i for i in range(vocab)}
+        self.idx2word.update({0: "<PAD>", 1: "<BOS>", 2: "<EOS>"})
+        self.word2idx = {w: i for i, w in self.idx2word.items()}
+        self.vocab_size = vocab
+
+
+def run_decode_reference(args, w, name):
+    """CPU restatement of the reference generation loops (one sess.run per token per beam at batch 1,
+    vae_model/decoder.py:145-320) on a bounded sample of images, numpy float64 on the host cores."""
+    import torch
+    from oracle import cvae_oracle as O
+    from oracle import decode_oracle as D
+    cores = cpu_cores()
+    torch.set_num_threads(cores)
+    cfg = O.Config(vocab_size=V)
+    params = O.init_params(cfg, seed=1)
+    model = D.GenModel(params, cfg)
+    g = np.random.Generator(np.random.PCG64(0))
+    n_img = max(1, args.ref_batch // 8)
+    feats = np.maximum(0, g.standard_normal((n_img, 4096))).astype(np.float32)
+
+    def step():
+        for i in range(n_img):
+            eps = g.standard_normal((cfg.gen_z_samples, cfg.latent_size))
+            D.online_inference(model.make_step(feats[i], None, eps), "greedy", cfg.gen_max_len, 1.0, 1, 2)
+            D.beam_search(model.make_step(feats[i], None, eps), 5, cfg.gen_max_len, 1, 2)
+
+    for _ in range(min(args.warmup, 1)):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = (time.perf_counter() - t0) / args.steps
+    val = n_img / dt
+    sample = "%d images per step, greedy + beam-5 each, numpy restatement of the per-token sess.run loops" % n_img
+    return {"metric": "images/sec (greedy + beam-5 decode)", "value": val, "unit": "images/s", "impl": "reference",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp64", "data": "synthetic",
+            "config": {"workload": name, "images_per_step": n_img, "gen_max_len": 30, "beam": 5, "vocab": V},
+            "cpu_baseline": {"value": val, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+
+
+def run_decode(args, w, name, rank, world, local_rank):
+    """cfg 5: Decoder.online_inference('greedy') + Decoder.beam_search(beam 5) (vae_model/decoder.py:145-320) batched on
+    the device. Replicas only: every rank decodes its own images, no collective."""
+    import torch
+    import torch.distributed as dist
+    from vae_captioning_b200 import lib as L
+    from vae_captioning_b200.engine import Engine
+    from vae_captioning_b200.decode import Decoder
+    from vae_captioning_b200 import synthetic
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    lib = L.load()
+    lib.vc_launch_count.restype = ctypes.c_ulonglong
+    p = params_for(w)
+    p.mode = "inference"
+    B = w["B"]
+    eng = Engine(p, vocab_size=V, max_batch=B, max_len=T, device=local_rank)
+    eng.load_state(synthetic.init_weights(eng.variables(), seed=1))
+    dec = Decoder(eng, p, _SynthDict(V))
+    g = np.random.Generator(np.random.PCG64(rank))
+    feats = np.maximum(0, g.standard_normal((B, 4096), dtype=np.float32))
+    host = torch.from_numpy(feats).pin_memory()
+
+    def step():
+        dec.greedy_tokens(host.numpy(), rng={"seed": 7})
+        dec.beam_tokens(host.numpy(), beam_size=5, rng={"seed": 7})
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    l0 = lib.vc_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    launches = int(lib.vc_launch_count() - l0)
+    clocks = sampler.stop() if sampler else None
+    value = world * B * args.steps / (ms / 1e3)
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        ra = argparse.Namespace(**vars(args))
+        ra.steps, ra.warmup = 1, 0
+        cpu_baseline = run_decode_reference(ra, w, name)["cpu_baseline"]
+    if rank == 0:
+        # weight-streaming view of the dominant kernel (the [M, 512] x [512, V] vocabulary projection per token):
+        # algorithmic bytes per decoded token row = its logits row (bf16) + the row's share of W_o
+        line = {"metric": "images/sec (greedy + beam-5 decode)", "value": value, "unit": "images/s", "n_gpus": world,
+                "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": name, "images_per_step_per_gpu": B, "gen_max_len": 30, "beam": 5, "vocab": V,
+                           "val_images": w["images"], "seconds_for_val_set": w["images"] / value,
+                           "note": "untrained seeded weights: most captions run to gen_max_len (worst case)",
+                           "parallelism": "replicas%d" % world},
+                "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 2 * int(host.numel()) * 4,
+                        "d2h_bytes_per_step": B * 30 * 4 + B * 5 * 30 * 4 + B * 5 * 8 + B * 8},
+                "gpu_launches": launches, "clocks": clocks, "roofline": None, "cpu_baseline": cpu_baseline}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    eng.close()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -207,8 +333,14 @@ def main():
 
     if args.impl == "reference":
         if rank == 0:
-            print(json.dumps(run_reference(args, w, args.workload)), flush=True)
+            fn = run_decode_reference if w.get("decode") else run_reference
+            print(json.dumps(fn(args, w, args.workload)), flush=True)
         return 0
+    if w.get("decode"):
+        import torch
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device -- the hot path has no CPU fallback")
+        return run_decode(args, w, args.workload, rank, world, local_rank)
 
     import torch
     import torch.distributed as dist
@@ -316,7 +448,7 @@ def main():
     # per-kernel-family timing with CUDA events on the launching stream (extra steps after the timed region)
     roofline = None
     families = {}
-    if rank == 0 and not args.no_profile:
+    if rank == 0 and world == 1 and not args.no_profile:  # extra steps on one rank only would strand its all-reduce
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
