@@ -368,6 +368,8 @@ def main():
     # pinned host buffers (e2e leg) and device-resident copies (value leg)
     host = {k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory() for k, v in feed.items()}
     dev = {k: v.cuda(non_blocking=True) for k, v in host.items()}
+    if w["vgg"]:  # the e2e leg feeds the pixels as uint8, the dtype of the reference's HDF5 image store (batch_gen.py:278-294)
+        host["image_f_inputs"] = torch.from_numpy(feed["image_f_inputs"].astype(np.uint8)).pin_memory()
     torch.cuda.synchronize()
     grad_ptr, grad_n = eng.grad_buffer()
     grad_t = None
@@ -399,6 +401,8 @@ def main():
                                  images=w["vgg"] and not w.get("fine_tune"))
         else:
             d = {k: v.cuda(non_blocking=True) for k, v in host.items()}
+            if w["vgg"]:
+                d["image_f_inputs"] = d["image_f_inputs"].float()  # uint8 over PCIe, widened on the device
             feats = eng.vgg_forward_device(d["image_f_inputs"]) if (w["vgg"] and not w.get("fine_tune")) else d["image_f_inputs"]
             eng.forward_backward_device(feats, d["ann_inputs_enc"], d["ann_inputs_dec"], d["ann_lengths"], step_no[0],
                                         c_i=d.get("c_i"), rng={"seed": 1234 + rank})

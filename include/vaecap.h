@@ -122,6 +122,12 @@ int vc_train_step(vc_handle* h, const float* feats_host, const int32_t* cap_lbl_
 int vc_train_step_images(vc_handle* h, const float* images_host, const int32_t* cap_lbl_host, const int32_t* cap_in_host,
                          const int32_t* len_host, const float* c_v_host, int B, int T, int64_t global_step,
                          const vc_rng* rng, vc_step_out* out, void* stream);
+/* Same with uint8 pixels [B,224,224,3] (RGB 0..255), the form the reference's HDF5 image store keeps them in
+ * (utils/batch_gen.py:278-294, preprocess.py:26-38): a quarter of the host-to-device bytes; the conversion and the
+ * mean subtraction happen in the first device kernel. Works on fine_tune handles too (the images are then the feed). */
+int vc_train_step_images_u8(vc_handle* h, const uint8_t* images_host, const int32_t* cap_lbl_host, const int32_t* cap_in_host,
+                            const int32_t* len_host, const float* c_v_host, int B, int T, int64_t global_step,
+                            const vc_rng* rng, vc_step_out* out, void* stream);
 /* Same, with inputs already resident in device memory. */
 int vc_train_step_dev(vc_handle* h, const float* feats_dev, const int32_t* cap_lbl_dev, const int32_t* cap_in_dev,
                       const int32_t* len_dev, const float* c_v_dev, int B, int T, int64_t global_step,
@@ -148,6 +154,7 @@ int vc_forward_debug(vc_handle* h, float* logits_host, float* mu_host, float* st
  * images fp32 [B,224,224,3] RGB 0..255 (host) -> fc2 fp32 [B,4096] (host). */
 int vc_vgg_forward(vc_handle* h, const float* images_host, float* fc2_host, int B, void* stream);
 int vc_vgg_forward_dev(vc_handle* h, const float* images_dev, float* fc2_dev, int B, void* stream);
+int vc_vgg_forward_u8(vc_handle* h, const uint8_t* images_host, float* fc2_host, int B, void* stream); /* uint8 pixels */
 /* Debug taps: vc_vgg_keep_activations(h, 1) makes later forwards materialise every conv output instead of fusing
  * the 2x2 max-pools into the conv epilogues; vc_vgg_activation then returns the NHWC activation of a layer
  * ("conv1_1".."conv5_3", post-ReLU; "pool1".."pool5") of the last forward as fp32. */

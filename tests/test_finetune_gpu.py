@@ -140,3 +140,19 @@ def test_finetune_philox_dropout_and_eval():
         ref = O.forward(params, cfg, batch, emulate=True)  # explicit masks: a different draw, same distribution
     assert abs(a["rec_loss"] - float(ref["rec_loss"])) <= 0.1 * abs(float(ref["rec_loss"]))
     eng.close()
+
+
+def test_finetune_uint8_feed():
+    """uint8 pixels (the dtype of the reference's HDF5 image store, utils/batch_gen.py:278-294) through
+    vc_train_step_images_u8 give the same step as the float feed."""
+    B, T = 2, 5
+    cfg, params, batch, keep = finetune_case(B, T, seed=11)
+    outs = []
+    for dtype in (np.float32, np.uint8):
+        eng = engine_for(cfg, params, B, T)
+        f = feed(batch)
+        f["image_f_inputs"] = f["image_f_inputs"].astype(dtype)
+        outs.append(eng.train_step(anneal=0, rng=rng_with_masks(batch, keep), **f))
+        eng.close()
+    assert abs(outs[0]["rec_loss"] - outs[1]["rec_loss"]) <= 1e-5 * abs(outs[0]["rec_loss"])
+    assert abs(outs[0]["global_norm"] - outs[1]["global_norm"]) <= 1e-4 * outs[0]["global_norm"]

@@ -52,6 +52,9 @@ def test_vgg_forward_layers_and_fc2(B):
     p5 = eng.vgg_activation("pool5", B)
     ref_p5 = torch.nn.functional.max_pool2d(taps["conv5_3"].permute(0, 3, 1, 2), 2, 2).permute(0, 2, 3, 1)
     assert rel_err(p5, ref_p5.numpy()) <= 2e-2
+    # 2b) uint8 pixels (the HDF5 store's dtype): same values, a quarter of the bytes -> identical up to atomics order
+    fc2_u8 = eng.vgg_forward(images.numpy().astype(np.uint8))
+    np.testing.assert_allclose(fc2_b, fc2_u8, rtol=1e-4, atol=1e-4 * np.abs(fc2_b).max())
     # 3) device-resident entry point
     fc2_c = eng.vgg_forward_device(images.cuda()).cpu().numpy()
     np.testing.assert_allclose(fc2_a, fc2_c, rtol=1e-4, atol=1e-4 * np.abs(fc2_a).max())

@@ -157,18 +157,28 @@ int vc_train_step(vc_handle* h, const float* feats, const int32_t* lbl, const in
   VC_GUARD_END
 }
 
-int vc_train_step_images(vc_handle* h, const float* images, const int32_t* lbl, const int32_t* inp, const int32_t* len,
-                         const float* cv, int B, int T, int64_t gs, const vc_rng* rng, vc_step_out* out, void* stream) {
+static int train_step_images_impl(vc_handle* h, const void* images, bool u8, const int32_t* lbl, const int32_t* inp,
+                                  const int32_t* len, const float* cv, int B, int T, int64_t gs, const vc_rng* rng,
+                                  vc_step_out* out, void* stream) {
   VC_GUARD_BEGIN
   if (!h || !images || !lbl || !inp || !len) return set_error(VC_E_ARG, "vc_train_step_images: null argument");
   Model& m = h->m;
   cudaSetDevice(m.device);
   cudaStream_t s = (cudaStream_t)stream;
   if (m.vgg.empty()) return set_error(VC_E_STATE, "this handle was created without the CNN (with_cnn = 0)");
-  if (m.cfg.fine_tune) return vc_train_step(h, images, lbl, inp, len, cv, B, T, gs, rng, out, stream);
+  if (m.cfg.fine_tune) {  // the image batch is the feed of the trainable graph (main.py:46-48)
+    StepInputs in{};
+    VC_TRY(m.stage_inputs(reinterpret_cast<const float*>(images), lbl, inp, len, cv, B, T, &in, s, u8));
+    in.global_step = gs;
+    if (rng) in.rng = *rng;
+    VC_TRY(m.forward(in, true, s));
+    VC_TRY(m.backward(in, s));
+    VC_TRY(m.apply(1.f, s));
+    return m.fetch(out, s);
+  }
   if (B < 1 || B > m.cfg.max_batch) return set_error(VC_E_SHAPE, "batch %d exceeds max_batch %d", B, m.cfg.max_batch);
-  VC_CUDA(cudaMemcpyAsync(m.st_images, images, (size_t)B * 224 * 224 * 3 * sizeof(float), cudaMemcpyHostToDevice, s));
-  VC_TRY(m.vgg_forward(m.st_images, nullptr, B, false, nullptr, s));
+  VC_CUDA(cudaMemcpyAsync(m.st_images, images, (size_t)B * 224 * 224 * 3 * (u8 ? 1 : sizeof(float)), cudaMemcpyHostToDevice, s));
+  VC_TRY(m.vgg_forward(m.st_images, nullptr, B, false, nullptr, s, u8));
   StepInputs in{};
   // captions / lengths / c_v are staged as usual; the features come from the on-device forward
   VC_TRY(m.stage_inputs(nullptr, lbl, inp, len, cv, B, T, &in, s));
@@ -180,6 +190,15 @@ int vc_train_step_images(vc_handle* h, const float* images, const int32_t* lbl, 
   VC_TRY(m.apply(1.f, s));
   return m.fetch(out, s);
   VC_GUARD_END
+}
+
+int vc_train_step_images(vc_handle* h, const float* images, const int32_t* lbl, const int32_t* inp, const int32_t* len,
+                         const float* cv, int B, int T, int64_t gs, const vc_rng* rng, vc_step_out* out, void* stream) {
+  return train_step_images_impl(h, images, false, lbl, inp, len, cv, B, T, gs, rng, out, stream);
+}
+int vc_train_step_images_u8(vc_handle* h, const uint8_t* images, const int32_t* lbl, const int32_t* inp, const int32_t* len,
+                            const float* cv, int B, int T, int64_t gs, const vc_rng* rng, vc_step_out* out, void* stream) {
+  return train_step_images_impl(h, images, true, lbl, inp, len, cv, B, T, gs, rng, out, stream);
 }
 
 int vc_eval_step(vc_handle* h, const float* feats, const int32_t* lbl, const int32_t* inp, const int32_t* len,
@@ -219,7 +238,7 @@ int vc_vgg_forward_dev(vc_handle* h, const float* images, float* fc2, int B, voi
   VC_GUARD_END
 }
 
-int vc_vgg_forward(vc_handle* h, const float* images_host, float* fc2_host, int B, void* stream) {
+static int vgg_forward_host(vc_handle* h, const void* images_host, bool u8, float* fc2_host, int B, void* stream) {
   VC_GUARD_BEGIN
   if (!h || !images_host || !fc2_host) return set_error(VC_E_ARG, "vc_vgg_forward: null argument");
   Model& m = h->m;
@@ -227,12 +246,18 @@ int vc_vgg_forward(vc_handle* h, const float* images_host, float* fc2_host, int 
   cudaStream_t s = (cudaStream_t)stream;
   if (m.vgg.empty()) return set_error(VC_E_STATE, "this handle was created without the CNN (with_cnn = 0)");
   if (B < 1 || B > m.cfg.max_batch) return set_error(VC_E_SHAPE, "vc_vgg_forward: batch %d exceeds max_batch %d", B, m.cfg.max_batch);
-  VC_CUDA(cudaMemcpyAsync(m.st_images, images_host, (size_t)B * 224 * 224 * 3 * sizeof(float), cudaMemcpyHostToDevice, s));
-  VC_TRY(m.vgg_forward(m.st_images, nullptr, B, m.vgg_keep, nullptr, s));
+  VC_CUDA(cudaMemcpyAsync(m.st_images, images_host, (size_t)B * 224 * 224 * 3 * (u8 ? 1 : sizeof(float)), cudaMemcpyHostToDevice, s));
+  VC_TRY(m.vgg_forward(m.st_images, nullptr, B, m.vgg_keep, nullptr, s, u8));
   VC_CUDA(cudaMemcpyAsync(fc2_host, m.fc2_f, (size_t)B * 4096 * sizeof(float), cudaMemcpyDeviceToHost, s));
   VC_CUDA(cudaStreamSynchronize(s));
   return VC_OK;
   VC_GUARD_END
+}
+int vc_vgg_forward(vc_handle* h, const float* images_host, float* fc2_host, int B, void* stream) {
+  return vgg_forward_host(h, images_host, false, fc2_host, B, stream);
+}
+int vc_vgg_forward_u8(vc_handle* h, const uint8_t* images_host, float* fc2_host, int B, void* stream) {
+  return vgg_forward_host(h, images_host, true, fc2_host, B, stream);
 }
 
 int vc_decode_greedy(vc_handle* h, const float* feats_host, const float* c_v_host, int B, int max_len, int mode,

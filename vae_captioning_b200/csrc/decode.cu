@@ -327,7 +327,7 @@ int Model::decode_begin(const float* feats_dev, const float* c_v_dev, int B, con
   auto cell = [&](const void* x) -> int {
     LstmFwdArgs a{};
     a.x = x; a.h_prev = hp; a.c_prev = cp; a.h_out = hn; a.c_out = cn;
-    a.w_t_perm = dec.w_t_perm; a.bias = pp(dec.p_bias); a.inv_keep = 1.f; a.t = 0; a.N = B; a.E = E; a.H = H;
+    a.w_t_perm = dec.w_t_perm; a.bias = pp(dec.p_bias); a.inv_keep = 1.f; a.t = 0; a.N = B; a.E = E; a.H = H; a.precise = 1;
     VC_TRY(lstm_fwd_step(s, a));
     std::swap(hp, hn);
     std::swap(cp, cn);
@@ -381,7 +381,7 @@ int Model::decode_advance(int M, cudaStream_t s) {
   VC_TRY(embed_gather(s, dec_emb_h, w->tok, w->x, nullptr, 1.f, M, 1, E, V));
   LstmFwdArgs a{};
   a.x = w->x; a.h_prev = w->h[w->cur]; a.c_prev = w->c[w->cur]; a.h_out = w->h[w->cur ^ 1]; a.c_out = w->c[w->cur ^ 1];
-  a.w_t_perm = dec.w_t_perm; a.bias = pp(dec.p_bias); a.inv_keep = 1.f; a.t = 0; a.N = M; a.E = E; a.H = H;
+  a.w_t_perm = dec.w_t_perm; a.bias = pp(dec.p_bias); a.inv_keep = 1.f; a.t = 0; a.N = M; a.E = E; a.H = H; a.precise = 1;
   VC_TRY(lstm_fwd_step(s, a));
   w->cur ^= 1;
   Operand A{w->h[w->cur], M, H, H, false}, Bw{wo_t, V, H, H, false};

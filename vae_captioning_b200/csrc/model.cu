@@ -217,6 +217,7 @@ int Model::init(const vc_config& c, int dev) {
     VC_TRY(dalloc((uint16_t**)&dheads, (size_t)N * heads_cols));
   }
   VC_TRY(dalloc(&scal, 64));
+  VC_TRY(dalloc(&seq_flags, (size_t)lstm_seq_flag_count(maxN, dec.steps + 1)));
   const size_t img_elems = cfg.fine_tune ? (size_t)224 * 224 * 3 : (size_t)F;
   VC_TRY(dalloc(&st_feats, (size_t)B * img_elems));
   VC_TRY(dalloc(&st_cv, (size_t)N * K));
@@ -319,12 +320,13 @@ int Model::refresh_shadows(cudaStream_t s) {
 
 // ------------------------------------------------------------------------------------------
 int Model::stage_inputs(const float* feats, const int32_t* lbl, const int32_t* inp, const int32_t* len, const float* cv,
-                        int B, int T, StepInputs* out, cudaStream_t s) {
+                        int B, int T, StepInputs* out, cudaStream_t s, bool feats_u8) {
   if (B < 1 || B > cfg.max_batch || T < 1 || T > maxT)
     return set_error(VC_E_SHAPE, "batch %d x len %d exceeds the handle's max_batch %d / max_len %d", B, T, cfg.max_batch, maxT);
   const int N = B * cfg.num_captions;
   const size_t fe = cfg.fine_tune ? (size_t)224 * 224 * 3 : (size_t)cfg.cnn_feature_size;
-  if (feats != nullptr) VC_CUDA(cudaMemcpyAsync(st_feats, feats, B * fe * sizeof(float), cudaMemcpyHostToDevice, s));
+  if (feats != nullptr) VC_CUDA(cudaMemcpyAsync(st_feats, feats, B * fe * (feats_u8 ? 1 : sizeof(float)), cudaMemcpyHostToDevice, s));
+  out->feats_u8 = feats_u8;
   VC_CUDA(cudaMemcpyAsync(st_lbl, lbl, (size_t)N * T * sizeof(int32_t), cudaMemcpyHostToDevice, s));
   VC_CUDA(cudaMemcpyAsync(st_in, inp, (size_t)N * T * sizeof(int32_t), cudaMemcpyHostToDevice, s));
   VC_CUDA(cudaMemcpyAsync(st_len, len, (size_t)N * sizeof(int32_t), cudaMemcpyHostToDevice, s));
@@ -352,6 +354,18 @@ int Model::lstm_forward(LstmNet& L, int N, int T, const int32_t* len, void* out,
   // call because the slot pitch depends on the current batch size
   VC_CUDA(cudaMemsetAsync(Hs, 0, (size_t)N * L.H * 2, s));
   VC_CUDA(cudaMemsetAsync(L.Cs, 0, (size_t)N * L.H * sizeof(float), s));
+  if (lstm_seq_applicable(N, L.H, steps)) {  // one persistent launch for the whole sequence
+    LstmSeqFwdArgs a{};
+    a.X = X; a.Hs = Hs; a.Cs = L.Cs; a.G = Gt; a.out = out;
+    a.w_t_perm = L.w_t_perm;
+    a.bias = pp(L.p_bias);
+    a.lengths = len;
+    a.out_keep = out_keep;
+    a.inv_keep = 1.f / cfg.dec_lstm_drop;
+    a.flags = seq_flags;
+    a.pre = L.pre; a.T = T; a.steps = steps; a.N = N; a.E = L.E; a.H = L.H;
+    return lstm_fwd_seq(s, a);
+  }
   for (int st = 0; st < steps; ++st) {
     LstmFwdArgs a{};
     const int t = st - L.pre;
@@ -382,7 +396,8 @@ int Model::lstm_backward(LstmNet& L, int N, int T, const int32_t* len, const flo
   const int steps = L.pre + T;
   uint16_t* Gt = (uint16_t*)L.G;
   uint16_t* dGt = (uint16_t*)L.dG;
-  for (int st = steps - 1; st >= 0; --st) {
+  const bool seq = lstm_seq_applicable(N, L.H, steps);
+  for (int st = steps - 1; st >= (seq ? steps - 1 : 0); --st) {
     LstmBwdArgs a{};
     const int t = st - L.pre;
     a.d_gates_next = st == steps - 1 ? nullptr : dGt + (size_t)(st + 1) * N * 4 * L.H;
@@ -403,6 +418,14 @@ int Model::lstm_backward(LstmNet& L, int N, int T, const int32_t* len, const flo
     a.E = L.E;
     a.H = L.H;
     VC_TRY(lstm_bwd_step(s, a));
+  }
+  if (seq) {  // steps steps-2 .. 0: one persistent launch
+    LstmSeqBwdArgs a{};
+    a.w_nat = L.w_nat; a.G = Gt; a.Cs = L.Cs; a.d_out = d_out; a.out_keep = out_keep;
+    a.inv_keep = 1.f / cfg.dec_lstm_drop;
+    a.dh_carry = L.dh_carry; a.dc_carry = L.dc_carry; a.dG = dGt; a.lengths = len; a.flags = seq_flags;
+    a.pre = L.pre; a.T = T; a.steps = steps; a.N = N; a.E = L.E; a.H = L.H;
+    VC_TRY(lstm_bwd_seq(s, a));
   }
   // weight gradient: dW[E+H, 4H] = [X ; H_prev]^T x dG over all steps (one GEMM, split-K, fp32 atomics)
   const long long rows = (long long)steps * N;
@@ -470,7 +493,7 @@ int Model::forward(const StepInputs& in, bool write_grad, cudaStream_t s) {
   if (cfg.fine_tune) {
     vgg_drop_seed = in.rng.seed;
     vgg_drop_step = (unsigned long long)in.global_step;
-    VC_TRY(vgg_forward(in.feats, nullptr, B, true, in.rng.cnn_keep_dev, s));
+    VC_TRY(vgg_forward(in.feats, nullptr, B, true, in.rng.cnn_keep_dev, s, in.feats_u8));
     feats = fc2_f;
     // l2_regularizer(weight_decay) on every cnn/ variable joins rec_loss through get_total_loss (main.py:67-74,
     // 159-160; Q11): scal[8] = sum of squares of the cnn/ region (its padding is zero)

@@ -51,7 +51,8 @@ struct VggLayer {
 struct DecodeWs;  // decode.cu
 
 struct StepInputs {
-  const float* feats;     // device fp32 [B, F] (or images when fine_tune)
+  const float* feats;     // device fp32 [B, F] (or images when fine_tune; uint8 pixels when feats_u8)
+  bool feats_u8 = false;
   const int32_t* cap_lbl; // device [N, T]
   const int32_t* cap_in;
   const int32_t* len;
@@ -103,6 +104,7 @@ class Model {
   float *st_feats = nullptr, *st_cv = nullptr;
   int32_t *st_lbl = nullptr, *st_in = nullptr, *st_len = nullptr;
   float* host_scal = nullptr;  // pinned
+  int* seq_flags = nullptr;    // inter-CTA step counters of the persistent LSTM kernels
 
   // --- VGG16 (vgg.cu)
   std::vector<VggLayer> vgg;
@@ -120,7 +122,8 @@ class Model {
   int vgg_init();
   int vgg_refresh_shadows(cudaStream_t s);
   int vgg_conv_layer(int l, const void* in, int B, bool fuse_pool, cudaStream_t s);
-  int vgg_forward(const float* images, float* fc2_out, int B, bool keep_unpooled, const float* fc_keep, cudaStream_t s);
+  int vgg_forward(const float* images, float* fc2_out, int B, bool keep_unpooled, const float* fc_keep, cudaStream_t s,
+                  bool images_u8 = false);
   int vgg_activation(const char* layer, float* dst_host);
 
   // --- generation (decode.cu)
@@ -157,7 +160,7 @@ class Model {
   int apply(float grad_scale, cudaStream_t s);
   int fetch(vc_step_out* out, cudaStream_t s);
   int stage_inputs(const float* feats, const int32_t* lbl, const int32_t* inp, const int32_t* len, const float* cv,
-                   int B, int T, StepInputs* out, cudaStream_t s);
+                   int B, int T, StepInputs* out, cudaStream_t s, bool feats_u8 = false);
   int forward_debug(float* logits_host, float* mu_host, float* std_host, float* z_host, float* kl_host, float* ce_host);
 
  private:

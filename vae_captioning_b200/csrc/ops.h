@@ -27,6 +27,7 @@ struct LstmFwdArgs {
   long long out_keep_ld;
   float inv_keep;
   int t, N, E, H;
+  int precise;           // see EpiLstmFwd::precise
 };
 int lstm_fwd_step(cudaStream_t stream, const LstmFwdArgs& a);
 
@@ -47,6 +48,40 @@ struct LstmBwdArgs {
   int t, N, E, H;
 };
 int lstm_bwd_step(cudaStream_t stream, const LstmBwdArgs& a);
+
+// lstm_seq.cu: whole-sequence persistent kernels (one launch for all steps) --------------------
+struct LstmSeqFwdArgs {
+  const void* X;         // bf16 [steps, N, E]
+  void* Hs;              // bf16 [steps+1, N, H]; slot 0 = initial state (zeroed by the caller)
+  float* Cs;             // fp32 [steps+1, N, H]; slot 0 zeroed by the caller
+  void* G;               // bf16 [steps, N, 4H] activated gates (for BPTT)
+  void* out;             // bf16 [T, N, H] emitted outputs of the caption steps (nullable)
+  const void* w_t_perm;  // bf16 [4H gate-interleaved, E+H]
+  const float* bias;
+  const int* lengths;    // nullable
+  const float* out_keep; // nullable [N, T, H]
+  float inv_keep;
+  int* flags;            // lstm_seq_flag_count(N, steps) ints of scratch
+  int pre, T, steps, N, E, H;
+};
+struct LstmSeqBwdArgs {
+  const void* w_nat;     // bf16 [E+H, 4H]
+  const void* G;         // bf16 [steps, N, 4H]
+  const float* Cs;       // fp32 [steps+1, N, H]
+  const float* d_out;    // fp32 [T, N, H] (nullable)
+  const float* out_keep; // nullable
+  float inv_keep;
+  float* dh_carry;
+  float* dc_carry;
+  void* dG;              // bf16 [steps, N, 4H]; slot steps-1 already filled (lstm_bwd_step with d_gates_next = nullptr)
+  const int* lengths;
+  int* flags;
+  int pre, T, steps, N, E, H;
+};
+bool lstm_seq_applicable(int N, int H, int steps);
+int lstm_seq_flag_count(int N, int steps);
+int lstm_fwd_seq(cudaStream_t stream, const LstmSeqFwdArgs& a);
+int lstm_bwd_seq(cudaStream_t stream, const LstmSeqBwdArgs& a);
 
 // vgg_bwd.cu -------------------------------------------------------------------------------
 int conv3x3_wgrad(cudaStream_t s, const void* x, const void* dy, float* dw, int B, int hw, int cin, int cout);

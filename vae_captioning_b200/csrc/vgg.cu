@@ -27,7 +27,8 @@ bool vgg_layer_pool(int l) { return kVggPool[l]; }
 // ------------------------------------------------------------------------------------------
 // images fp32 [B,224,224,3] (RGB 0..255) -> A bf16 [B*224*224, 32]: column (r*3+s)*3+c holds
 // (pixel(h+r-1, w+s-1, c) - mean[c]) or 0 outside the image; columns 27..31 are zero.
-__global__ void k_im2col_rgb(const float* __restrict__ img, __nv_bfloat16* __restrict__ A, int B, int H, int W) {
+template <class TIn>
+__global__ void k_im2col_rgb(const TIn* __restrict__ img, __nv_bfloat16* __restrict__ A, int B, int H, int W) {
   const long long total = (long long)B * H * W;
   const float mean[3] = {123.68f, 116.779f, 103.939f};  // image_embeddings.py:30-34
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -44,9 +45,9 @@ __global__ void k_im2col_rgb(const float* __restrict__ img, __nv_bfloat16* __res
       for (int s = 0; s < 3; ++s) {
         const int hh = h + r - 1, ww = w + s - 1;
         const bool ok = hh >= 0 && hh < H && ww >= 0 && ww < W;
-        const float* p = img + ((b * H + hh) * W + ww) * 3;
+        const TIn* p = img + ((b * H + hh) * W + ww) * 3;
 #pragma unroll
-        for (int c = 0; c < 3; ++c) v[(r * 3 + s) * 3 + c] = ok ? p[c] - mean[c] : 0.f;
+        for (int c = 0; c < 3; ++c) v[(r * 3 + s) * 3 + c] = ok ? static_cast<float>(p[c]) - mean[c] : 0.f;
       }
     }
     uint4* dst = reinterpret_cast<uint4*>(A + i * 32);
@@ -222,14 +223,17 @@ int Model::vgg_conv_layer(int l, const void* in, int B, bool fuse_pool, cudaStre
 // images: device fp32 [B,224,224,3]; fc2_out: device fp32 [B,4096] (nullable -> only fc2_f is filled).
 // keep_unpooled: materialise every conv output (debug taps / fine-tune backward) instead of fusing the pools.
 int Model::vgg_forward(const float* images, float* fc2_out, int B, bool keep_unpooled, const float* fc_keep,
-                       cudaStream_t s) {
+                       cudaStream_t s, bool images_u8) {
   if (vgg.empty()) return set_error(VC_E_STATE, "this handle was created without the CNN (with_cnn = 0)");
   if (B < 1 || B > cfg.max_batch) return set_error(VC_E_SHAPE, "vgg_forward: batch %d exceeds max_batch %d", B, cfg.max_batch);
   if (vgg_shadows_dirty) VC_TRY(vgg_refresh_shadows(s));
   {
     ProfScope ps(s, "im2col_rgb");
     const long long n = (long long)B * 224 * 224;
-    k_im2col_rgb<<<ew_grid(n, 256), 256, 0, s>>>(images, (__nv_bfloat16*)vgg_im2col, B, 224, 224);
+    if (images_u8)  // uint8 pixels as the HDF5 image store keeps them (utils/batch_gen.py:278-294): a quarter of the bytes
+      k_im2col_rgb<uint8_t><<<ew_grid(n, 256), 256, 0, s>>>(reinterpret_cast<const uint8_t*>(images), (__nv_bfloat16*)vgg_im2col, B, 224, 224);
+    else
+      k_im2col_rgb<float><<<ew_grid(n, 256), 256, 0, s>>>(images, (__nv_bfloat16*)vgg_im2col, B, 224, 224);
   }
   VC_CUDA(cudaGetLastError());
   const void* x = vgg_im2col;

@@ -114,6 +114,8 @@ class Engine(object):
         lib.vc_train_step.argtypes = step_args + [ctypes.POINTER(VcStepOut), vp]
         lib.vc_train_step_dev.argtypes = step_args + [ctypes.POINTER(VcStepOut), vp]
         lib.vc_train_step_images.argtypes = step_args + [ctypes.POINTER(VcStepOut), vp]
+        lib.vc_train_step_images_u8.argtypes = step_args + [ctypes.POINTER(VcStepOut), vp]
+        lib.vc_vgg_forward_u8.argtypes = [vp, vp, vp, ci, vp]
         lib.vc_forward_backward_dev.argtypes = step_args + [vp]
         lib.vc_eval_step.argtypes = [vp, vp, vp, vp, vp, vp, ci, ci, ctypes.POINTER(VcRng), ctypes.POINTER(VcStepOut), vp]
         lib.vc_set_cluster_means.argtypes = [vp, vp]
@@ -219,7 +221,9 @@ class Engine(object):
 
         Host (numpy) inputs: copied to the device inside the call. Returns dict(kld, rec_loss, lower_bound,
         annealing, global_norm, n_tokens), or None when fetch=False (no synchronisation)."""
-        feats = _f32(image_f_inputs)
+        # uint8 pixel arrays (the HDF5 image store's dtype, utils/batch_gen.py:278-294) are fed as they are
+        u8 = getattr(image_f_inputs, "dtype", None) == np.uint8 and (images or self.cfg.fine_tune)
+        feats = np.ascontiguousarray(image_f_inputs) if u8 else _f32(image_f_inputs)
         lbl, inp = _i32(ann_inputs_enc), _i32(ann_inputs_dec)
         ln = _i32(np.asarray(ann_lengths).ravel())
         cv = _f32(c_i) if c_i is not None else None
@@ -228,7 +232,7 @@ class Engine(object):
         r, keep = self._rng(rng)
         out = VcStepOut()
         self._keep = [feats, lbl, inp, ln, cv, keep]
-        fn = self.lib.vc_train_step_images if images else self.lib.vc_train_step
+        fn = self.lib.vc_train_step_images_u8 if u8 else (self.lib.vc_train_step_images if images else self.lib.vc_train_step)
         L.check(fn(self._h, _np_ptr(feats), _np_ptr(lbl), _np_ptr(inp), _np_ptr(ln), _np_ptr(cv), B, T,
                                        int(anneal), ctypes.byref(r), ctypes.byref(out) if fetch else None, self._stream()))
         return out.as_dict() if fetch else None
@@ -294,11 +298,13 @@ class Engine(object):
     def vgg_forward(self, images):
         """sess.run(features, {input_img: images}) of Data.extract_features_from_dir (utils/data.py:120-125), batched:
         images [B,224,224,3] RGB 0..255 (host) -> fc2 features fp32 [B,4096] (host)."""
-        img = _f32(images)
+        u8 = getattr(images, "dtype", None) == np.uint8
+        img = np.ascontiguousarray(images) if u8 else _f32(images)
         if img.ndim != 4 or img.shape[1:] != (224, 224, 3):
             raise ValueError("images must be [B,224,224,3], got %s" % (img.shape,))
         out = np.empty((img.shape[0], 4096), np.float32)
-        L.check(self.lib.vc_vgg_forward(self._h, _np_ptr(img), _np_ptr(out), img.shape[0], self._stream()))
+        fn = self.lib.vc_vgg_forward_u8 if u8 else self.lib.vc_vgg_forward
+        L.check(fn(self._h, _np_ptr(img), _np_ptr(out), img.shape[0], self._stream()))
         return out
 
     def vgg_forward_device(self, images):
