@@ -480,6 +480,13 @@ def main():
             ms_c = sum(families[k]["ms_per_step"] for k in layer_fams)
             families["conv"] = {"ms_per_step": ms_c, "launches_per_step": sum(families[k]["launches_per_step"] for k in layer_fams),
                                 "bound": "tensor", "achieved": work["conv"][1] / (ms_c / 1e3) / 1e12}
+        for agg, pre in (("conv_wgrad", "wgrad"), ("conv_dgrad", "dgrad")):
+            parts = [k for k in families if k.startswith(pre) and k[len(pre):len(pre) + 1].isdigit()]
+            if parts:
+                ms_c = sum(families[k]["ms_per_step"] for k in parts)
+                families[agg] = {"ms_per_step": ms_c, "launches_per_step": sum(families[k]["launches_per_step"] for k in parts),
+                                 "bound": "tensor", "achieved": work[agg][1] / (ms_c / 1e3) / 1e12}
+                layer_fams += parts
         if families:
             top = max((k for k in families if k not in layer_fams), key=lambda k: families[k]["ms_per_step"])
             f = families[top]

@@ -60,7 +60,8 @@ def test_relu_pool_backward_bit_exact(B, hw, C, pooled):
     dA = torch.randn(B, ho, ho, C, generator=g).to(torch.bfloat16)
     od, dAd = out.cuda(), dA.cuda()
     dY = torch.full((B, hw, hw, C), 3.0, dtype=torch.bfloat16, device="cuda")
-    L.check(lib.vc_relu_pool_bwd(L.ptr(dAd), L.ptr(od), L.ptr(dY), B, hw, C, pooled, L.stream_ptr()))
+    db = torch.zeros(C, device="cuda")
+    L.check(lib.vc_relu_pool_bwd(L.ptr(dAd), L.ptr(od), L.ptr(dY), L.ptr(db), B, hw, C, pooled, L.stream_ptr()))
     torch.cuda.synchronize()
     o32 = out.float().permute(0, 3, 1, 2).requires_grad_(True)  # CPU autograd: first-max routing
     r = torch.relu(o32)  # out is post-ReLU: relu'(out) = out > 0
@@ -68,3 +69,6 @@ def test_relu_pool_backward_bit_exact(B, hw, C, pooled):
     y.backward(dA.float().permute(0, 3, 1, 2))
     ref = o32.grad.permute(0, 2, 3, 1).to(torch.bfloat16)
     assert torch.equal(dY.cpu(), ref)
+    # fused bias gradient: per-channel sum of dY (fp32 accumulation of the bf16 values)
+    want = ref.float().sum(dim=(0, 1, 2))
+    assert (db.cpu() - want).abs().max().item() <= 1e-3 * max(1.0, want.abs().max().item())

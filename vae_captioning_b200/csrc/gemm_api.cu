@@ -72,6 +72,8 @@ extern "C" int vc_conv3x3_bwd(const void* x, const void* dy, const float* w, flo
   return st;
 }
 
-extern "C" int vc_relu_pool_bwd(const void* dA, const void* out, void* dY, int B, int hw, int C, int pooled, void* stream) {
-  return vc::relu_pool_bwd(static_cast<cudaStream_t>(stream), dA, out, dY, B, hw, C, pooled != 0);
+// db: fp32 [C] device, accumulated into (the bias gradient = per-channel sum of dY)
+extern "C" int vc_relu_pool_bwd(const void* dA, const void* out, void* dY, float* db, int B, int hw, int C, int pooled,
+                                void* stream) {
+  return vc::relu_pool_bwd(static_cast<cudaStream_t>(stream), dA, out, dY, B, hw, C, pooled != 0, db);
 }

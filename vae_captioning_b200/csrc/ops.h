@@ -84,10 +84,12 @@ int lstm_fwd_seq(cudaStream_t stream, const LstmSeqFwdArgs& a);
 int lstm_bwd_seq(cudaStream_t stream, const LstmSeqBwdArgs& a);
 
 // vgg_bwd.cu -------------------------------------------------------------------------------
-int conv3x3_wgrad(cudaStream_t s, const void* x, const void* dy, float* dw, int B, int hw, int cin, int cout);
-int conv3x3_dgrad(cudaStream_t s, const void* dy, const void* wt_d, void* dx, int B, int hw, int cin, int cout);
+int conv3x3_wgrad(cudaStream_t s, const void* x, const void* dy, float* dw, int B, int hw, int cin, int cout,
+                  const char* tag = "conv_wgrad");
+int conv3x3_dgrad(cudaStream_t s, const void* dy, const void* wt_d, void* dx, int B, int hw, int cin, int cout,
+                  const char* tag = "conv_dgrad");
 int dgrad_shadow(cudaStream_t s, const float* w_hwio, void* wt_d, int cin, int cout);
-int relu_pool_bwd(cudaStream_t s, const void* dA, const void* out, void* dY, int B, int hw, int C, bool pooled);
+int relu_pool_bwd(cudaStream_t s, const void* dA, const void* out, void* dY, int B, int hw, int C, bool pooled, float* db);
 
 // elementwise.cu ---------------------------------------------------------------------------
 int cast_f32_bf16(cudaStream_t s, const float* src, void* dst, long long rows, int cols, long long ld_src,

@@ -22,8 +22,23 @@ static inline int ew_grid(long long n, int block) {
   return (int)(g > cap ? cap : (g < 1 ? 1 : g));
 }
 
-// dY = dA * (out > 0), 8 channels per thread (ReLU derivative; un-pooled layers)
-__global__ void k_relu_bwd(const uint4* __restrict__ dA, const uint4* __restrict__ out, uint4* __restrict__ dY, long long n8) {
+// Bias gradient fused into the derivative kernels: C/8 divides the grid stride, so a thread sees the same 8 channels
+// in every iteration and keeps their sums in registers; one shared-memory and one global atomic per channel per CTA.
+__device__ __forceinline__ void bias_grad_flush(const float (&acc)[8], int c8, int C, float* __restrict__ db) {
+  extern __shared__ float s_db[];
+  for (int c = threadIdx.x; c < C; c += blockDim.x) s_db[c] = 0.f;
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < 8; ++j) atomicAdd(&s_db[c8 * 8 + j], acc[j]);
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) atomicAdd(db + c, s_db[c]);
+}
+
+// dY = dA * (out > 0), 8 channels per thread (ReLU derivative; un-pooled layers); db[c] += sum of dY over pixels
+__global__ void k_relu_bwd(const uint4* __restrict__ dA, const uint4* __restrict__ out, uint4* __restrict__ dY, long long n8,
+                           int C, float* __restrict__ db) {
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  const int c8 = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) % (C / 8));
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
     uint4 g = dA[i];
     const uint4 o = out[i];
@@ -36,18 +51,23 @@ __global__ void k_relu_bwd(const uint4* __restrict__ dA, const uint4* __restrict
       gf.x = of.x > 0.f ? gf.x : 0.f;
       gf.y = of.y > 0.f ? gf.y : 0.f;
       gv[j] = __floats2bfloat162_rn(gf.x, gf.y);
+      acc[2 * j] += gf.x;
+      acc[2 * j + 1] += gf.y;
     }
     dY[i] = g;
   }
+  bias_grad_flush(acc, c8, C, db);
 }
 
 // 2x2/2 max-pool + ReLU derivative: dA is the gradient of the pooled map [B, H/2, W/2, C]; dY (un-pooled,
 // [B, H, W, C]) receives it at the window's first maximum (scan order (0,0),(0,1),(1,0),(1,1), as TF's and
 // torch's MaxPoolGrad do) if that maximum is positive, zero elsewhere. One thread = one window x 8 channels.
 __global__ void k_pool_relu_bwd(const __nv_bfloat16* __restrict__ dA, const __nv_bfloat16* __restrict__ out,
-                                __nv_bfloat16* __restrict__ dY, int B, int H, int W, int C) {
+                                __nv_bfloat16* __restrict__ dY, int B, int H, int W, int C, float* __restrict__ db) {
   const int Ho = H / 2, Wo = W / 2, C8 = C / 8;
   const long long total = (long long)B * Ho * Wo * C8;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  const int c8_fix = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) % C8);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int c8 = (int)(i % C8);
     long long r = i / C8;
@@ -78,11 +98,13 @@ __global__ void k_pool_relu_bwd(const __nv_bfloat16* __restrict__ dA, const __nv
 #pragma unroll
         for (int k = 0; k < 4; ++k)
           if (k == arg) reinterpret_cast<__nv_bfloat16*>(&o[k])[j] = gv[j];
+        acc[j] += __bfloat162float(gv[j]);
       }
     }
 #pragma unroll
     for (int k = 0; k < 4; ++k) *reinterpret_cast<uint4*>(dY + offs[k]) = o[k];
   }
+  bias_grad_flush(acc, c8_fix, C, db);
 }
 
 // fc layers: dPre = dOut * scale where the (post-ReLU, post-dropout) activation y is positive. y > 0 <=> the unit
@@ -110,8 +132,8 @@ __global__ void k_dgrad_shadow(const float* __restrict__ w, __nv_bfloat16* __res
 }
 
 // dW[9*Cin, Cout] (fp32, HWIO row-major, accumulated with atomics: the caller zeroes it) += patches(x)^T x dY
-int conv3x3_wgrad(cudaStream_t s, const void* x, const void* dy, float* dw, int B, int hw, int cin, int cout) {
-  ProfTag pt("conv_wgrad");
+int conv3x3_wgrad(cudaStream_t s, const void* x, const void* dy, float* dw, int B, int hw, int cin, int cout, const char* tag) {
+  ProfTag pt(tag);
   const int bn = cout >= 256 ? 256 : cout;
   GemmPlan plan;
   const int tiles = ((9 * cin + 127) / 128) * (cout / bn);
@@ -123,8 +145,8 @@ int conv3x3_wgrad(cudaStream_t s, const void* x, const void* dy, float* dw, int 
 }
 
 // dx [B, hw, hw, Cin] (bf16 NHWC) = conv3x3_same(dy, tap-reversed W^T); wt_d is the [Cin, 9*Cout] shadow
-int conv3x3_dgrad(cudaStream_t s, const void* dy, const void* wt_d, void* dx, int B, int hw, int cin, int cout) {
-  ProfTag pt("conv_dgrad");
+int conv3x3_dgrad(cudaStream_t s, const void* dy, const void* wt_d, void* dx, int B, int hw, int cin, int cout, const char* tag) {
+  ProfTag pt(tag);
   const int bnd = cin >= 256 ? 256 : cin;
   EpiTma epi{};
   epi.bias = nullptr; epi.N = cin; epi.bn = bnd; epi.relu = 0; epi.alpha = 1.f; epi.mode = kConv;
@@ -154,15 +176,17 @@ int dgrad_shadow(cudaStream_t s, const float* w_hwio, void* wt_d, int cin, int c
 }
 
 // ReLU (+ 2x2 max-pool when pooled) derivative: dA -> dY (un-pooled), see the kernels above
-int relu_pool_bwd(cudaStream_t s, const void* dA, const void* out, void* dY, int B, int hw, int C, bool pooled) {
+int relu_pool_bwd(cudaStream_t s, const void* dA, const void* out, void* dY, int B, int hw, int C, bool pooled, float* db) {
   const long long pix = (long long)B * hw * hw;
+  if (C % 8 != 0 || 256 % (C / 8) != 0) return set_error(VC_E_SHAPE, "relu_pool_bwd: C=%d must be 8 x a divisor of 256", C);
+  const size_t smem = (size_t)C * sizeof(float);
   if (pooled) {
     ProfScope ps(s, "pool_relu_bwd");
-    k_pool_relu_bwd<<<ew_grid(pix / 4 * (C / 8), 256), 256, 0, s>>>((const __nv_bfloat16*)dA, (const __nv_bfloat16*)out,
-                                                                   (__nv_bfloat16*)dY, B, hw, hw, C);
+    k_pool_relu_bwd<<<ew_grid(pix / 4 * (C / 8), 256), 256, smem, s>>>((const __nv_bfloat16*)dA, (const __nv_bfloat16*)out,
+                                                                      (__nv_bfloat16*)dY, B, hw, hw, C, db);
   } else {
     ProfScope ps(s, "relu_bwd");
-    k_relu_bwd<<<ew_grid(pix * (C / 8), 256), 256, 0, s>>>((const uint4*)dA, (const uint4*)out, (uint4*)dY, pix * (C / 8));
+    k_relu_bwd<<<ew_grid(pix * (C / 8), 256), 256, smem, s>>>((const uint4*)dA, (const uint4*)out, (uint4*)dY, pix * (C / 8), C, db);
   }
   VC_CUDA(cudaGetLastError());
   return VC_OK;
@@ -259,13 +283,12 @@ int Model::vgg_backward(const float* dfeats, int B, cudaStream_t s) {
   for (int l = 12; l >= 0; --l) {
     VggLayer& L = vgg[l];
     const long long pix = (long long)B * L.hw * L.hw;
-    VC_TRY(relu_pool_bwd(s, dA, L.out, dY, B, L.hw, L.cout, L.pool));
-    VC_TRY(colsum_bf16(s, dY, pix, L.cout, L.cout, gp(L.p_b)));
+    VC_TRY(relu_pool_bwd(s, dA, L.out, dY, B, L.hw, L.cout, L.pool, gp(L.p_b)));  // + bias gradient
     if (l == 0) {
       // conv1_1: dW[27, 64] = im2col[pixels, 27]^T x dY[pixels, 64]. Both operands are read as two-pixel rows
       // ([pixels/2, 128] and [pixels/2, 64]: full 128-byte TMA rows, see k_conv1_shadow), which yields the 128 x 64
       // matrix D[par*64 + co, par'*32 + k]; the filter gradient is the sum of its two parity-diagonal blocks.
-      ProfTag pt("conv_wgrad");
+      ProfTag pt("wgrad1_1");
       VC_CUDA(cudaMemsetAsync(conv1_wg, 0, 128 * 64 * sizeof(float), s));
       Operand A{dY, pix / 2, 128, 128, true}, Bm{vgg_im2col, pix / 2, 64, 64, true};
       EpiStore e{};
@@ -279,8 +302,12 @@ int Model::vgg_backward(const float* dfeats, int B, cudaStream_t s) {
       break;
     }
     const void* x_in = vgg[l - 1].pool ? vgg[l - 1].pooled : vgg[l - 1].out;
-    VC_TRY(conv3x3_wgrad(s, x_in, dY, gp(L.p_w), B, L.hw, L.cin, L.cout));
-    VC_TRY(conv3x3_dgrad(s, dY, L.wt_d, dA, B, L.hw, L.cin, L.cout));
+    static const char* kWg[13] = {"wgrad1_1", "wgrad1_2", "wgrad2_1", "wgrad2_2", "wgrad3_1", "wgrad3_2", "wgrad3_3", "wgrad4_1",
+                                  "wgrad4_2", "wgrad4_3", "wgrad5_1", "wgrad5_2", "wgrad5_3"};
+    static const char* kDg[13] = {"", "dgrad1_2", "dgrad2_1", "dgrad2_2", "dgrad3_1", "dgrad3_2", "dgrad3_3", "dgrad4_1",
+                                  "dgrad4_2", "dgrad4_3", "dgrad5_1", "dgrad5_2", "dgrad5_3"};
+    VC_TRY(conv3x3_wgrad(s, x_in, dY, gp(L.p_w), B, L.hw, L.cin, L.cout, kWg[l]));
+    VC_TRY(conv3x3_dgrad(s, dY, L.wt_d, dA, B, L.hw, L.cin, L.cout, kDg[l]));
   }
   return VC_OK;
 }

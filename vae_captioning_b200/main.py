@@ -1,0 +1,150 @@
+"""`main.py` of the reference (main.py:14-300) on the B200 path: same flags (`Parameters.parse_args`), same loop
+structure, prints and file outputs (`./checkpoints/{checkpoint}.ckpt*`, `./val_{gen_name}.json`, `./test_{gen_name}.json`),
+with the TF graph + session replaced by `Engine` / `Decoder`.
+
+The data side (COCO json / jpg / hdf5 readers, utils/data.py, utils/batch_gen.py) is outside the hot path (SURVEY 2,
+"OUT" rows); `feeder` is anything with the reference generators' interface. Without one, a seeded synthetic feeder
+with the reference's shapes and dtypes is used (there is no COCO on the box):
+
+    python -m vae_captioning_b200.main --gpu 0 --bs 32 --epochs 1 [--prior AG --c_v] [--mode inference]
+"""
+import os
+import sys
+
+import numpy as np
+
+from . import checkpoint, synthetic
+from .caption_utils import preprocess_captions
+from .parameters import Parameters
+
+
+class SyntheticFeeder(object):
+    """Stands in for Data.load_train_data_generator / get_valid_data / get_test_data (utils/data.py, batch_gen.py:164-345):
+    yields (f_images_batch, (inputs, labels), lengths, c_v) with captions as [B, C, T] like the reference's generator."""
+
+    def __init__(self, params, vocab_size, batches, seed=0, T=20):
+        self.params, self.V, self.batches, self.seed, self.T = params, vocab_size, batches, seed, T
+
+    def _batch(self, i):
+        p = self.params
+        f = synthetic.make_batch(p.batch_size, p.num_captions, self.T, self.V, seed=self.seed + i, images=p.fine_tune,
+                                 cluster_vectors=True, ragged=True)
+        B, C, T = p.batch_size, p.num_captions, self.T
+        c_v = np.concatenate([np.zeros((B * C, 1), np.float32), f["c_i"]], axis=1).reshape(B, C, 91)
+        lengths = f["ann_lengths"].astype(np.float64).reshape(B, C)  # float64 like batch_gen.py:317; 0 = missing caption
+        return f["image_f_inputs"], (f["ann_inputs_dec"].reshape(B, C, T), f["ann_inputs_enc"].reshape(B, C, T)), lengths, c_v
+
+    def next_batch(self, use_obj_vectors=False, num_captions=1):
+        for i in range(self.batches):
+            yield self._batch(i)
+
+    def next_val_batch(self, get_image_ids=False, use_obj_vectors=False):
+        for i in range(self.batches):
+            feats, caps, lens, c_v = self._batch(1000 + i)
+            ids = list(range(i * len(feats), (i + 1) * len(feats)))
+            yield feats, caps, lens, ids, c_v[:, 0, :]
+
+    def next_test_batch(self, use_obj_vectors=False):
+        for i in range(self.batches):
+            feats, _, _, c_v = self._batch(2000 + i)
+            yield feats, list(range(i * len(feats), (i + 1) * len(feats))), c_v[:, 0, :]
+
+
+class _Vocabulary(object):
+    def __init__(self, vocab_size):
+        self.idx2word = {i: "w%d" % i for i in range(vocab_size)}
+        self.idx2word.update({0: "<PAD>", 1: "<BOS>", 2: "<EOS>"})
+        self.word2idx = {w: i for i, w in self.idx2word.items()}
+        self.vocab_size = vocab_size
+
+
+def _feed(params, f_images_batch, captions_batch, cl_batch, c_v):
+    """main.py:225-236: flatten [B, C, T] captions, pick labels/inputs, drop the background cluster column."""
+    if params.num_captions > 1:
+        captions_batch, cl_batch, c_v = preprocess_captions(captions_batch, cl_batch, c_v)
+    feed = dict(image_f_inputs=f_images_batch, ann_inputs_enc=captions_batch[1], ann_inputs_dec=captions_batch[0],
+                ann_lengths=cl_batch)
+    if params.use_c_v or params.prior in ("GMM", "AG"):
+        feed["c_i"] = np.asarray(c_v)[:, 1:]
+    return feed
+
+
+def run(params, feeder=None, val_feeder=None, test_feeder=None, vocabulary=None, device=0, out=print, max_len=64,
+        report_every=500):
+    """The body of main() (main.py:14-289). Returns the Engine (its variables are the checkpoint)."""
+    from .decode import Decoder
+    from .engine import Engine
+    from . import inference as inference_mod
+    vocab = vocabulary or _Vocabulary(params.vocab_size or 11313)
+    feeder = feeder or SyntheticFeeder(params, vocab.vocab_size, batches=8)
+    val_feeder = val_feeder or feeder
+    test_feeder = test_feeder or feeder
+    eng = Engine(params, vocab_size=vocab.vocab_size, max_batch=params.batch_size, max_len=max_len, device=device,
+                 with_cnn=bool(params.fine_tune))
+    ckpt = checkpoint.checkpoint_path(params)
+    if params.mode == "training":
+        if not params.restore:
+            eng.load_state(synthetic.init_weights(eng.variables(), seed=1))  # tf.global_variables_initializer
+            if params.fine_tune and os.path.exists(params.image_net_weights_path):
+                out("Loading imagenet weights for futher usage")
+                eng.load_state(checkpoint.vgg16_npz_state(params.image_net_weights_path))
+        else:
+            out("Restoring from checkpoint")
+            checkpoint.restore(eng, ckpt)
+        if params.prior == "AG" and not params.no_encoder:
+            eng.set_cluster_means(synthetic.init_clusters(params.num_clusters, params.latent_size))
+        gs = 0
+        lb = rl = float("nan")
+        for e in range(params.num_epochs):
+            gs_epoch = 0
+            stop = False
+            while not stop:
+                n_batches = 0
+                for f_images_batch, captions_batch, cl_batch, c_v in feeder.next_batch(
+                        use_obj_vectors=params.use_c_v, num_captions=params.num_captions):
+                    n_batches += 1
+                    res = eng.train_step(anneal=gs, rng={"seed": gs}, **_feed(params, f_images_batch, captions_batch, cl_batch, c_v))
+                    kl, rl, lb, ann = res["kld"], res["rec_loss"], res["lower_bound"], res["annealing"]
+                    gs += 1
+                    gs_epoch += 1
+                    if gs % report_every == 0:
+                        out("Epoch: {} Iteration: {} VLB: {} Rec Loss: {}".format(e, gs, lb, rl))
+                        if not params.no_encoder:
+                            out("Annealing coefficient:{} KLD: {}".format(ann, kl))
+                    if gs_epoch * params.batch_size > params.num_ex_per_epoch:
+                        stop = True
+                        break
+                if n_batches == 0 or not getattr(feeder, "endless", False):
+                    stop = True
+            out("Epoch: {} Iteration: {} VLB: {} Rec Loss: {}".format(e, gs, lb, rl))
+            val_rec = []  # validate(): rec_loss of the training graph on the validation batches (main.py:262-284)
+            for f_images_batch, captions_batch, cl_batch, c_v in val_feeder.next_batch(
+                    use_obj_vectors=params.use_c_v, num_captions=params.num_captions):
+                val_rec.append(eng.eval_step(rng={"seed": gs}, **_feed(params, f_images_batch, captions_batch, cl_batch, c_v))["rec_loss"])
+            out("Validation reconstruction loss: {}".format(np.mean(val_rec) if val_rec else float("nan")))
+            out("-----------------------------------------------")
+            save_path = checkpoint.save(ckpt, eng.state())
+            out("Model saved in file: %s" % save_path)
+    if params.mode == "inference":
+        checkpoint.restore(eng, ckpt)
+        decoder = Decoder(eng, params, vocab)
+        inference_mod.inference(params, decoder, val_feeder, test_feeder)
+    return eng
+
+
+def main(argv=None):
+    params = Parameters()
+    params.parse_args(argv)
+    if params.save_params:  # main.py:295-304
+        import pickle
+        if not os.path.exists("./pickles"):
+            os.makedirs("./pickles")
+        fn = "./pickles/params_{}_{}_{}_{}.pickle".format(params.prior, params.no_encoder, params.checkpoint, params.use_c_v)
+        with open(fn, "wb") as wf:
+            pickle.dump(params, wf)
+    run(params)
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

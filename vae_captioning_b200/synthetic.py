@@ -67,3 +67,23 @@ def make_batch(B, C, T, V, seed=0, feature_size=4096, images=False, cluster_vect
             cv[b, rng.choice(used, size=k, replace=False)] = 1.0 / k
         feed["c_i"] = np.repeat(cv[:, None, :], C, axis=1).reshape(N, 91)[:, 1:].copy()  # main.py:236 drops column 0
     return feed
+
+
+def init_clusters(num_clusters, latent_size, seed=2, c_m_file=None):
+    """Cluster means of the AG prior (utils/vae_utils.py:6-31): num_clusters random vectors in [-1, 1]^Z scaled to unit
+    norm, persisted in (and re-read from) `c_m_file` (the reference's ./pickles/cluster_means.pickle) when given."""
+    import os
+    import pickle
+    if c_m_file and os.path.exists(c_m_file):
+        with open(c_m_file, "rb") as rf:
+            return np.squeeze(np.asarray(pickle.load(rf), dtype=np.float32))
+    rng = np.random.Generator(np.random.PCG64(seed))
+    m = 2 * rng.random((num_clusters, latent_size)) - 1
+    m = (m / np.sqrt(np.sum(m ** 2, axis=1, keepdims=True))).astype(np.float32)
+    if c_m_file:
+        d = os.path.dirname(c_m_file)
+        if d and not os.path.exists(d):
+            os.makedirs(d)
+        with open(c_m_file, "wb") as wf:
+            pickle.dump(m[:, None, :], wf)  # the reference stacks [1, Z] rows: shape [K, 1, Z]
+    return m
