@@ -18,6 +18,7 @@
 #ifndef VAECAP_H_
 #define VAECAP_H_
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -195,6 +196,10 @@ int vc_decode_state_set(vc_handle* h, const float* c_host, const float* h_host, 
 int vc_beam_search_host(int (*step)(void* user, int token, int state_in, float* probs_out), void* user, int V, int beam,
                         int max_len, int bos, int eos, float len_norm, int32_t* out_tokens, int32_t* out_len,
                         float* out_score, int32_t* out_n);
+
+/* Host-only (no GPU): CRC-32C continuing from `crc` (0 to start). The checkpoint writer/reader of the Python host side
+ * (tf.train.Saver's V2 tensor-bundle files, main.py:186-191, 211, 288) checksums every tensor and index block with it. */
+uint32_t vc_crc32c(uint32_t crc, const void* data, size_t n);
 
 #ifdef __cplusplus
 }

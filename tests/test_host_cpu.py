@@ -11,24 +11,30 @@ from vae_captioning_b200.main import SyntheticFeeder, _feed
 from vae_captioning_b200.parameters import Parameters
 
 
-def test_checkpoint_roundtrip_keeps_tf_names(tmp_path):
+@pytest.mark.parametrize("suffix", ["", ".npz"])
+def test_checkpoint_roundtrip_keeps_tf_names(tmp_path, suffix):
     state = {"imf_emb/kernel": np.arange(12, dtype=np.float32).reshape(3, 4),
              "decoder/net/multi_rnn_cell/cell_0/lstm_cell/bias": np.ones(8, np.float32),
              "cnn/conv5_1/weights_conv": np.zeros((3, 3, 2, 2), np.float32)}
     p = Parameters()
     p.checkpoint = "unit"
     path = checkpoint.checkpoint_path(p, str(tmp_path / "checkpoints"))
-    assert path.endswith("checkpoints/unit.ckpt.npz")
-    checkpoint.save(path, state)
+    assert path.endswith("checkpoints/unit.ckpt")  # main.py:211, 288
+    assert checkpoint.checkpoint_path(p) == "./checkpoints/unit.ckpt"
+    path += suffix
+    assert checkpoint.save(path, state) == path
+    if not suffix:  # Saver.save leaves the V2 bundle pair and the `checkpoint` state file
+        assert sorted(os.listdir(str(tmp_path / "checkpoints"))) == ["checkpoint", "unit.ckpt.data-00000-of-00001", "unit.ckpt.index"]
     back = checkpoint.load(path)
     assert sorted(back) == sorted(state)
     for k in state:
         np.testing.assert_array_equal(back[k], state[k])
     with pytest.raises(FileNotFoundError):
-        checkpoint.load(str(tmp_path / "missing.npz"))
+        checkpoint.load(str(tmp_path / ("missing" + suffix)))
 
 
-def test_restore_checks_names_and_shapes(tmp_path):
+@pytest.mark.parametrize("suffix", [".ckpt", ".npz"])
+def test_restore_checks_names_and_shapes(tmp_path, suffix):
     class FakeEngine(object):
         def __init__(self):
             self.got = {}
@@ -39,7 +45,7 @@ def test_restore_checks_names_and_shapes(tmp_path):
         def set_variable(self, n, v):
             self.got[n] = v
 
-    path = str(tmp_path / "c.npz")
+    path = str(tmp_path / ("c" + suffix))
     checkpoint.save(path, {"a/kernel": np.zeros((2, 3)), "a/bias": np.zeros(3)})
     e = FakeEngine()
     checkpoint.restore(e, path)

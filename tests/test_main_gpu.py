@@ -33,8 +33,8 @@ def test_train_checkpoint_inference_roundtrip(tmp_path, monkeypatch, kw):
     eng = M.run(p, feeder=feeder, out=lines.append, max_len=8, report_every=2)
     assert any(l.startswith("Epoch: 0 Iteration: 2 VLB:") for l in lines)
     assert any(l.startswith("Validation reconstruction loss:") for l in lines)
-    assert lines[-1] == "Model saved in file: ./checkpoints/unit.ckpt.npz"
-    saved = checkpoint.load("./checkpoints/unit.ckpt.npz")
+    assert lines[-1] == "Model saved in file: ./checkpoints/unit.ckpt"
+    saved = checkpoint.load("./checkpoints/unit.ckpt")
     assert sorted(saved) == sorted(n for n, _, _ in eng.variables())
     w0 = eng.get_variable("decoder/rnn_logits/kernel")
     np.testing.assert_array_equal(saved["decoder/rnn_logits/kernel"], w0)

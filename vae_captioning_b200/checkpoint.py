@@ -2,13 +2,17 @@
 `vgg16_weights.npz` loader, utils/image_embeddings.py:240-246).
 
 Variables are exchanged by their TensorFlow names and layouts, so a state dict produced here maps one to
-one onto the reference's checkpoint. The on-disk container is `.npz` (one array per variable name); reading and writing
-TF's V2 tensor-bundle files is a "next" row of the scope table. Optimiser state is not saved -- the
-reference's Saver holds only the trainable variables (+ the cnn/ variables when they are frozen).
+one onto the reference's checkpoint. The on-disk container is TensorFlow's V2 tensor bundle
+(`{name}.ckpt.index` + `{name}.ckpt.data-00000-of-00001`, written and read by `tf_bundle` without TensorFlow, SURVEY
+8f-2) plus the `checkpoint` state file Saver keeps beside it; a path ending in `.npz` selects a plain numpy archive
+instead (one array per variable name). Optimiser state is not saved -- the reference's Saver holds only the trainable
+variables (+ the cnn/ variables when they are frozen).
 """
 import os
 
 import numpy as np
+
+from . import tf_bundle
 
 # creation order of vgg16.parameters (utils/image_embeddings.py:36-238): conv kernels/biases, then fc1, fc2
 VGG_VARIABLES = []
@@ -20,29 +24,41 @@ VGG_VARIABLES += ["cnn/fc1/weights", "cnn/fc1/biases", "cnn/fc2/weights", "cnn/f
 
 
 def checkpoint_path(params, directory="./checkpoints"):
-    """'./checkpoints/{checkpoint}.ckpt' of the reference (main.py:211, 288) with the .npz container suffix."""
-    return os.path.join(directory, "{}.ckpt.npz".format(params.checkpoint))
+    """'./checkpoints/{checkpoint}.ckpt' of the reference (main.py:211, 288): the prefix of the bundle files."""
+    return "{}/{}.ckpt".format(directory.rstrip("/"), params.checkpoint)
 
 
 def save(path, state):
-    """state: {tf_variable_name: array}. Names contain '/', which np.savez keeps verbatim as archive member names."""
+    """saver.save(sess, path): state is {tf_variable_name: array}. Returns `path` like Saver.save does."""
     d = os.path.dirname(path)
     if d and not os.path.exists(d):
         os.makedirs(d)
-    np.savez(path, **{k: np.asarray(v, dtype=np.float32) for k, v in state.items()})
+    state = {k: np.asarray(v, dtype=np.float32) for k, v in state.items()}
+    if path.endswith(".npz"):
+        np.savez(path, **state)  # names contain '/', which np.savez keeps verbatim as archive member names
+        return path
+    tf_bundle.write_bundle(path, state)
+    tf_bundle.update_checkpoint_state(d or ".", path)
     return path
 
 
-def load(path):
-    if not os.path.exists(path):
-        raise FileNotFoundError(path)
-    with np.load(path) as z:
-        return {k: z[k] for k in z.files}
+def load(path, names=None):
+    """{tf_variable_name: array} of a bundle prefix (or .npz archive); `names` restricts what is read from a bundle."""
+    if path.endswith(".npz"):
+        if not os.path.exists(path):
+            raise FileNotFoundError(path)
+        with np.load(path) as z:
+            return {k: z[k] for k in z.files if names is None or k in names}
+    return tf_bundle.read_bundle(path, names)
 
 
 def restore(engine, path, strict=True):
     """saver.restore: every variable of the engine must be present with its shape (TF raises otherwise)."""
-    state = load(path)
+    if path.endswith(".npz"):
+        state = load(path)
+    else:  # a reference-written bundle also carries cnn/ variables the engine may not hold: read only what it needs
+        _, entries = tf_bundle.list_bundle(path)
+        state = load(path, [n for n, _, _ in engine.variables() if n in entries])
     for name, shape, _ in engine.variables():
         if name not in state:
             if strict:

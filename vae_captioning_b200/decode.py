@@ -38,7 +38,8 @@ class Decoder(object):
         if feats.ndim != 2 or feats.shape[1] != self.engine.cfg.cnn_feature_size:
             raise ValueError("in_pictures must be [B, %d] features, got %s" % (self.engine.cfg.cnn_feature_size, feats.shape))
         cv = None
-        if c_v is not None and len(c_v) != 0:
+        feeds_c_i = self.params.use_c_v or self.params.prior in ("GMM", "AG")  # decoder.c_i is set only then (main.py:103-110)
+        if feeds_c_i and c_v is not None and len(c_v) != 0:
             cv = _f32(c_v)
             if cv.shape != (feats.shape[0], self.engine.cfg.num_clusters):
                 raise ValueError("c_v must be [%d, %d], got %s" % (feats.shape[0], self.engine.cfg.num_clusters, cv.shape))
