@@ -129,7 +129,18 @@ int vc_train_step_images(vc_handle* h, const float* images_host, const int32_t* 
 int vc_train_step_images_u8(vc_handle* h, const uint8_t* images_host, const int32_t* cap_lbl_host, const int32_t* cap_in_host,
                             const int32_t* len_host, const float* c_v_host, int B, int T, int64_t global_step,
                             const vc_rng* rng, vc_step_out* out, void* stream);
-/* Same, with inputs already resident in device memory. */
+/* Double-buffered feed for the same step (the reference feeds one numpy batch per sess.run, main.py:229-244; here the
+ * H2D copy of batch i+1 overlaps the compute of batch i). vc_stage_batch copies one step's HOST buffers into staging
+ * slot 0 or 1 on `copy_stream` (asynchronous when the host memory is pinned) and records an event;
+ * vc_train_step_staged runs the train step on `stream` from that slot, waiting for the copy on the device. A slot may
+ * be refilled as soon as the step that consumes it has been enqueued (the copy waits for that step's last read).
+ * kind: 0 = the vc_train_step feed (fc2 features fp32 [B, F]; fp32 images when fine_tune), 1 = fp32 images
+ * [B,224,224,3], 2 = uint8 images (both: on-device VGG16 forward, or the fine-tune feed). Errors as vc_train_step. */
+int vc_stage_batch(vc_handle* h, int slot, const void* feats_or_images_host, int kind, const int32_t* cap_lbl_host,
+                   const int32_t* cap_in_host, const int32_t* len_host, const float* c_v_host, int B, int T, void* copy_stream);
+int vc_train_step_staged(vc_handle* h, int slot, int64_t global_step, const vc_rng* rng, vc_step_out* out, void* stream);
+
+/* vc_train_step with inputs already resident in device memory. */
 int vc_train_step_dev(vc_handle* h, const float* feats_dev, const int32_t* cap_lbl_dev, const int32_t* cap_in_dev,
                       const int32_t* len_dev, const float* c_v_dev, int B, int T, int64_t global_step,
                       const vc_rng* rng, vc_step_out* out, void* stream);

@@ -255,7 +255,161 @@ def inference_json_fixture():
     dump("inference_json.json", out)
 
 
+def _jsonable(x):
+    if isinstance(x, np.ndarray):
+        return {"shape": list(x.shape), "dtype": str(x.dtype), "data": x.tolist()}
+    if isinstance(x, (tuple, list)):
+        return [_jsonable(v) for v in x]
+    if isinstance(x, (np.integer,)):
+        return int(x)
+    if isinstance(x, (np.floating,)):
+        return float(x)
+    return x
+
+
+def batch_gen_fixture():
+    """utils/captions.py Captions + Dictionary and utils/batch_gen.py Batch_Generator, unmodified, over the miniature
+    COCO tree of tests/golden/fake_coco.py. tensorflow / h5py are imported by batch_gen.py at module level but only
+    h5py.File is used (for the uint8 image store), so stubs are enough; `glob` is wrapped to return sorted lists so
+    the file order does not depend on the file system."""
+    import glob as glob_mod
+    import importlib
+    import random
+    sys.path.insert(0, HERE)
+    import fake_coco
+    h5 = types.ModuleType("h5py")
+
+    class _H5File(dict):
+        def __init__(self, path, mode="r"):
+            dict.__init__(self, images=np.load(path))
+    h5.File = _H5File
+    tf = mock.MagicMock()
+    out = {}
+    cwd = os.getcwd()
+    with tempfile.TemporaryDirectory() as td, mock.patch.dict(sys.modules, {"tensorflow": tf, "h5py": h5}):
+        names = fake_coco.build(td)
+        os.chdir(td)
+        try:
+            for m in ("utils.batch_gen", "utils.captions"):
+                sys.modules.pop(m, None)
+            bg = importlib.import_module("utils.batch_gen")
+            cp = importlib.import_module("utils.captions")
+            bg.glob = lambda pat: sorted(glob_mod.glob(pat))
+            coco = os.path.join(td, "coco") + "/"
+            sink = io.StringIO()
+            with contextlib.redirect_stdout(sink):
+                cap_tr = cp.Captions(coco + "annotations/captions_train2014.json", 100)
+                cap_val = cp.Captions(coco + "annotations/captions_val2014.json", 100)
+                raw_tr = {k: [list(c) for c in v] for k, v in cap_tr.captions.items()}
+                d = cp.Dictionary(cap_tr.captions, 2)
+                cap_tr.index_captions(d.word2idx)
+                cap_val.index_captions(d.word2idx)
+            out["captions"] = {"raw_train": raw_tr, "word2idx": d.word2idx, "indexed_train": dict(cap_tr.captions_indexed),
+                               "indexed_val": dict(cap_val.captions_indexed), "fn_to_id": cap_tr.filename_to_imid,
+                               "num_captions": cap_tr.num_captions}
+            fd_tr = fake_coco.feature_dict(names["train"], 5)
+            fd_val = fake_coco.feature_dict(names["val"], 6)
+            fd_test = fake_coco.feature_dict(names["test"], 7)
+            fake_coco.image_store(td, names["train"] + names["val"])
+            tr_dir, val_dir, test_dir = (coco + "images/%s2014/" % s for s in ("train", "val", "test"))
+            runs = []
+
+            def record(tag, gen_factory, method, kwargs, seed):
+                random.seed(seed)
+                with contextlib.redirect_stdout(sink):
+                    g = gen_factory()
+                    batches = [_jsonable(b) for b in getattr(g, method)(**kwargs)]
+                runs.append({"tag": tag, "method": method, "kwargs": kwargs, "seed": seed, "batches": batches,
+                             "unused_cap_in": [n.split("/")[-1] for n in (g.unused_cap_in or [])]})
+
+            feats = lambda bs: bg.Batch_Generator(tr_dir, coco + "annotations/captions_train2014.json", cap_tr, bs,
+                                                  feature_dict=fd_tr)
+            record("train_feats_bs3_c1", lambda: feats(3), "next_batch", {"use_obj_vectors": False, "num_captions": 1}, 1)
+            record("train_feats_bs3_c5_cv", lambda: feats(3), "next_batch", {"use_obj_vectors": True, "num_captions": 5}, 2)
+            record("train_feats_bs4_c2", lambda: feats(4), "next_batch", {"use_obj_vectors": False, "num_captions": 2}, 3)
+            record("train_feats_all", lambda: feats(None), "next_batch", {"use_obj_vectors": True, "num_captions": 1}, 4)
+
+            def store_gen():
+                return bg.Batch_Generator(tr_dir, coco + "annotations/captions_train2014.json", cap_tr, 3, use_hdf5=True,
+                                          hdf5_file=os.path.join(td, "store.npy"), feature_dict=None)
+            record("train_store_bs3_c5", store_gen, "next_batch", {"use_obj_vectors": True, "num_captions": 5}, 5)
+
+            def repart():
+                g = feats(4)
+                g.repartiton(cap_val, fd_val, 2)
+                return g
+            record("train_repartition_bs4_c3", repart, "next_batch", {"use_obj_vectors": True, "num_captions": 3}, 6)
+
+            def val_gen():
+                return bg.Batch_Generator(val_dir, coco + "annotations/captions_val2014.json", cap_val, 2,
+                                          feature_dict=fd_val, get_image_ids=True)
+            record("val_ids_cv", val_gen, "next_val_batch", {"get_image_ids": True, "use_obj_vectors": True}, 7)
+            record("val_noids", val_gen, "next_val_batch", {"get_image_ids": False, "use_obj_vectors": False}, 8)
+            unused = [val_dir + n for n in names["val"][-2:]]
+            record("val_unused_only", lambda: bg.Batch_Generator(val_dir, coco + "annotations/captions_val2014.json", cap_val,
+                                                                 None, feature_dict=fd_val, get_image_ids=True,
+                                                                 val_tr_unused=list(unused)),
+                   "next_val_batch", {"get_image_ids": True, "use_obj_vectors": False}, 9)
+
+            def test_gen():
+                return bg.Batch_Generator(test_dir, train_cap_json=coco + "annotations/image_info_test2014.json", batch_size=2,
+                                          feature_dict=fd_test, get_image_ids=True, get_test_ids=True)
+            record("test_cv", test_gen, "next_test_batch", {"use_obj_vectors": True}, 10)
+            record("test_nocv", test_gen, "next_test_batch", {"use_obj_vectors": False}, 11)
+            out["runs"] = runs
+            errs = {}
+            for tag, fn in (("empty_dir", lambda: bg.Batch_Generator(os.path.join(td, "nowhere") + "/", batch_size=2)),
+                            ("hdf5_no_file", lambda: bg.Batch_Generator(tr_dir, use_hdf5=True)),
+                            ("repartition_no_caps", lambda: feats(2).repartiton(None, fd_val, 2)),
+                            ("repartition_no_feats", lambda: feats(2).repartiton(cap_val, None, 2))):
+                try:
+                    with contextlib.redirect_stdout(sink):
+                        fn()
+                    errs[tag] = None
+                except Exception as e:
+                    errs[tag] = type(e).__name__
+            out["errors"] = errs
+            # utils/data.py Data over the same tree, features served from ./pickles/{split}2014.pickle (so the TF graph in
+            # extract_features_from_dir is never built); repartition on, like main.py:22-36.
+            import pickle
+            for split, fd in (("train", fd_tr), ("val", fd_val), ("test", fd_test)):
+                with open("./pickles/%s2014.pickle" % split, "wb") as wf:
+                    pickle.dump(fd, wf)
+            for m in ("utils.data", "utils.image_embeddings", "utils.parameters"):
+                sys.modules.pop(m, None)
+            dm = importlib.import_module("utils.data")
+            dm.Batch_Generator = bg.Batch_Generator
+            from utils.parameters import Parameters
+            p = Parameters()
+            p.coco_dir, p.use_hdf5, p.keep_words, p.cap_max_length = coco, False, 2, 100
+            droot = {}
+            random.seed(12)
+            with contextlib.redirect_stdout(sink):
+                data = dm.Data(p, True, "weights.npz", repartiton=True, gen_val_cap=2)
+                tr = data.load_train_data_generator(3)
+                droot["num_examples"] = data.num_examples
+                droot["vocab_size"] = data.dictionary.vocab_size
+                droot["unused_cap_in"] = [n.split("/")[-1] for n in tr.unused_cap_in]
+                droot["train"] = [_jsonable(b) for b in tr.next_batch(use_obj_vectors=True, num_captions=2)]
+                va = data.get_valid_data(2, val_tr_unused=tr.unused_cap_in)
+                droot["val"] = [_jsonable(b) for b in va.next_val_batch(get_image_ids=True, use_obj_vectors=True)]
+                te = data.get_test_data(2)
+                droot["test"] = [_jsonable(b) for b in te.next_test_batch(use_obj_vectors=True)]
+            err = None
+            try:
+                with contextlib.redirect_stdout(sink):
+                    dm.Data(p, False, None, repartiton=True, gen_val_cap=None)
+            except Exception as e:
+                err = type(e).__name__
+            droot["repartition_without_count"] = err
+            out["data"] = droot
+        finally:
+            os.chdir(cwd)
+    dump("batch_gen.json", out)
+
+
 if __name__ == "__main__":
+    batch_gen_fixture()
     topn_fixture()
     caption_utils_fixture()
     parameters_fixture()

@@ -49,3 +49,39 @@ class Dictionary(object):
 
     def __len__(self):
         return len(self._idx2word)
+
+
+class Captions(object):
+    """COCO caption annotations of one split (reference: utils/captions.py:5-63).
+
+    `captions` maps file name -> list of token lists (`<BOS>` w.. `<EOS>`), in annotation order; `captions_indexed` is
+    the same mapping after `index_captions` replaced the words by vocabulary ids (out-of-vocabulary -> `<UNK>`).
+    The reference's length clip (`captions.py:34-36`) tests `len()` of the annotation *dict* (its key count), so it
+    never triggers for COCO's three-key annotations and would raise on a longer one; captions are therefore never
+    clipped here either and `max_length` is only recorded."""
+
+    def __init__(self, captions_file, max_length=16, verbose=True):
+        import json
+        self._cap_json = captions_file
+        self.max_length = max_length
+        self.captions = collections.defaultdict(list)
+        with open(captions_file) as rf:
+            j = json.loads(rf.read())
+        name_of = {img["id"]: img["file_name"] for img in j["images"]}
+        self._fn_to_id = {img["file_name"]: img["id"] for img in j["images"]}
+        for ann in j["annotations"]:
+            self.captions[name_of[ann["image_id"]]].append(tokenize_caption(ann["caption"]))
+        self.captions_indexed = self.captions.copy()  # shallow: index_captions rewrites the shared lists in place
+        self.num_captions = len(self.captions)
+        if verbose:
+            print("Number of images in set", self.num_captions)
+
+    def index_captions(self, word2idx):
+        unk = word2idx["<UNK>"]
+        for caps in self.captions_indexed.values():
+            for i, cap in enumerate(caps):
+                caps[i] = [word2idx.get(w, unk) for w in cap]
+
+    @property
+    def filename_to_imid(self):
+        return self._fn_to_id

@@ -201,6 +201,25 @@ int vc_train_step_images_u8(vc_handle* h, const uint8_t* images, const int32_t* 
   return train_step_images_impl(h, images, true, lbl, inp, len, cv, B, T, gs, rng, out, stream);
 }
 
+int vc_stage_batch(vc_handle* h, int slot, const void* px, int kind, const int32_t* lbl, const int32_t* inp, const int32_t* len,
+                   const float* cv, int B, int T, void* copy_stream) {
+  VC_GUARD_BEGIN
+  if (!h || !px || !lbl || !inp || !len) return set_error(VC_E_ARG, "vc_stage_batch: null argument");
+  cudaSetDevice(h->m.device);
+  return h->m.stage_slot(slot, px, kind, lbl, inp, len, cv, B, T, (cudaStream_t)copy_stream);
+  VC_GUARD_END
+}
+
+int vc_train_step_staged(vc_handle* h, int slot, int64_t gs, const vc_rng* rng, vc_step_out* out, void* stream) {
+  VC_GUARD_BEGIN
+  if (!h) return set_error(VC_E_ARG, "null handle");
+  cudaSetDevice(h->m.device);
+  cudaStream_t s = (cudaStream_t)stream;
+  VC_TRY(h->m.step_from_slot(slot, gs, rng, s));
+  return h->m.fetch(out, s);
+  VC_GUARD_END
+}
+
 int vc_eval_step(vc_handle* h, const float* feats, const int32_t* lbl, const int32_t* inp, const int32_t* len,
                  const float* cv, int B, int T, const vc_rng* rng, vc_step_out* out, void* stream) {
   VC_GUARD_BEGIN

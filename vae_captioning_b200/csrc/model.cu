@@ -11,6 +11,10 @@ static inline int64_t round_up(int64_t x, int64_t a) { return (x + a - 1) / a * 
 Model::~Model() {
   decode_release();
   for (void* p : allocs) cudaFree(p);
+  for (StageSlot& q : slots) {
+    if (q.ready) cudaEventDestroy(q.ready);
+    if (q.consumed) cudaEventDestroy(q.consumed);
+  }
   if (host_scal) cudaFreeHost(host_scal);
 }
 
@@ -342,6 +346,75 @@ int Model::stage_inputs(const float* feats, const int32_t* lbl, const int32_t* i
   out->B = B;
   out->T = T;
   return VC_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// Double-buffered feed. kind: 0 = what vc_train_step takes (fc2 features, or fp32 images when fine_tune),
+// 1 = fp32 images for the on-device VGG16 forward, 2 = uint8 images (fine-tune feed or on-device forward).
+int Model::stage_slot(int slot, const void* px_host, int kind, const int32_t* lbl, const int32_t* inp, const int32_t* len,
+                      const float* cv, int B, int T, cudaStream_t cs) {
+  if (slot < 0 || slot > 1) return set_error(VC_E_ARG, "staging slot must be 0 or 1, got %d", slot);
+  if (kind < 0 || kind > 2) return set_error(VC_E_ARG, "unknown feed kind %d", kind);
+  if (B < 1 || B > cfg.max_batch || T < 1 || T > maxT)
+    return set_error(VC_E_SHAPE, "batch %d x len %d exceeds the handle's max_batch %d / max_len %d", B, T, cfg.max_batch, maxT);
+  const bool images = kind != 0 || cfg.fine_tune;
+  if (kind != 0 && !cfg.fine_tune && vgg.empty())
+    return set_error(VC_E_STATE, "this handle was created without the CNN (with_cnn = 0)");
+  StageSlot& q = slots[slot];
+  const int N = B * cfg.num_captions;
+  if (q.lbl == nullptr) {
+    const size_t px_elems = (cfg.fine_tune || !vgg.empty()) ? (size_t)224 * 224 * 3 : (size_t)cfg.cnn_feature_size;
+    VC_TRY(dalloc((float**)&q.px, (size_t)cfg.max_batch * std::max(px_elems, (size_t)cfg.cnn_feature_size), false));
+    VC_TRY(dalloc(&q.cv, (size_t)maxN * cfg.num_clusters, false));
+    VC_TRY(dalloc(&q.lbl, (size_t)maxN * maxT, false));
+    VC_TRY(dalloc(&q.in, (size_t)maxN * maxT, false));
+    VC_TRY(dalloc(&q.len, (size_t)maxN, false));
+    VC_CUDA(cudaEventCreateWithFlags(&q.ready, cudaEventDisableTiming));
+    VC_CUDA(cudaEventCreateWithFlags(&q.consumed, cudaEventDisableTiming));
+  }
+  if (q.in_use) VC_CUDA(cudaStreamWaitEvent(cs, q.consumed, 0));  // the step that last read this slot must be past it
+  const size_t per = images ? (size_t)224 * 224 * 3 * (kind == 2 ? 1 : sizeof(float)) : (size_t)cfg.cnn_feature_size * sizeof(float);
+  VC_CUDA(cudaMemcpyAsync(q.px, px_host, (size_t)B * per, cudaMemcpyHostToDevice, cs));
+  VC_CUDA(cudaMemcpyAsync(q.lbl, lbl, (size_t)N * T * sizeof(int32_t), cudaMemcpyHostToDevice, cs));
+  VC_CUDA(cudaMemcpyAsync(q.in, inp, (size_t)N * T * sizeof(int32_t), cudaMemcpyHostToDevice, cs));
+  VC_CUDA(cudaMemcpyAsync(q.len, len, (size_t)N * sizeof(int32_t), cudaMemcpyHostToDevice, cs));
+  q.has_cv = cv != nullptr;
+  if (cv) VC_CUDA(cudaMemcpyAsync(q.cv, cv, (size_t)N * cfg.num_clusters * sizeof(float), cudaMemcpyHostToDevice, cs));
+  VC_CUDA(cudaEventRecord(q.ready, cs));
+  q.B = B;
+  q.T = T;
+  q.kind = kind;
+  q.filled = true;
+  return VC_OK;
+}
+
+int Model::step_from_slot(int slot, int64_t gs, const vc_rng* rng, cudaStream_t s) {
+  if (slot < 0 || slot > 1 || !slots[slot].filled)
+    return set_error(VC_E_STATE, "vc_train_step_staged: slot %d holds no batch (call vc_stage_batch first)", slot);
+  StageSlot& q = slots[slot];
+  VC_CUDA(cudaStreamWaitEvent(s, q.ready, 0));
+  StepInputs in{};
+  in.B = q.B;
+  in.T = q.T;
+  in.cap_lbl = q.lbl;
+  in.cap_in = q.in;
+  in.len = q.len;
+  in.c_v = q.has_cv ? q.cv : nullptr;
+  in.global_step = gs;
+  if (rng) in.rng = *rng;
+  if (q.kind != 0 && !cfg.fine_tune) {  // frozen extractor: images -> fc2 on the device, then the caption model
+    VC_TRY(vgg_forward(reinterpret_cast<const float*>(q.px), nullptr, q.B, false, nullptr, s, q.kind == 2));
+    in.feats = fc2_f;
+  } else {
+    in.feats = reinterpret_cast<const float*>(q.px);
+    in.feats_u8 = q.kind == 2;
+  }
+  VC_TRY(forward(in, true, s));
+  VC_TRY(backward(in, s));
+  VC_CUDA(cudaEventRecord(q.consumed, s));
+  q.in_use = true;
+  q.filled = false;
+  return apply(1.f, s);
 }
 
 // ------------------------------------------------------------------------------------------

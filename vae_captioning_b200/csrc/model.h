@@ -104,6 +104,20 @@ class Model {
   float *st_feats = nullptr, *st_cv = nullptr;
   int32_t *st_lbl = nullptr, *st_in = nullptr, *st_len = nullptr;
   float* host_scal = nullptr;  // pinned
+  // Double-buffered feed (vc_stage_batch / vc_train_step_staged): the next step's host buffers are copied into one slot
+  // on a copy stream while the current step computes from the other. Slots are allocated on first use.
+  struct StageSlot {
+    void* px = nullptr;  // features fp32 [B, F], or images (fp32 / uint8) [B, 224, 224, 3]
+    float* cv = nullptr;
+    int32_t *lbl = nullptr, *in = nullptr, *len = nullptr;
+    cudaEvent_t ready = nullptr, consumed = nullptr;
+    int B = 0, T = 0, kind = -1;
+    bool has_cv = false, filled = false, in_use = false;
+  };
+  StageSlot slots[2];
+  int stage_slot(int slot, const void* px_host, int kind, const int32_t* lbl, const int32_t* inp, const int32_t* len,
+                 const float* cv, int B, int T, cudaStream_t copy_stream);
+  int step_from_slot(int slot, int64_t gs, const vc_rng* rng, cudaStream_t s);
   int* seq_flags = nullptr;    // inter-CTA step counters of the persistent LSTM kernels
 
   // --- VGG16 (vgg.cu)

@@ -116,6 +116,8 @@ class Engine(object):
         lib.vc_train_step_images.argtypes = step_args + [ctypes.POINTER(VcStepOut), vp]
         lib.vc_train_step_images_u8.argtypes = step_args + [ctypes.POINTER(VcStepOut), vp]
         lib.vc_vgg_forward_u8.argtypes = [vp, vp, vp, ci, vp]
+        lib.vc_stage_batch.argtypes = [vp, ci, vp, ci, vp, vp, vp, vp, ci, ci, vp]
+        lib.vc_train_step_staged.argtypes = [vp, ci, cll, ctypes.POINTER(VcRng), ctypes.POINTER(VcStepOut), vp]
         lib.vc_forward_backward_dev.argtypes = step_args + [vp]
         lib.vc_eval_step.argtypes = [vp, vp, vp, vp, vp, vp, ci, ci, ctypes.POINTER(VcRng), ctypes.POINTER(VcStepOut), vp]
         lib.vc_set_cluster_means.argtypes = [vp, vp]
@@ -236,6 +238,42 @@ class Engine(object):
         L.check(fn(self._h, _np_ptr(feats), _np_ptr(lbl), _np_ptr(inp), _np_ptr(ln), _np_ptr(cv), B, T,
                                        int(anneal), ctypes.byref(r), ctypes.byref(out) if fetch else None, self._stream()))
         return out.as_dict() if fetch else None
+
+    # ------------------------------------------------------------------ double-buffered feed
+    def stage_batch(self, slot, image_f_inputs, ann_inputs_enc, ann_inputs_dec, ann_lengths, c_i=None, images=False):
+        """Starts the H2D copy of one step's feed into staging slot 0/1 on the engine's copy stream and returns at
+        once (asynchronous for pinned host arrays, see `pinned`). Run it with `train_step_staged(slot, ...)`; staging
+        batch i+1 before launching step i overlaps its copy with step i's compute."""
+        import torch
+        u8 = getattr(image_f_inputs, "dtype", None) == np.uint8 and (images or self.cfg.fine_tune)
+        feats = np.ascontiguousarray(image_f_inputs) if u8 else _f32(image_f_inputs)
+        lbl, inp = _i32(ann_inputs_enc), _i32(ann_inputs_dec)
+        ln = _i32(np.asarray(ann_lengths).ravel())
+        cv = _f32(c_i) if c_i is not None else None
+        B, T = feats.shape[0], lbl.shape[1]
+        self._check_feed(feats, lbl, inp, ln, cv, B, T, images)
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+            self._staged = {}
+        kind = 2 if u8 else (1 if images and not self.cfg.fine_tune else 0)
+        self._staged[slot] = (feats, lbl, inp, ln, cv)  # the host arrays must outlive the asynchronous copy
+        L.check(self.lib.vc_stage_batch(self._h, int(slot), _np_ptr(feats), kind, _np_ptr(lbl), _np_ptr(inp), _np_ptr(ln),
+                                        _np_ptr(cv), B, T, ctypes.c_void_p(self._copy_stream.cuda_stream)))
+
+    def train_step_staged(self, slot, anneal, rng=None, fetch=True):
+        """The train step (main.py:229-244) on the batch staged in `slot`. Same return value as train_step."""
+        r, keep = self._rng(rng)
+        out = VcStepOut()
+        self._keep = [keep]
+        L.check(self.lib.vc_train_step_staged(self._h, int(slot), int(anneal), ctypes.byref(r),
+                                              ctypes.byref(out) if fetch else None, self._stream()))
+        return out.as_dict() if fetch else None
+
+    @staticmethod
+    def pinned(array):
+        """A page-locked copy of a numpy array (torch as the allocator), for truly asynchronous stage_batch copies."""
+        import torch
+        return torch.from_numpy(np.ascontiguousarray(array)).pin_memory().numpy()
 
     def train_step_device(self, feats, cap_lbl, cap_in, lengths, anneal, c_i=None, rng=None, fetch=True):
         """Same step with inputs already resident on the device (torch CUDA tensors as containers)."""

@@ -2,9 +2,9 @@
 structure, prints and file outputs (`./checkpoints/{checkpoint}.ckpt*`, `./val_{gen_name}.json`, `./test_{gen_name}.json`),
 with the TF graph + session replaced by `Engine` / `Decoder`.
 
-The data side (COCO json / jpg / hdf5 readers, utils/data.py, utils/batch_gen.py) is outside the hot path (SURVEY 2,
-"OUT" rows); `feeder` is anything with the reference generators' interface. Without one, a seeded synthetic feeder
-with the reference's shapes and dtypes is used (there is no COCO on the box):
+The data side mirrors utils/data.py / utils/batch_gen.py (`data.Data`, `batch_gen.Batch_Generator`) and is
+used when `params.coco_dir` exists; `feeder` is anything with the reference generators' interface. Without a COCO
+tree, a seeded synthetic feeder with the reference's shapes and dtypes is used (there is no COCO on the bench box):
 
     python -m vae_captioning_b200.main --gpu 0 --bs 32 --epochs 1 [--prior AG --c_v] [--mode inference]
 """
@@ -69,9 +69,26 @@ def _feed(params, f_images_batch, captions_batch, cl_batch, c_v):
     return feed
 
 
+def load_data(params):
+    """main.py:19-39: Data -> (train, val, test) generators + the vocabulary. Features come from the ./pickles cache or
+    the device VGG16 (Data.extract_features_from_dir); with --fine_tune the generators yield uint8 images instead."""
+    from .data import Data
+    repartiton = not params.gen_val_captions < 0
+    data = Data(params, True, params.image_net_weights_path, repartiton=repartiton, gen_val_cap=params.gen_val_captions)
+    batch_gen = data.load_train_data_generator(params.batch_size, params.fine_tune)
+    pretrained = not params.fine_tune
+    val_gen = data.get_valid_data(params.batch_size, val_tr_unused=batch_gen.unused_cap_in, pretrained=pretrained)
+    test_gen = data.get_test_data(params.batch_size, pretrained=pretrained)
+    if data.engine is not None:  # the feature-extraction handle (VGG16 workspace) is not needed any more
+        data.engine.close()
+        data.engine = None
+    return batch_gen, val_gen, test_gen, data.dictionary
+
+
 def run(params, feeder=None, val_feeder=None, test_feeder=None, vocabulary=None, device=0, out=print, max_len=64,
-        report_every=500):
+        report_every=500, prefetch=2):
     """The body of main() (main.py:14-289). Returns the Engine (its variables are the checkpoint)."""
+    from .batch_gen import Prefetcher
     from .decode import Decoder
     from .engine import Engine
     from . import inference as inference_mod
@@ -100,10 +117,23 @@ def run(params, feeder=None, val_feeder=None, test_feeder=None, vocabulary=None,
             stop = False
             while not stop:
                 n_batches = 0
-                for f_images_batch, captions_batch, cl_batch, c_v in feeder.next_batch(
-                        use_obj_vectors=params.use_c_v, num_captions=params.num_captions):
+                batches = feeder.next_batch(use_obj_vectors=params.use_c_v, num_captions=params.num_captions)
+                if prefetch:  # batch i+1 is assembled on a host thread while the device runs batch i
+                    batches = Prefetcher(batches, depth=prefetch)
+                # double-buffered feed: batch i+1 is copied to the device (copy stream) while step i computes
+                it = iter(batches)
+                nxt = next(it, None)
+                slot = 0
+                if nxt is not None:
+                    eng.stage_batch(slot, **_feed(params, *nxt))
+                while nxt is not None:
                     n_batches += 1
-                    res = eng.train_step(anneal=gs, rng={"seed": gs}, **_feed(params, f_images_batch, captions_batch, cl_batch, c_v))
+                    cur_slot = slot
+                    nxt = next(it, None)
+                    if nxt is not None:
+                        slot ^= 1
+                        eng.stage_batch(slot, **_feed(params, *nxt))
+                    res = eng.train_step_staged(cur_slot, anneal=gs, rng={"seed": gs})
                     kl, rl, lb, ann = res["kld"], res["rec_loss"], res["lower_bound"], res["annealing"]
                     gs += 1
                     gs_epoch += 1
@@ -114,6 +144,8 @@ def run(params, feeder=None, val_feeder=None, test_feeder=None, vocabulary=None,
                     if gs_epoch * params.batch_size > params.num_ex_per_epoch:
                         stop = True
                         break
+                if hasattr(batches, "close"):
+                    batches.close()
                 if n_batches == 0 or not getattr(feeder, "endless", False):
                     stop = True
             out("Epoch: {} Iteration: {} VLB: {} Rec Loss: {}".format(e, gs, lb, rl))
@@ -142,7 +174,13 @@ def main(argv=None):
         fn = "./pickles/params_{}_{}_{}_{}.pickle".format(params.prior, params.no_encoder, params.checkpoint, params.use_c_v)
         with open(fn, "wb") as wf:
             pickle.dump(params, wf)
-    run(params)
+    if os.path.isdir(params.coco_dir):
+        batch_gen, val_gen, test_gen, dictionary = load_data(params)
+        batch_gen.endless = True  # the reference loops `while True` over next_batch until num_ex_per_epoch (main.py:216-246)
+        run(params, feeder=batch_gen, val_feeder=val_gen, test_feeder=test_gen, vocabulary=dictionary)
+    else:
+        print("No COCO tree at {}: running on the seeded synthetic feeder".format(params.coco_dir))
+        run(params)
     return 0
 
 
