@@ -19,7 +19,9 @@ pytestmark = pytest.mark.gpu
 # (B, hw, cin, cout): every VGG16 geometry class (224/112: 16x4 patches + halo dgrad at cout = 64, 56: 8x8, 28: 4x4x4
 # with an image-count tail, 14: 2x2x16 with a tail), Cin = 64 (two taps per A tile, odd tap count) and Cin >= 128
 CASES = [(1, 32, 64, 64), (2, 16, 64, 128), (2, 16, 128, 128), (3, 56, 128, 256), (3, 28, 256, 512), (5, 14, 512, 512),
-         (1, 224, 64, 64), (2, 112, 64, 128), (17, 14, 512, 512), (2, 8, 256, 256)]
+         (1, 224, 64, 64), (2, 112, 64, 128), (17, 14, 512, 512), (2, 8, 256, 256),
+         # streamed-filter halo kernel (contraction over 128 / 256 channels into 64 / 128): full-size dgrad2_2, ragged rows
+         (2, 112, 128, 128), (1, 24, 128, 256), (3, 40, 64, 256)]
 
 
 @pytest.mark.parametrize("B,hw,cin,cout", CASES)

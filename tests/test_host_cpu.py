@@ -83,8 +83,8 @@ def test_synthetic_feeder_and_feed_shapes():
     assert len(batches) == 2
     feats, (inp, lbl), lens, c_v = batches[0]
     assert feats.shape == (4, 4096) and inp.shape == (4, 5, 7) and lbl.shape == (4, 5, 7)
-    assert lens.shape == (4, 5) and lens.dtype == np.float64 and c_v.shape == (4, 5, 91)
-    feed = _feed(p, feats, (inp, lbl), lens, c_v[:, 0, :])
+    assert lens.shape == (4, 5) and lens.dtype == np.float64 and c_v.shape == (4, 91)
+    feed = _feed(p, feats, (inp, lbl), lens, c_v)
     assert feed["ann_inputs_enc"].shape == (20, 7) and feed["ann_lengths"].shape == (20,)
     assert feed["c_i"].shape == (20, 90)  # column 0 dropped (main.py:236), rows repeated per caption
     np.testing.assert_array_equal(feed["c_i"][0], feed["c_i"][4])

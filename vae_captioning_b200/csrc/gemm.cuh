@@ -40,6 +40,8 @@ struct GemmCore {
   int b_mn;      // 1: B is MN-major (2-D map); 2: MN-major gathered from an NHWC map by 64-pixel patches (A_WGRAD3x3)
   int a_switch;  // A_KMAJOR: k-block at which A switches to tmA2 (coordinates restart at 0)
                  // A_MNMAJOR: m-tile at which A switches to tmA2. <0: never.
+  int n_fast;    // tile order: 0 = m fastest (B tile shared by consecutive CTAs), 1 = n fastest (the n-tiles of one
+                 // m-row run side by side, so a long-K A row panel is fetched from HBM once and hit in L2 after)
   // A_CONV3x3 geometry. A tile is 4 patches of 32 pixels; a patch is pw x ph x pn (w, h, image) with
   // pw*ph*pn == 32, so each epilogue warp owns one patch and 2x2 max-pool partners are lanes of the
   // same warp. Patches are arranged tw x th x (4/(tw*th)) inside the tile.
@@ -88,8 +90,13 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmCore& g, int tile) {
   const int mn = g.m_tiles * g.n_tiles;
   t.split = tile / mn;
   const int rem = tile - t.split * mn;
-  t.n_blk = rem / g.m_tiles;
-  t.m_blk = rem - t.n_blk * g.m_tiles;
+  if (g.n_fast) {
+    t.m_blk = rem / g.n_tiles;
+    t.n_blk = rem - t.m_blk * g.n_tiles;
+  } else {
+    t.n_blk = rem / g.m_tiles;
+    t.m_blk = rem - t.n_blk * g.m_tiles;
+  }
   const int kps = (g.k_blocks + g.splits - 1) / g.splits;
   t.kb_begin = t.split * kps;
   t.kb_end = min(g.k_blocks, t.kb_begin + kps);
@@ -596,6 +603,182 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const uint32_t acc_phase = (ord / nacc) & 1;
       TileCoord t;
       t.m_blk = m_blk; t.n_blk = n_blk; t.split = 0; t.kb_begin = 0; t.kb_end = 9;
+      mbar_wait(&tfull[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + acc * acc_stride + (uint32_t(q * 32) << 16);
+      epi(taddr, g, t, q * 32 + lane, grp_smem, grp, epi_phase);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+    }
+    epi.finish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<512>(tmem_base);
+}
+
+// ------------------------------------------------------------------------------------------
+// Halo form for Cin = 128 / 256 with a narrow output (Cout <= 128): conv2_2, and the input gradients of conv2_1,
+// conv2_2 and conv3_1 (which run through the forward kernel on tap-reversed weights).
+//
+// With Cout <= 128 the generic A_CONV3x3 path is bound by L2 -> SM operand traffic, not by the tensor pipe: every
+// 128-pixel tile re-reads its input patch once per filter tap (9 x Cin/64 x 16 KB) next to the [bn, 9*Cin] filter
+// slice (conv2_2: 295 KB + 295 KB per 37.7 MFLOP tile, ~19 TB/s at tensor speed). Here the patch + halo of each
+// 64-channel slice is staged ONCE per tile (one 4-D TMA box, same layout and shifted-descriptor trick as
+// conv_halo_kernel) and only the filter slice streams through a second ring, one [bn x 64] block per (channel slice,
+// tap): 74 KB + 295 KB per tile for conv2_2. Two producer lanes (warp 0: halos, warp 3: filter blocks) keep the two
+// rings independent. The contraction order is (channel slice, tap, k) instead of (tap, channel slice, k): the same
+// products, summed in a different order in fp32.
+constexpr int kHaloBStages = 4;
+
+__host__ inline int conv_halo_stream_smem_bytes(int bn, int epi_bytes) {
+  return kHaloStages * kHaloBytes + kHaloBStages * bn * 128 + epi_bytes + 1024 + 512;
+}
+
+template <class Epi>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+conv_halo_stream_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmCore g,
+                        const __grid_constant__ Epi epi) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int b_bytes = g.bn * 128;
+  uint8_t* halo = smem;
+  uint8_t* bring = smem + kHaloStages * kHaloBytes;
+  uint8_t* epi_smem = bring + kHaloBStages * b_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_smem + Epi::kSmemBytes);
+  uint64_t* hfull = bars;
+  uint64_t* hempty = hfull + kHaloStages;
+  uint64_t* bfull = hempty + kHaloStages;
+  uint64_t* bempty = bfull + kHaloBStages;
+  uint64_t* tfull = bempty + kHaloBStages;
+  uint64_t* tempty = tfull + kMaxAcc;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + kMaxAcc);
+  const int nacc = gemm_acc_buffers(g.bn);
+  const int acc_stride = gemm_acc_stride(g.bn);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int total_tiles = g.m_tiles * g.n_tiles;
+  const int cin = g.cpk * 64;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < kHaloStages; ++i) {
+      mbar_init(&hfull[i], 1);
+      mbar_init(&hempty[i], 1);
+    }
+    for (int i = 0; i < kHaloBStages; ++i) {
+      mbar_init(&bfull[i], 1);
+      mbar_init(&bempty[i], 1);
+    }
+    for (int i = 0; i < kMaxAcc; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ halo producer: one box per (tile, channel slice)
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const PatchOrigin po = conv_patch_origin(g, tile / g.n_tiles, 0);
+        for (int c = 0; c < g.cpk; ++c) {
+          mbar_wait(&hempty[stage], phase ^ 1);
+          mbar_expect_tx(&hfull[stage], kHaloBytes);
+          tma_load_4d(halo + stage * kHaloBytes, &tmA, &hfull[stage], c * 64, po.w - 1, po.h - 1, po.n);
+          if (++stage == kHaloStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 3) {
+    // ------------------------------------------------------------ filter producer: one [bn x 64] block per (slice, tap)
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int n0 = (tile % g.n_tiles) * g.bn;
+        for (int c = 0; c < g.cpk; ++c) {
+          for (int tap = 0; tap < 9; ++tap) {
+            mbar_wait(&bempty[stage], phase ^ 1);
+            mbar_expect_tx(&bfull[stage], b_bytes);
+            tma_load_2d(bring + stage * b_bytes, &tmB, &bfull[stage], tap * cin + c * 64, n0);
+            if (++stage == kHaloBStages) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(kBM, g.bn, false, false);
+      int hs = 0, bs = 0, acc = 0;
+      uint32_t hphase = 0, bphase = 0, acc_phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * acc_stride;
+        for (int c = 0; c < g.cpk; ++c) {
+          mbar_wait(&hfull[hs], hphase);
+          const uint32_t hbase = smem_u32(halo + hs * kHaloBytes);
+#pragma unroll 1
+          for (int tap = 0; tap < 9; ++tap) {
+            mbar_wait(&bfull[bs], bphase);
+            tc_fence_after();
+            const int fr = tap / 3, fs = tap - fr * 3;
+            const uint64_t adesc = make_smem_desc(hbase + (fr * kHaloLineRows + fs) * 128, 16u, kHaloLineRows * 128);
+            const uint64_t bdesc = make_smem_desc(smem_u32(bring + bs * b_bytes), 16u, 1024);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_bf16(d_tmem, adesc + uint64_t(k * 2), bdesc + uint64_t(k * 2), idesc, (c > 0 || tap > 0 || k > 0) ? 1u : 0u);
+            umma_commit(&bempty[bs]);
+            if (++bs == kHaloBStages) {
+              bs = 0;
+              bphase ^= 1;
+            }
+          }
+          umma_commit(&hempty[hs]);
+          if (++hs == kHaloStages) {
+            hs = 0;
+            hphase ^= 1;
+          }
+        }
+        umma_commit(&tfull[acc]);
+        if (++acc == nacc) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    const int q = warp & 3;
+    const int grp = (warp - 4) >> 2;
+    int epi_phase = 0;
+    uint8_t* grp_smem = epi_smem + grp * (Epi::kSmemBytes / 2);
+    int ord = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ord) {
+      if ((ord & 1) != grp) continue;
+      const int acc = ord % nacc;
+      const uint32_t acc_phase = (ord / nacc) & 1;
+      TileCoord t;
+      t.m_blk = tile / g.n_tiles; t.n_blk = tile % g.n_tiles; t.split = 0; t.kb_begin = 0; t.kb_end = 9 * g.cpk;
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + acc * acc_stride + (uint32_t(q * 32) << 16);

@@ -8,6 +8,8 @@ int gemm_store(cudaStream_t stream, const Operand& A, const Operand* A2, long lo
                int N, int K, const EpiStore& epi_in, int bn, int splits) {
   GemmPlan plan;
   VC_TRY(plan_gemm(&plan, A, A2, a2_at, B, M, N, K, bn, splits));
+  // few n-tiles under a long contraction (dgrad of the vocab projection: 2 x 177 k-blocks): run them side by side
+  plan.core.n_fast = (plan.core.n_tiles <= 4 && plan.core.k_blocks >= 64 && plan.core.m_tiles > plan.core.n_tiles) ? 1 : 0;
   EpiStore epi = epi_in;
   epi.M = M;
   epi.N = N;

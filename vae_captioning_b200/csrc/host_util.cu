@@ -237,6 +237,37 @@ int plan_conv_halo(GemmPlan* p, const void* in, const void* wt, const ConvGeom& 
   return VC_OK;
 }
 
+bool conv_halo_stream_applicable(int W, int H, int Cin, int Cout) {
+  static const bool enabled = [] {
+    const char* e = getenv("VC_CONV_HALO2");
+    return !(e && e[0] == '0');
+  }();
+  return enabled && (Cin == 128 || Cin == 256) && (Cout == 64 || Cout == 128) && W % 8 == 0 && H % 2 == 0 && H >= 16;
+}
+
+int plan_conv_halo_stream(GemmPlan* p, const void* in, const void* wt, const ConvGeom& cg) {
+  if (!(cg.Cin == 128 || cg.Cin == 256) || !(cg.Cout == 64 || cg.Cout == 128) || cg.W % 8 != 0)
+    return set_error(VC_E_SHAPE, "plan_conv_halo_stream: unsupported layer %dx%d Cin=%d Cout=%d", cg.W, cg.H, cg.Cin, cg.Cout);
+  memset(p, 0, sizeof(*p));
+  GemmCore& g = p->core;
+  g.pw = cg.pw; g.ph = cg.ph; g.pn = cg.pn; g.tw = cg.tw; g.th = cg.th;
+  g.tiles_w = cg.W / 8;
+  g.tiles_h = (cg.H + 15) / 16;  // a ragged last tile row: TMA zero-fills the loads and clips the stores
+  g.m_tiles = g.tiles_w * g.tiles_h * cg.Nimg;
+  g.n_tiles = 1;
+  g.cpk = cg.Cin / 64;
+  g.k_blocks = 9 * g.cpk;
+  g.splits = 1;
+  g.bn = cg.Cout;
+  g.stages = kHaloStages;
+  g.a_mode = A_CONV3x3;
+  g.a_switch = -1;
+  VC_TRY(make_tmap_nhwc(&p->tmA, in, cg.Cin, cg.W, cg.H, cg.Nimg, kHaloLineRows, kHaloLines, 1));
+  p->tmA2 = p->tmA;
+  VC_TRY(make_tmap_2d(&p->tmB, wt, 9ull * cg.Cin, cg.Cout, 9ull * cg.Cin, 64, cg.Cout));
+  return VC_OK;
+}
+
 int plan_conv(GemmPlan* p, const void* in, const void* wt, const ConvGeom& cg, int bn) {
   if (cg.Cin % 64 != 0) return set_error(VC_E_SHAPE, "plan_conv: Cin=%d must be a multiple of 64", cg.Cin);
   if (bn % 64 != 0 || bn > 256) return set_error(VC_E_ARG, "plan_conv: bn=%d", bn);

@@ -97,6 +97,30 @@ bool conv_halo_applicable(int W, int H, int Cin, int Cout);
 int conv_halo_geometry(ConvGeom* g, int W, int H, int Nimg, int Cin, int Cout);
 int plan_conv_halo(GemmPlan* p, const void* in, const void* wt, const ConvGeom& g);
 
+// Streamed-filter halo form for Cin in {128, 256} and Cout in {64, 128} (see conv_halo_stream_kernel); the tile width
+// is the whole Cout. VC_CONV_HALO2=0 in the environment turns it off (the generic implicit-GEMM path is used instead).
+bool conv_halo_stream_applicable(int W, int H, int Cin, int Cout);
+int plan_conv_halo_stream(GemmPlan* p, const void* in, const void* wt, const ConvGeom& g);
+
+template <class Epi>
+int launch_conv_halo_stream(const GemmPlan& p, const Epi& epi, cudaStream_t stream) {
+  static bool configured = false;
+  if (!configured) {
+    VC_CUDA(cudaFuncSetAttribute(conv_halo_stream_kernel<Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    configured = true;
+  }
+  const int total = p.core.m_tiles * p.core.n_tiles;
+  if (total <= 0) return VC_OK;
+  const int grid = total < num_sms() ? total : num_sms();
+  const int smem = conv_halo_stream_smem_bytes(p.core.bn, Epi::kSmemBytes);
+  {
+    ProfScope ps(stream, "conv_halo_stream");
+    conv_halo_stream_kernel<Epi><<<grid, kGemmThreads, smem, stream>>>(p.tmA, p.tmB, p.core, epi);
+  }
+  VC_CUDA(cudaGetLastError());
+  return VC_OK;
+}
+
 template <class Epi>
 int launch_conv_halo(const GemmPlan& p, const Epi& epi, cudaStream_t stream) {
   static bool configured = false;

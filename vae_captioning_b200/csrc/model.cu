@@ -672,8 +672,22 @@ int Model::backward(const StepInputs& in, cudaStream_t s) {
     EpiStore e2{};
     e2.out = gp(pidx("decoder/rnn_logits/kernel")); e2.ld = V; e2.alpha = 1.f;
     {
+      // [Hd, V] in 128 x 256 tiles is only (Hd/128) * ceil(V/256) = 180 tiles for 148 SMs (2 waves, the second a fifth
+      // full); split the token contraction so the tile count lands just under a whole number of waves. The gradient
+      // buffer was zeroed above, the partial sums meet in fp32 atomics.
       ProfTag ptag("logits_wgrad");
-      VC_TRY(gemm_store(s, A2, nullptr, 0, B2, Hd, V, (int)rows, e2, 256, 1));
+      const int tiles = ((Hd + 127) / 128) * ((V + 255) / 256);
+      int splits = 1;
+      if (rows >= 4096 && tiles < 4 * num_sms()) {
+        double best = 0.0;
+        for (int sp = 1; sp <= 8; ++sp) {
+          const int t = tiles * sp;
+          const double eff = (double)t / (double)(((t + num_sms() - 1) / num_sms()) * num_sms());
+          if (eff > best + 0.02) { best = eff; splits = sp; }
+        }
+      }
+      e2.atomic = splits > 1 ? 1 : 0;
+      VC_TRY(gemm_store(s, A2, nullptr, 0, B2, Hd, V, (int)rows, e2, 256, splits));
     }
     VC_TRY(colsum_bf16(s, logits, rows, V, VP, gp(pidx("decoder/rnn_logits/bias"))));
   }

@@ -201,10 +201,15 @@ int Model::vgg_conv_layer(int l, const void* in, int B, bool fuse_pool, cudaStre
   }
   ConvGeom g;
   const bool halo = conv_halo_applicable(L.hw, L.hw, L.cin, L.cout);
+  const bool halo2 = !halo && conv_halo_stream_applicable(L.hw, L.hw, L.cin, L.cout);
   if (halo) {
     VC_TRY(conv_halo_geometry(&g, L.hw, L.hw, B, L.cin, L.cout));
     VC_TRY(plan_conv_halo(&plan, in, L.wt, g));
     epi.bn = 64;
+  } else if (halo2) {
+    VC_TRY(conv_halo_geometry(&g, L.hw, L.hw, B, L.cin, L.cout));
+    VC_TRY(plan_conv_halo_stream(&plan, in, L.wt, g));
+    epi.bn = L.cout;
   } else {
     VC_TRY(conv_geometry(&g, L.hw, L.hw, B, L.cin, L.cout));
     VC_TRY(plan_conv(&plan, in, L.wt, g, bn));
@@ -217,6 +222,7 @@ int Model::vgg_conv_layer(int l, const void* in, int B, bool fuse_pool, cudaStre
     VC_TRY(make_tmap_nhwc(&epi.tm, L.out, L.cout, L.hw, L.hw, B, g.pw * g.tw, g.ph * g.th, g.pn * (4 / (g.tw * g.th))));
   }
   if (halo) return launch_conv_halo(plan, epi, s);
+  if (halo2) return launch_conv_halo_stream(plan, epi, s);
   return launch_gemm(plan, epi, s);
 }
 

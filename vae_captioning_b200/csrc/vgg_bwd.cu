@@ -153,16 +153,22 @@ int conv3x3_dgrad(cudaStream_t s, const void* dy, const void* wt_d, void* dx, in
   GemmPlan plan;
   ConvGeom g;
   const bool halo = conv_halo_applicable(hw, hw, cout, cin);
+  const bool halo2 = !halo && conv_halo_stream_applicable(hw, hw, cout, cin);
   if (halo) {
     VC_TRY(conv_halo_geometry(&g, hw, hw, B, cout, cin));
     VC_TRY(plan_conv_halo(&plan, dy, wt_d, g));
     epi.bn = 64;
+  } else if (halo2) {
+    VC_TRY(conv_halo_geometry(&g, hw, hw, B, cout, cin));
+    VC_TRY(plan_conv_halo_stream(&plan, dy, wt_d, g));
+    epi.bn = cin;
   } else {
     VC_TRY(conv_geometry(&g, hw, hw, B, cout, cin));
     VC_TRY(plan_conv(&plan, dy, wt_d, g, bnd));
   }
   VC_TRY(make_tmap_nhwc(&epi.tm, dx, cin, hw, hw, B, g.pw * g.tw, g.ph * g.th, g.pn * (4 / (g.tw * g.th))));
   if (halo) return launch_conv_halo(plan, epi, s);
+  if (halo2) return launch_conv_halo_stream(plan, epi, s);
   return launch_gemm(plan, epi, s);
 }
 

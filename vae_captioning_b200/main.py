@@ -30,7 +30,8 @@ class SyntheticFeeder(object):
         f = synthetic.make_batch(p.batch_size, p.num_captions, self.T, self.V, seed=self.seed + i, images=p.fine_tune,
                                  cluster_vectors=True, ragged=True)
         B, C, T = p.batch_size, p.num_captions, self.T
-        c_v = np.concatenate([np.zeros((B * C, 1), np.float32), f["c_i"]], axis=1).reshape(B, C, 91)
+        # one 91-wide cluster vector per IMAGE, like the generator's cl_v (batch_gen.py:101-130); preprocess_captions tiles it
+        c_v = np.concatenate([np.zeros((B * C, 1), np.float32), f["c_i"]], axis=1).reshape(B, C, 91)[:, 0, :]
         lengths = f["ann_lengths"].astype(np.float64).reshape(B, C)  # float64 like batch_gen.py:317; 0 = missing caption
         return f["image_f_inputs"], (f["ann_inputs_dec"].reshape(B, C, T), f["ann_inputs_enc"].reshape(B, C, T)), lengths, c_v
 
@@ -42,12 +43,12 @@ class SyntheticFeeder(object):
         for i in range(self.batches):
             feats, caps, lens, c_v = self._batch(1000 + i)
             ids = list(range(i * len(feats), (i + 1) * len(feats)))
-            yield feats, caps, lens, ids, c_v[:, 0, :]
+            yield feats, caps, lens, ids, c_v
 
     def next_test_batch(self, use_obj_vectors=False):
         for i in range(self.batches):
             feats, _, _, c_v = self._batch(2000 + i)
-            yield feats, list(range(i * len(feats), (i + 1) * len(feats))), c_v[:, 0, :]
+            yield feats, list(range(i * len(feats), (i + 1) * len(feats))), c_v
 
 
 class _Vocabulary(object):
