@@ -9,9 +9,12 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def declared_symbols():
-    src = open(os.path.join(ROOT, "include", "vaecap.h")).read()
-    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"\b(vc_[a-z0-9_]+)\s*\(", src)))
+    names = set()
+    for header in sorted(os.listdir(os.path.join(ROOT, "include"))):
+        src = open(os.path.join(ROOT, "include", header)).read()
+        src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+        names.update(re.findall(r"\b(vc_[a-z0-9_]+)\s*\(", src))
+    return sorted(names)
 
 
 def test_header_symbols_exported():

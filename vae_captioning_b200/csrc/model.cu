@@ -365,6 +365,7 @@ int Model::stage_slot(int slot, const void* px_host, int kind, const int32_t* lb
   if (q.lbl == nullptr) {
     const size_t px_elems = (cfg.fine_tune || !vgg.empty()) ? (size_t)224 * 224 * 3 : (size_t)cfg.cnn_feature_size;
     VC_TRY(dalloc((float**)&q.px, (size_t)cfg.max_batch * std::max(px_elems, (size_t)cfg.cnn_feature_size), false));
+    if (!vgg.empty() && !cfg.fine_tune) VC_TRY(dalloc(&q.fc2, (size_t)cfg.max_batch * 4096, false));
     VC_TRY(dalloc(&q.cv, (size_t)maxN * cfg.num_clusters, false));
     VC_TRY(dalloc(&q.lbl, (size_t)maxN * maxT, false));
     VC_TRY(dalloc(&q.in, (size_t)maxN * maxT, false));
@@ -380,6 +381,10 @@ int Model::stage_slot(int slot, const void* px_host, int kind, const int32_t* lb
   VC_CUDA(cudaMemcpyAsync(q.len, len, (size_t)N * sizeof(int32_t), cudaMemcpyHostToDevice, cs));
   q.has_cv = cv != nullptr;
   if (cv) VC_CUDA(cudaMemcpyAsync(q.cv, cv, (size_t)N * cfg.num_clusters * sizeof(float), cudaMemcpyHostToDevice, cs));
+  // Frozen extractor: the VGG16 forward of the staged images does not depend on the step in flight (its weights never
+  // change), so it runs here, behind the copy on the copy stream, and overlaps the caption model of the previous batch
+  // (whose recurrent kernels leave SMs idle). The step then starts from the slot's fc2 features.
+  if (kind != 0 && !cfg.fine_tune) VC_TRY(vgg_forward(reinterpret_cast<const float*>(q.px), q.fc2, B, false, nullptr, cs, kind == 2));
   VC_CUDA(cudaEventRecord(q.ready, cs));
   q.B = B;
   q.T = T;
@@ -402,9 +407,8 @@ int Model::step_from_slot(int slot, int64_t gs, const vc_rng* rng, cudaStream_t 
   in.c_v = q.has_cv ? q.cv : nullptr;
   in.global_step = gs;
   if (rng) in.rng = *rng;
-  if (q.kind != 0 && !cfg.fine_tune) {  // frozen extractor: images -> fc2 on the device, then the caption model
-    VC_TRY(vgg_forward(reinterpret_cast<const float*>(q.px), nullptr, q.B, false, nullptr, s, q.kind == 2));
-    in.feats = fc2_f;
+  if (q.kind != 0 && !cfg.fine_tune) {  // frozen extractor: fc2 was computed behind the copy (stage_slot)
+    in.feats = q.fc2;
   } else {
     in.feats = reinterpret_cast<const float*>(q.px);
     in.feats_u8 = q.kind == 2;

@@ -108,6 +108,7 @@ class Model {
   // on a copy stream while the current step computes from the other. Slots are allocated on first use.
   struct StageSlot {
     void* px = nullptr;  // features fp32 [B, F], or images (fp32 / uint8) [B, 224, 224, 3]
+    float* fc2 = nullptr;  // frozen extractor: fc2 features of the staged images, computed on the copy stream
     float* cv = nullptr;
     int32_t *lbl = nullptr, *in = nullptr, *len = nullptr;
     cudaEvent_t ready = nullptr, consumed = nullptr;

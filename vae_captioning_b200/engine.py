@@ -345,11 +345,13 @@ class Engine(object):
         L.check(fn(self._h, _np_ptr(img), _np_ptr(out), img.shape[0], self._stream()))
         return out
 
-    def vgg_forward_device(self, images):
-        """Device-resident form: images is a CUDA float32 tensor [B,224,224,3]; returns a CUDA tensor [B,4096]."""
+    def vgg_forward_device(self, images, out=None):
+        """Device-resident form: images is a CUDA float32 tensor [B,224,224,3]; returns a CUDA tensor [B,4096]
+        (`out` when given). Runs on torch's current stream."""
         import torch
         B = images.shape[0]
-        out = torch.empty((B, 4096), dtype=torch.float32, device=images.device)
+        if out is None:
+            out = torch.empty((B, 4096), dtype=torch.float32, device=images.device)
         self._keep_vgg = (images, out)
         L.check(self.lib.vc_vgg_forward_dev(self._h, L.ptr(images), L.ptr(out), B, self._stream()))
         return out
