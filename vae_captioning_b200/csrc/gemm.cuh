@@ -630,10 +630,18 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 // tap): 74 KB + 295 KB per tile for conv2_2. Two producer lanes (warp 0: halos, warp 3: filter blocks) keep the two
 // rings independent. The contraction order is (channel slice, tap, k) instead of (tap, channel slice, k): the same
 // products, summed in a different order in fp32.
-constexpr int kHaloBStages = 4;
+// Ring depths: a filter block is consumed in 4 MMAs (256 cycles at bn = 128, 128 at bn = 64), far less than the L2
+// latency, so the filter ring must hold many blocks in flight (an ncu capture with 4 stages showed the MMA warp
+// waiting on it 28 % of the time); a halo lasts 9 blocks, two stages are enough.
+constexpr int kHaloSStages = 2;
+constexpr int kHaloBMaxStages = 12;
 
+__host__ __device__ inline int conv_halo_stream_b_stages(int bn, int epi_bytes) {
+  const int n = (227 * 1024 - 1024 - 512 - epi_bytes - kHaloSStages * kHaloBytes) / (bn * 128);
+  return n > kHaloBMaxStages ? kHaloBMaxStages : n;
+}
 __host__ inline int conv_halo_stream_smem_bytes(int bn, int epi_bytes) {
-  return kHaloStages * kHaloBytes + kHaloBStages * bn * 128 + epi_bytes + 1024 + 512;
+  return kHaloSStages * kHaloBytes + conv_halo_stream_b_stages(bn, epi_bytes) * bn * 128 + epi_bytes + 1024 + 512;
 }
 
 template <class Epi>
@@ -644,14 +652,15 @@ conv_halo_stream_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int b_bytes = g.bn * 128;
   uint8_t* halo = smem;
-  uint8_t* bring = smem + kHaloStages * kHaloBytes;
-  uint8_t* epi_smem = bring + kHaloBStages * b_bytes;
+  const int b_stages = conv_halo_stream_b_stages(g.bn, Epi::kSmemBytes);
+  uint8_t* bring = smem + kHaloSStages * kHaloBytes;
+  uint8_t* epi_smem = bring + b_stages * b_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(epi_smem + Epi::kSmemBytes);
   uint64_t* hfull = bars;
-  uint64_t* hempty = hfull + kHaloStages;
-  uint64_t* bfull = hempty + kHaloStages;
-  uint64_t* bempty = bfull + kHaloBStages;
-  uint64_t* tfull = bempty + kHaloBStages;
+  uint64_t* hempty = hfull + kHaloSStages;
+  uint64_t* bfull = hempty + kHaloSStages;
+  uint64_t* bempty = bfull + kHaloBMaxStages;
+  uint64_t* tfull = bempty + kHaloBMaxStages;
   uint64_t* tempty = tfull + kMaxAcc;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + kMaxAcc);
   const int nacc = gemm_acc_buffers(g.bn);
@@ -667,11 +676,11 @@ conv_halo_stream_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
     tma_prefetch_desc(&tmB);
   }
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < kHaloStages; ++i) {
+    for (int i = 0; i < kHaloSStages; ++i) {
       mbar_init(&hfull[i], 1);
       mbar_init(&hempty[i], 1);
     }
-    for (int i = 0; i < kHaloBStages; ++i) {
+    for (int i = 0; i < kHaloBMaxStages; ++i) {
       mbar_init(&bfull[i], 1);
       mbar_init(&bempty[i], 1);
     }
@@ -698,7 +707,7 @@ conv_halo_stream_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
           mbar_wait(&hempty[stage], phase ^ 1);
           mbar_expect_tx(&hfull[stage], kHaloBytes);
           tma_load_4d(halo + stage * kHaloBytes, &tmA, &hfull[stage], c * 64, po.w - 1, po.h - 1, po.n);
-          if (++stage == kHaloStages) {
+          if (++stage == kHaloSStages) {
             stage = 0;
             phase ^= 1;
           }
@@ -717,7 +726,7 @@ conv_halo_stream_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
             mbar_wait(&bempty[stage], phase ^ 1);
             mbar_expect_tx(&bfull[stage], b_bytes);
             tma_load_2d(bring + stage * b_bytes, &tmB, &bfull[stage], tap * cin + c * 64, n0);
-            if (++stage == kHaloBStages) {
+            if (++stage == b_stages) {
               stage = 0;
               phase ^= 1;
             }
@@ -749,13 +758,13 @@ conv_halo_stream_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
             for (int k = 0; k < 4; ++k)
               umma_bf16(d_tmem, adesc + uint64_t(k * 2), bdesc + uint64_t(k * 2), idesc, (c > 0 || tap > 0 || k > 0) ? 1u : 0u);
             umma_commit(&bempty[bs]);
-            if (++bs == kHaloBStages) {
+            if (++bs == b_stages) {
               bs = 0;
               bphase ^= 1;
             }
           }
           umma_commit(&hempty[hs]);
-          if (++hs == kHaloStages) {
+          if (++hs == kHaloSStages) {
             hs = 0;
             hphase ^= 1;
           }
