@@ -307,11 +307,34 @@ def run_decode(args, w, name, rank, world, local_rank):
                 "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 2 * int(host.numel()) * 4,
                         "d2h_bytes_per_step": B * 30 * 4 + B * 5 * 30 * 4 + B * 5 * 8 + B * 8},
                 "gpu_launches": launches, "clocks": clocks, "roofline": None, "cpu_baseline": cpu_baseline}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
     eng.close()
     return 0
+
+
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """Library chatter on stdout (NCCL's version banner, torchrun notices) would precede the result line: send fd 1 to
+    stderr for the duration of the run and keep the real stdout for the ONE JSON line."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
 
 
 def main():
@@ -326,6 +349,7 @@ def main():
     ap.add_argument("--no-profile", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (used under ncu only)")
     args = ap.parse_args()
+    quiet_stdout()
     w = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -334,7 +358,7 @@ def main():
     if args.impl == "reference":
         if rank == 0:
             fn = run_decode_reference if w.get("decode") else run_reference
-            print(json.dumps(fn(args, w, args.workload)), flush=True)
+            emit(fn(args, w, args.workload))
         return 0
     if w.get("decode"):
         import torch
@@ -438,12 +462,17 @@ def main():
             stage((i + 1) & 1)
             out = eng.train_step_staged(i & 1, i, rng={"seed": 1234})
         else:
-            d = {k: v.cuda(non_blocking=True) for k, v in host.items()}
-            if w["vgg"]:
-                d["image_f_inputs"] = d["image_f_inputs"].float()  # uint8 over PCIe, widened on the device
-            feats = eng.vgg_forward_device(d["image_f_inputs"]) if (w["vgg"] and not w.get("fine_tune")) else d["image_f_inputs"]
-            eng.forward_backward_device(feats, d["ann_inputs_enc"], d["ann_inputs_dec"], d["ann_lengths"], step_no[0],
-                                        c_i=d.get("c_i"), rng={"seed": 1234 + rank})
+            # same double-buffered feed per rank; the gradient all-reduce sits between the two halves of the step
+            i = step_no[0]
+            stage = lambda slot: eng.stage_batch(slot, host["image_f_inputs"].numpy(), host["ann_inputs_enc"].numpy(),
+                                                 host["ann_inputs_dec"].numpy(), host["ann_lengths"].numpy(),
+                                                 c_i=host["c_i"].numpy() if "c_i" in host else None,
+                                                 images=w["vgg"] and not w.get("fine_tune"))
+            if not e2e_primed:
+                stage(i & 1)
+                e2e_primed.append(True)
+            stage((i + 1) & 1)
+            eng.forward_backward_staged(i & 1, i, rng={"seed": 1234 + rank})
             dist.all_reduce(grad_t)
             out = eng.apply_gradients(1.0 / world, fetch=True)
         step_no[0] += 1
@@ -584,7 +613,7 @@ def main():
                 "serial_ms_per_step": (ms_serial / args.steps) if ms_serial else None,
                 "step_tflops": tf, "step_tensor_frac": (tf / world / peaks_tf) if peaks_tf else None,
                 "families": families}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
     eng.close()

@@ -139,6 +139,9 @@ int vc_train_step_images_u8(vc_handle* h, const uint8_t* images_host, const int3
 int vc_stage_batch(vc_handle* h, int slot, const void* feats_or_images_host, int kind, const int32_t* cap_lbl_host,
                    const int32_t* cap_in_host, const int32_t* len_host, const float* c_v_host, int B, int T, void* copy_stream);
 int vc_train_step_staged(vc_handle* h, int slot, int64_t global_step, const vc_rng* rng, vc_step_out* out, void* stream);
+/* Data-parallel form of the staged step: forward + backward from the slot, gradients left in vc_grad_buffer for the
+ * caller's all-reduce; finish with vc_apply_gradients(1/world). */
+int vc_forward_backward_staged(vc_handle* h, int slot, int64_t global_step, const vc_rng* rng, void* stream);
 
 /* vc_train_step with inputs already resident in device memory. */
 int vc_train_step_dev(vc_handle* h, const float* feats_dev, const int32_t* cap_lbl_dev, const int32_t* cap_in_dev,

@@ -208,7 +208,11 @@ def test_double_buffered_feed_equals_plain_steps(kw):
     for i in range(4):
         if i + 1 < 4:
             staged.stage_batch((i + 1) & 1, **pinned[i + 1])
-        got.append(staged.train_step_staged(i & 1, anneal=i, rng={"seed": 5 + i}))
+        if i % 2 == 0:
+            got.append(staged.train_step_staged(i & 1, anneal=i, rng={"seed": 5 + i}))
+        else:  # the data-parallel split of the same step (the all-reduce would sit between the two calls)
+            staged.forward_backward_staged(i & 1, anneal=i, rng={"seed": 5 + i})
+            got.append(staged.apply_gradients(1.0))
     for a, b in zip(got, want):
         for k in ("rec_loss", "kld", "lower_bound", "global_norm", "n_tokens", "annealing"):
             assert abs(a[k] - b[k]) <= 1e-4 * max(1.0, abs(b[k])), (k, a[k], b[k])

@@ -220,6 +220,14 @@ int vc_train_step_staged(vc_handle* h, int slot, int64_t gs, const vc_rng* rng, 
   VC_GUARD_END
 }
 
+int vc_forward_backward_staged(vc_handle* h, int slot, int64_t gs, const vc_rng* rng, void* stream) {
+  VC_GUARD_BEGIN
+  if (!h) return set_error(VC_E_ARG, "null handle");
+  cudaSetDevice(h->m.device);
+  return h->m.step_from_slot(slot, gs, rng, (cudaStream_t)stream, false);
+  VC_GUARD_END
+}
+
 int vc_eval_step(vc_handle* h, const float* feats, const int32_t* lbl, const int32_t* inp, const int32_t* len,
                  const float* cv, int B, int T, const vc_rng* rng, vc_step_out* out, void* stream) {
   VC_GUARD_BEGIN

@@ -393,7 +393,7 @@ int Model::stage_slot(int slot, const void* px_host, int kind, const int32_t* lb
   return VC_OK;
 }
 
-int Model::step_from_slot(int slot, int64_t gs, const vc_rng* rng, cudaStream_t s) {
+int Model::step_from_slot(int slot, int64_t gs, const vc_rng* rng, cudaStream_t s, bool apply_update) {
   if (slot < 0 || slot > 1 || !slots[slot].filled)
     return set_error(VC_E_STATE, "vc_train_step_staged: slot %d holds no batch (call vc_stage_batch first)", slot);
   StageSlot& q = slots[slot];
@@ -418,7 +418,7 @@ int Model::step_from_slot(int slot, int64_t gs, const vc_rng* rng, cudaStream_t 
   VC_CUDA(cudaEventRecord(q.consumed, s));
   q.in_use = true;
   q.filled = false;
-  return apply(1.f, s);
+  return apply_update ? apply(1.f, s) : VC_OK;
 }
 
 // ------------------------------------------------------------------------------------------

@@ -118,7 +118,7 @@ class Model {
   StageSlot slots[2];
   int stage_slot(int slot, const void* px_host, int kind, const int32_t* lbl, const int32_t* inp, const int32_t* len,
                  const float* cv, int B, int T, cudaStream_t copy_stream);
-  int step_from_slot(int slot, int64_t gs, const vc_rng* rng, cudaStream_t s);
+  int step_from_slot(int slot, int64_t gs, const vc_rng* rng, cudaStream_t s, bool apply_update = true);
   int* seq_flags = nullptr;    // inter-CTA step counters of the persistent LSTM kernels
 
   // --- VGG16 (vgg.cu)

@@ -118,6 +118,7 @@ class Engine(object):
         lib.vc_vgg_forward_u8.argtypes = [vp, vp, vp, ci, vp]
         lib.vc_stage_batch.argtypes = [vp, ci, vp, ci, vp, vp, vp, vp, ci, ci, vp]
         lib.vc_train_step_staged.argtypes = [vp, ci, cll, ctypes.POINTER(VcRng), ctypes.POINTER(VcStepOut), vp]
+        lib.vc_forward_backward_staged.argtypes = [vp, ci, cll, ctypes.POINTER(VcRng), vp]
         lib.vc_forward_backward_dev.argtypes = step_args + [vp]
         lib.vc_eval_step.argtypes = [vp, vp, vp, vp, vp, vp, ci, ci, ctypes.POINTER(VcRng), ctypes.POINTER(VcStepOut), vp]
         lib.vc_set_cluster_means.argtypes = [vp, vp]
@@ -268,6 +269,13 @@ class Engine(object):
         L.check(self.lib.vc_train_step_staged(self._h, int(slot), int(anneal), ctypes.byref(r),
                                               ctypes.byref(out) if fetch else None, self._stream()))
         return out.as_dict() if fetch else None
+
+    def forward_backward_staged(self, slot, anneal, rng=None):
+        """Data-parallel half of train_step_staged: gradients stay in grad_buffer() for the all-reduce; finish with
+        apply_gradients(1 / world)."""
+        r, keep = self._rng(rng)
+        self._keep = [keep]
+        L.check(self.lib.vc_forward_backward_staged(self._h, int(slot), int(anneal), ctypes.byref(r), self._stream()))
 
     @staticmethod
     def pinned(array):
