@@ -308,3 +308,106 @@ def test_gen_model_matches_training_graph_step():
     probs, _ = step(int(batch["cap_in"][0, 0]), None)
     want = torch.softmax(res["logits"][0], 0).numpy()
     np.testing.assert_allclose(probs.ravel(), want, rtol=1e-9, atol=1e-14)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# Second opinions: TensorFlow cannot run here, so the oracle's restatement of the TF ops is also checked against
+# INDEPENDENT implementations of the same published definitions (torch.nn modules written by other people), with the
+# TF-specific conventions (gate order, forget bias, padding rule, epsilon placement) applied by re-mapping.
+def test_lstm_agrees_with_torch_nn_lstm_after_gate_remap():
+    """tf LSTMCell: [x;h] @ W[E+H, 4H] + b, gates i|j|f|o, forget_bias 1. torch.nn.LSTM: gates i|f|g|o, W_ih[4H,E],
+    W_hh[4H,H], no forget bias. Same recurrence once columns are permuted and 1.0 is folded into b_f."""
+    torch.manual_seed(0)
+    N, T, E, H = 5, 7, 6, 4
+    kernel = torch.randn(E + H, 4 * H, dtype=torch.float64) * 0.4
+    bias = torch.randn(4 * H, dtype=torch.float64) * 0.1
+    x = torch.randn(N, T, E, dtype=torch.float64)
+    lengths = torch.tensor([7, 3, 0, 5, 1])
+    out, h, c = O.dynamic_rnn(x, lengths, torch.zeros(N, H, dtype=torch.float64), torch.zeros(N, H, dtype=torch.float64), kernel, bias)
+    i, j, f, o = torch.chunk(kernel, 4, dim=1)
+    bi, bj, bf, bo = torch.chunk(bias, 4)
+    ref = torch.nn.LSTM(E, H, batch_first=True).double()
+    with torch.no_grad():
+        w = torch.cat([i, f, j, o], dim=1)  # torch order: input, forget, cell (g = tf's j), output
+        ref.weight_ih_l0.copy_(w[:E].t())
+        ref.weight_hh_l0.copy_(w[E:].t())
+        ref.bias_ih_l0.copy_(torch.cat([bi, bf + 1.0, bj, bo]))
+        ref.bias_hh_l0.zero_()
+        for n in range(N):  # dynamic_rnn(sequence_length): run each row for its own length, zeros after, state frozen
+            L = int(lengths[n])
+            if L == 0:
+                assert out[n].abs().max() == 0 and h[n].abs().max() == 0 and c[n].abs().max() == 0
+                continue
+            y, (hn, cn) = ref(x[n:n + 1, :L])
+            np.testing.assert_allclose(out[n, :L].numpy(), y[0].numpy(), rtol=1e-10, atol=1e-12)
+            assert out[n, L:].abs().max() == 0 if L < T else True
+            np.testing.assert_allclose(h[n].numpy(), hn[0, 0].numpy(), rtol=1e-10, atol=1e-12)
+            np.testing.assert_allclose(c[n].numpy(), cn[0, 0].numpy(), rtol=1e-10, atol=1e-12)
+
+
+def test_masked_ce_agrees_with_torch_cross_entropy():
+    """main.py:152-158: sparse softmax CE per token, mask = sign(label), token mean == F.cross_entropy(ignore_index=0)."""
+    import torch.nn.functional as F
+    cfg, params, batch = make_case(TINY, 3, 6, seed=4, ragged=True)
+    res = O.forward(params, cfg, batch)
+    logits = res["logits"]  # row = n * T + t, the order of cap_lbl.reshape(-1) (decoder.py:126-129, main.py:152)
+    labels = batch["cap_lbl"].reshape(-1).long()
+    ce = F.cross_entropy(logits, labels, ignore_index=0, reduction="mean")
+    np.testing.assert_allclose(float(res["rec_loss"]), float(ce), rtol=1e-10)
+    assert int((labels != 0).sum()) > 0
+
+
+def test_adam_agrees_with_torch_adam_up_to_epsilon_placement():
+    """TF1 Adam puts epsilon outside the bias correction (eps_hat = eps / sqrt(1 - beta2^t) relative to the paper form
+    torch implements). With eps -> 0 the two coincide; with the TF epsilon they differ exactly by that rescaling."""
+    torch.manual_seed(1)
+    p0 = torch.randn(50, dtype=torch.float64)
+    grads = [torch.randn(50, dtype=torch.float64) for _ in range(4)]
+    p, m, v = p0.clone(), torch.zeros(50, dtype=torch.float64), torch.zeros(50, dtype=torch.float64)
+    q = p0.clone().requires_grad_(True)
+    opt = torch.optim.Adam([q], lr=5e-4, betas=(0.8, 0.999), eps=1e-300)
+    for t, g in enumerate(grads, start=1):
+        p, m, v = O.adam_update(p, g, m, v, lr=5e-4, t=t, eps=0.0)
+        q.grad = g.clone()
+        opt.step()
+        np.testing.assert_allclose(p.numpy(), q.detach().numpy(), rtol=1e-9, atol=1e-15)
+    # TF epsilon: p -= lr_t * m / (sqrt(v) + eps)  ==  paper form with eps' = eps / sqrt(1 - beta2^t)
+    g = grads[0]
+    p1, _, _ = O.adam_update(p0, g, torch.zeros(50, dtype=torch.float64), torch.zeros(50, dtype=torch.float64), lr=5e-4, t=1, eps=1e-8)
+    m1, v1 = 0.2 * g, 0.001 * g * g
+    paper = p0 - 5e-4 * (m1 / 0.2) / (torch.sqrt(v1 / 0.001) + 1e-8 / math.sqrt(0.001))
+    np.testing.assert_allclose(p1.numpy(), paper.numpy(), rtol=1e-9)
+
+
+def test_vgg_first_layers_agree_with_explicit_window_sums():
+    """utils/image_embeddings.py:26-58: mean-subtracted RGB, 3x3 SAME convolution with HWIO filters (TF's
+    cross-correlation: out[h,w,o] = sum_{r,s,c} x[h+r-1, w+s-1, c] * W[r,s,c,o]) + bias + ReLU, then 2x2/2 max-pool --
+    restated with explicit shifted-window sums in numpy (no convolution routine involved)."""
+    torch.manual_seed(2)
+    images = torch.randint(0, 256, (1, 224, 224, 3)).double()
+    cfg = O.Config()
+    params = O.init_params(cfg, seed=3, with_cnn=True, dtype=torch.float64)
+    for n in list(params):
+        if n.startswith("cnn/") and params[n].dim() == 1:
+            params[n] = torch.linspace(-0.5, 0.5, params[n].numel(), dtype=torch.float64)
+    taps = {}
+    with torch.no_grad():
+        O.vgg16_fc2(params, images, taps=taps)
+    x = images[0].numpy() - np.array([123.68, 116.779, 103.939])
+
+    def conv_relu(x, w, b):
+        H, W, _ = x.shape
+        xp = np.pad(x, ((1, 1), (1, 1), (0, 0)))
+        out = np.zeros((H, W, w.shape[3]))
+        for r in range(3):
+            for s_ in range(3):
+                out += np.einsum("hwc,co->hwo", xp[r:r + H, s_:s_ + W], w[r, s_])
+        return np.maximum(out + b, 0)
+
+    a1 = conv_relu(x, params["cnn/conv1_1/weights"].numpy(), params["cnn/conv1_1/biases"].numpy())
+    np.testing.assert_allclose(taps["conv1_1"][0].numpy(), a1, rtol=1e-9, atol=1e-9)
+    a2 = conv_relu(a1, params["cnn/conv1_2/weights"].numpy(), params["cnn/conv1_2/biases"].numpy())
+    np.testing.assert_allclose(taps["conv1_2"][0].numpy(), a2, rtol=1e-9, atol=1e-8)
+    pooled = a2.reshape(112, 2, 112, 2, 64).max(axis=(1, 3))
+    a3 = conv_relu(pooled, params["cnn/conv2_1/weights"].numpy(), params["cnn/conv2_1/biases"].numpy())
+    np.testing.assert_allclose(taps["conv2_1"][0].numpy(), a3, rtol=1e-9, atol=1e-8)
