@@ -803,4 +803,148 @@ conv_halo_stream_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
   if (warp == 2) tmem_dealloc<512>(tmem_base);
 }
 
+// ------------------------------------------------------------------------------------------
+// Filter gradient of a 3x3 SAME convolution in halo form, for the wide feature maps with few channels (conv1_2,
+// conv2_1, conv2_2: Cin, Cout <= 128), where gemm_tc_kernel's A_WGRAD3x3 mode is bound by L2 -> SM operand traffic:
+// it gathers a fresh shifted 64-pixel x patch per (tap, 64-channel chunk) pair and re-reads the dy patch for every
+// 128-row tile of dW (conv1_2: 24 KB of operands per 128-cycle k-block = 187 B/cycle per SM, three times what an SM can
+// pull from L2).
+//
+// One CTA owns dW[9 taps x 64 cin (chunk c)][64 cout (chunk n)] -- five [128 x 64] accumulators (tap pairs; the ninth
+// tap is paired with itself and its copy is dropped), 320 TMEM columns -- over a range of 8 x 8-pixel patches
+// (split-K across CTAs, fp32 atomics at the end). Per patch it loads ONE x box with the halo (64 ch x 16 w x 10 h,
+// 16-pixel line pitch as in conv_halo_kernel) and ONE dy box (64 ch x 8 x 8): 28 KB for 20 MMAs (640 cycles). Both
+// operands are MN-major (rows = pixels = the contraction). A tap's A operand is the halo buffer read from a shifted
+// start row (fr * 16 + fs): 8-pixel k-groups are one line pitch (2048 B) apart, and the two taps of a pair are the two
+// 64-row halves of the UMMA M extent, their distance carried by the descriptor's leading-dimension byte offset.
+constexpr int kWgHaloBytes = kHaloLineRows * 10 * 128;  // 20,480: x box 16 w x 10 h pixels x 64 channels
+constexpr int kWgDyBytes = 64 * 128;                    // 8,192: dy box 8 x 8 pixels x 64 channels
+constexpr int kWgStageBytes = kWgHaloBytes + kWgDyBytes;
+constexpr int kWgStages = 7;
+
+struct WgradHaloArgs {
+  float* dw;          // [9 * Cin, Cout] fp32, accumulated with atomics
+  int Cin, Cout;
+  int tiles_w, tiles_h, n_img;  // 8 x 8 patches per image row / column (ragged edges: TMA zero fill)
+  int k_total, splits;
+};
+
+static __global__ void __launch_bounds__(256, 1)
+conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDy,
+                       const WgradHaloArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kWgStages * kWgStageBytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + kWgStages;
+  uint64_t* tfull = bars + 2 * kWgStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kWgStages + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int unit = blockIdx.x / a.splits;
+  const int split = blockIdx.x - unit * a.splits;
+  const int n_chunks = a.Cout / 64;
+  const int c_chunk = unit / n_chunks;
+  const int n_chunk = unit - c_chunk * n_chunks;
+  const int kps = (a.k_total + a.splits - 1) / a.splits;
+  const int kb_begin = split * kps;
+  const int kb_end = min(a.k_total, kb_begin + kps);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmDy);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < kWgStages; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    mbar_init(tfull, 1);
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = kb_begin; kb < kb_end; ++kb) {
+        const int tiw = kb % a.tiles_w;
+        const int r = kb / a.tiles_w;
+        const int w0 = tiw * 8, h0 = (r % a.tiles_h) * 8, n0 = r / a.tiles_h;
+        mbar_wait(&empty[stage], phase ^ 1);
+        uint8_t* sx = smem + stage * kWgStageBytes;
+        mbar_expect_tx(&full[stage], kWgStageBytes);
+        tma_load_4d(sx, &tmX, &full[stage], c_chunk * 64, w0 - 1, h0 - 1, n0);
+        tma_load_4d(sx + kWgHaloBytes, &tmDy, &full[stage], n_chunk * 64, w0, h0, n0);
+        if (++stage == kWgStages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(kBM, 64, true, true);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = kb_begin; kb < kb_end; ++kb) {
+        mbar_wait(&full[stage], phase);
+        tc_fence_after();
+        const uint32_t sx = smem_u32(smem + stage * kWgStageBytes);
+        const uint64_t bdesc = make_smem_desc(sx + kWgHaloBytes, 8192u, 1024);
+#pragma unroll
+        for (int p = 0; p < 5; ++p) {
+          const int ta = 2 * p, tb = p < 4 ? 2 * p + 1 : 8;
+          const int ra = (ta / 3) * kHaloLineRows + ta % 3, rb = (tb / 3) * kHaloLineRows + tb % 3;
+          const uint64_t adesc = make_smem_desc(sx + ra * 128, uint32_t(rb - ra) * 128u, kHaloLineRows * 128);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(tmem_base + p * 64, adesc + uint64_t(k * ((2 * kHaloLineRows * 128) >> 4)), bdesc + uint64_t(k * (2048 >> 4)),
+                      idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
+        }
+        umma_commit(&empty[stage]);
+        if (++stage == kWgStages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      umma_commit(tfull);
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------ epilogue: 128 threads, one accumulator row each
+    if (kb_end > kb_begin) {
+      const int q = warp & 3;
+      const int row = q * 32 + lane;
+      mbar_wait(tfull, 0);
+      tc_fence_after();
+#pragma unroll 1
+      for (int p = 0; p < 5; ++p) {
+        const int tap = 2 * p + (row >> 6);
+        const bool keep = p < 4 || row < 64;  // the second half of the last pair is a copy of tap 8
+        float* o = a.dw + ((long long)tap * a.Cin + c_chunk * 64 + (row & 63)) * a.Cout + n_chunk * 64;
+#pragma unroll 1
+        for (int c = 0; c < 64; c += 32) {
+          float v[32];
+          __syncwarp();
+          tmem_ld32(tmem_base + (uint32_t(q * 32) << 16) + p * 64 + c, v);
+          tmem_ld_wait();
+          if (keep) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) atomicAdd(o + c + j, v[j]);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<512>(tmem_base);
+}
+
 }  // namespace vc

@@ -1,6 +1,7 @@
 #include "host_util.h"
 #include <cstdarg>
 #include <cstdlib>
+#include <algorithm>
 #include <atomic>
 #include <mutex>
 #include <vector>
@@ -234,6 +235,54 @@ int plan_conv_halo(GemmPlan* p, const void* in, const void* wt, const ConvGeom& 
   VC_TRY(make_tmap_nhwc(&p->tmA, in, cg.Cin, cg.W, cg.H, cg.Nimg, kHaloLineRows, kHaloLines, 1));
   p->tmA2 = p->tmA;
   VC_TRY(make_tmap_2d(&p->tmB, wt, 9ull * cg.Cin, cg.Cout, 9ull * cg.Cin, 64, 64));
+  return VC_OK;
+}
+
+static int wg_max_ch() {  // VC_WGRAD_HALO_MAXCH: widest layer that takes the halo form (experiment knob)
+  static const int v = [] {
+    const char* e = getenv("VC_WGRAD_HALO_MAXCH");
+    return e ? atoi(e) : 256;
+  }();
+  return v;
+}
+
+bool conv_wgrad_halo_applicable(int W, int H, int Cin, int Cout) {
+  static const bool enabled = [] {
+    const char* e = getenv("VC_WGRAD_HALO");
+    return !(e && e[0] == '0');
+  }();
+  // maps of 56 x 56 and wider (conv1_2 .. conv3_3): there the generic pixel-contraction gather is L2-operand-bound
+  // (measured: wgrad1_2 4.39 -> 0.98 ms, wgrad2_2 2.07 -> 0.95, wgrad3_2 1.19 -> 0.96); 28 x 28 and 14 x 14 maps do not
+  // tile into 8 x 8 patches without waste and keep the generic path
+  return enabled && Cin % 64 == 0 && Cout % 64 == 0 && Cin <= wg_max_ch() && Cout <= wg_max_ch() && W >= 56 && H >= 56;
+}
+
+int launch_conv_wgrad_halo(cudaStream_t stream, const void* x, const void* dy, float* dw, int W, int H, int Nimg, int Cin,
+                           int Cout) {
+  static bool configured = false;
+  const int smem = kWgStages * kWgStageBytes + 1024 + 256;
+  if (!configured) {
+    VC_CUDA(cudaFuncSetAttribute(conv_wgrad_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  WgradHaloArgs a{};
+  a.dw = dw;
+  a.Cin = Cin;
+  a.Cout = Cout;
+  a.tiles_w = (W + 7) / 8;
+  a.tiles_h = (H + 7) / 8;
+  a.n_img = Nimg;
+  a.k_total = a.tiles_w * a.tiles_h * Nimg;
+  const int units = (Cin / 64) * (Cout / 64);
+  a.splits = std::max(1, std::min(num_sms() / units, a.k_total));
+  CUtensorMap tmX, tmDy;
+  VC_TRY(make_tmap_nhwc(&tmX, x, Cin, W, H, Nimg, kHaloLineRows, 10, 1));
+  VC_TRY(make_tmap_nhwc(&tmDy, dy, Cout, W, H, Nimg, 8, 8, 1));
+  {
+    ProfScope ps(stream, "conv_wgrad_halo");
+    conv_wgrad_halo_kernel<<<units * a.splits, 256, smem, stream>>>(tmX, tmDy, a);
+  }
+  VC_CUDA(cudaGetLastError());
   return VC_OK;
 }
 

@@ -97,6 +97,12 @@ bool conv_halo_applicable(int W, int H, int Cin, int Cout);
 int conv_halo_geometry(ConvGeom* g, int W, int H, int Nimg, int Cin, int Cout);
 int plan_conv_halo(GemmPlan* p, const void* in, const void* wt, const ConvGeom& g);
 
+// Halo-form filter gradient (see conv_wgrad_halo_kernel): x, dy bf16 NHWC; dw fp32 [9*Cin, Cout] accumulated with
+// atomics (the caller zeroes it). VC_WGRAD_HALO=0 in the environment turns it off; VC_WGRAD_HALO_MAXCH caps the channel count.
+bool conv_wgrad_halo_applicable(int W, int H, int Cin, int Cout);
+int launch_conv_wgrad_halo(cudaStream_t stream, const void* x, const void* dy, float* dw, int W, int H, int Nimg, int Cin,
+                           int Cout);
+
 // Streamed-filter halo form for Cin in {128, 256} and Cout in {64, 128} (see conv_halo_stream_kernel); the tile width
 // is the whole Cout. VC_CONV_HALO2=0 in the environment turns it off (the generic implicit-GEMM path is used instead).
 bool conv_halo_stream_applicable(int W, int H, int Cin, int Cout);

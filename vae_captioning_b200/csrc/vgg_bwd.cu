@@ -134,6 +134,7 @@ __global__ void k_dgrad_shadow(const float* __restrict__ w, __nv_bfloat16* __res
 // dW[9*Cin, Cout] (fp32, HWIO row-major, accumulated with atomics: the caller zeroes it) += patches(x)^T x dY
 int conv3x3_wgrad(cudaStream_t s, const void* x, const void* dy, float* dw, int B, int hw, int cin, int cout, const char* tag) {
   ProfTag pt(tag);
+  if (conv_wgrad_halo_applicable(hw, hw, cin, cout)) return launch_conv_wgrad_halo(s, x, dy, dw, hw, hw, B, cin, cout);
   const int bn = cout >= 256 ? 256 : cout;
   GemmPlan plan;
   const int tiles = ((9 * cin + 127) / 128) * (cout / bn);
