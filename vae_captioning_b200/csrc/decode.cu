@@ -312,13 +312,16 @@ int Model::decode_begin(const float* feats_dev, const float* c_v_dev, int B, con
   if (has_cv && c_v_dev == nullptr) return set_error(VC_E_ARG, "this configuration needs cluster vectors (c_v)");
   if (shadows_dirty) VC_TRY(refresh_shadows(s));
   VC_TRY(cast_f32_bf16(s, feats_dev, w->feats_h, B, F, F, F));
-  VC_CUDA(cudaMemsetAsync(w->fv_f, 0, (size_t)B * E * sizeof(float), s));
+  // Generation runs its two long contractions (imf_emb K = 4096, z_rnn K = S*Z = 15000) un-split: split-K meets in fp32
+  // atomics whose order changes from run to run, and a 1e-7 wobble in the initial state is enough to flip a bf16
+  // rounding and with it a near-tie between tokens or beams (measured: 6-8 of 1024 captions differed between identical
+  // calls). One tile per CTA costs ~30 us per decode call and makes the token output reproducible bit for bit.
   {
     Operand A{w->feats_h, B, F, F, false}, Bw{imf_wt, E, F, F, false};
     EpiStore e{};
-    e.out = w->fv_f; e.ld = E; e.bias = pp(pidx("imf_emb/bias")); e.atomic = 1; e.alpha = 1.f;
+    e.out = w->fv_f; e.ld = E; e.bias = pp(pidx("imf_emb/bias")); e.alpha = 1.f;
     ProfTag ptag("imf_emb");
-    VC_TRY(gemm_store(s, A, nullptr, 0, Bw, B, E, F, e, 64, 8));
+    VC_TRY(gemm_store(s, A, nullptr, 0, Bw, B, E, F, e, 64, 1));
   }
   VC_TRY(cast_f32_bf16(s, w->fv_f, w->fv_h, B, E, E, E));
   VC_CUDA(cudaMemsetAsync(w->h0, 0, (size_t)B * H * 2, s));
@@ -353,15 +356,13 @@ int Model::decode_begin(const float* feats_dev, const float* c_v_dev, int B, con
           S, Z, K);
     }
     VC_CUDA(cudaGetLastError());
-    VC_CUDA(cudaMemsetAsync(w->zd_f, 0, (size_t)B * E * sizeof(float), s));
     const int SZ = S * Z;
     Operand A{w->z_h, B, SZ, SZ, false}, Bw{z_wt, E, SZ, SZ, false};
     EpiStore e{};
-    e.out = w->zd_f; e.ld = E; e.bias = pp(pidx("decoder/net/z_rnn/bias")); e.atomic = 1; e.alpha = 1.f;
-    const int tiles = ((B + 127) / 128) * ((E + 127) / 128);
+    e.out = w->zd_f; e.ld = E; e.bias = pp(pidx("decoder/net/z_rnn/bias")); e.alpha = 1.f;
     {
       ProfTag ptag("z_rnn");
-      VC_TRY(gemm_store(s, A, nullptr, 0, Bw, B, E, SZ, e, 128, std::max(1, num_sms() / tiles)));
+      VC_TRY(gemm_store(s, A, nullptr, 0, Bw, B, E, SZ, e, 64, 1));
     }
     VC_TRY(cast_f32_bf16(s, w->zd_f, w->zd_h, B, E, E, E));
     VC_TRY(cell(w->zd_h));
