@@ -222,7 +222,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // the whole warp walks the schedule (uniform control flow, descriptors in uniform registers); one elected lane
+    // issues the tcgen05 instructions
+    {
       const bool a_mn = g.a_mode == A_MNMAJOR || g.a_mode == A_WGRAD3x3;
       const uint32_t idesc = make_idesc_bf16(kBM, g.bn, a_mn, g.b_mn != 0);
       const uint32_t a_lbo = a_mn ? 8192u : 16u;
@@ -244,18 +246,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const uint32_t sa = smem_u32(smem + stage * stage_bytes);
           const uint64_t adesc = make_smem_desc(sa, a_lbo, 1024);
           const uint64_t bdesc = make_smem_desc(sa + kABytes, b_lbo, 1024);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < kBK / 16; ++k) {
-            umma_bf16(d_tmem, adesc + uint64_t(k * a_kstep), bdesc + uint64_t(k * b_kstep), idesc,
-                      (kb > t.kb_begin || k > 0) ? 1u : 0u);
+            for (int k = 0; k < kBK / 16; ++k) {
+              umma_bf16(d_tmem, adesc + uint64_t(k * a_kstep), bdesc + uint64_t(k * b_kstep), idesc,
+                        (kb > t.kb_begin || k > 0) ? 1u : 0u);
+            }
+            umma_commit(&empty[stage]);
           }
-          umma_commit(&empty[stage]);
+          __syncwarp();
           if (++stage == g.stages) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit(&tfull[acc]);
+        if (elect_one()) umma_commit(&tfull[acc]);
+        __syncwarp();
         if (++acc == nacc) {
           acc = 0;
           acc_phase ^= 1;
@@ -555,7 +561,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    // MMA issuer: the whole warp walks the schedule (uniform control flow), one elected lane issues
+    {
       const uint32_t idesc = make_idesc_bf16(kBM, 64, false, false);
       int stage = 0;
       uint32_t phase = 0;
@@ -570,17 +577,20 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * acc_stride;
         const uint32_t hbase = smem_u32(halo + stage * kHaloBytes);
+        if (elect_one()) {
 #pragma unroll
-        for (int tap = 0; tap < 9; ++tap) {
-          const int fr = tap / 3, fs = tap - fr * 3;
-          const uint64_t adesc = make_smem_desc(hbase + (fr * kHaloLineRows + fs) * 128, 16u, kHaloLineRows * 128);
-          const uint64_t bdesc = make_smem_desc(wbase + tap * 8192, 16u, 1024);
+          for (int tap = 0; tap < 9; ++tap) {
+            const int fr = tap / 3, fs = tap - fr * 3;
+            const uint64_t adesc = make_smem_desc(hbase + (fr * kHaloLineRows + fs) * 128, 16u, kHaloLineRows * 128);
+            const uint64_t bdesc = make_smem_desc(wbase + tap * 8192, 16u, 1024);
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_bf16(d_tmem, adesc + uint64_t(k * 2), bdesc + uint64_t(k * 2), idesc, (tap > 0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < 4; ++k)
+              umma_bf16(d_tmem, adesc + uint64_t(k * 2), bdesc + uint64_t(k * 2), idesc, (tap > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&hempty[stage]);
+          umma_commit(&tfull[acc]);
         }
-        umma_commit(&hempty[stage]);
-        umma_commit(&tfull[acc]);
+        __syncwarp();
         if (++stage == kHaloStages) {
           stage = 0;
           phase ^= 1;
@@ -735,8 +745,8 @@ conv_halo_stream_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // ------------------------------------------------------------ MMA issuer (whole warp, one elected lane issues)
+    {
       const uint32_t idesc = make_idesc_bf16(kBM, g.bn, false, false);
       int hs = 0, bs = 0, acc = 0;
       uint32_t hphase = 0, bphase = 0, acc_phase = 0;
@@ -754,22 +764,27 @@ conv_halo_stream_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
             const int fr = tap / 3, fs = tap - fr * 3;
             const uint64_t adesc = make_smem_desc(hbase + (fr * kHaloLineRows + fs) * 128, 16u, kHaloLineRows * 128);
             const uint64_t bdesc = make_smem_desc(smem_u32(bring + bs * b_bytes), 16u, 1024);
+            if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              umma_bf16(d_tmem, adesc + uint64_t(k * 2), bdesc + uint64_t(k * 2), idesc, (c > 0 || tap > 0 || k > 0) ? 1u : 0u);
-            umma_commit(&bempty[bs]);
+              for (int k = 0; k < 4; ++k)
+                umma_bf16(d_tmem, adesc + uint64_t(k * 2), bdesc + uint64_t(k * 2), idesc, (c > 0 || tap > 0 || k > 0) ? 1u : 0u);
+              umma_commit(&bempty[bs]);
+            }
+            __syncwarp();
             if (++bs == b_stages) {
               bs = 0;
               bphase ^= 1;
             }
           }
-          umma_commit(&hempty[hs]);
+          if (elect_one()) umma_commit(&hempty[hs]);
+          __syncwarp();
           if (++hs == kHaloSStages) {
             hs = 0;
             hphase ^= 1;
           }
         }
-        umma_commit(&tfull[acc]);
+        if (elect_one()) umma_commit(&tfull[acc]);
+        __syncwarp();
         if (++acc == nacc) {
           acc = 0;
           acc_phase ^= 1;
@@ -889,7 +904,7 @@ conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {  // whole warp walks the k-range, one elected lane issues
       const uint32_t idesc = make_idesc_bf16(kBM, 64, true, true);
       int stage = 0;
       uint32_t phase = 0;
@@ -898,23 +913,27 @@ conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
         tc_fence_after();
         const uint32_t sx = smem_u32(smem + stage * kWgStageBytes);
         const uint64_t bdesc = make_smem_desc(sx + kWgHaloBytes, 8192u, 1024);
+        if (elect_one()) {
 #pragma unroll
-        for (int p = 0; p < 5; ++p) {
-          const int ta = 2 * p, tb = p < 4 ? 2 * p + 1 : 8;
-          const int ra = (ta / 3) * kHaloLineRows + ta % 3, rb = (tb / 3) * kHaloLineRows + tb % 3;
-          const uint64_t adesc = make_smem_desc(sx + ra * 128, uint32_t(rb - ra) * 128u, kHaloLineRows * 128);
+          for (int p = 0; p < 5; ++p) {
+            const int ta = 2 * p, tb = p < 4 ? 2 * p + 1 : 8;
+            const int ra = (ta / 3) * kHaloLineRows + ta % 3, rb = (tb / 3) * kHaloLineRows + tb % 3;
+            const uint64_t adesc = make_smem_desc(sx + ra * 128, uint32_t(rb - ra) * 128u, kHaloLineRows * 128);
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_bf16(tmem_base + p * 64, adesc + uint64_t(k * ((2 * kHaloLineRows * 128) >> 4)), bdesc + uint64_t(k * (2048 >> 4)),
-                      idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
+            for (int k = 0; k < 4; ++k)
+              umma_bf16(tmem_base + p * 64, adesc + uint64_t(k * ((2 * kHaloLineRows * 128) >> 4)), bdesc + uint64_t(k * (2048 >> 4)),
+                        idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty[stage]);
         }
-        umma_commit(&empty[stage]);
+        __syncwarp();
         if (++stage == kWgStages) {
           stage = 0;
           phase ^= 1;
         }
       }
-      umma_commit(tfull);
+      if (elect_one()) umma_commit(tfull);
+      __syncwarp();
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------ epilogue: 128 threads, one accumulator row each

@@ -131,7 +131,7 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {  // whole warp walks the steps (uniform control flow), one elected lane issues the tcgen05 instructions
       const uint32_t idesc = make_idesc_bf16(kBM, g.bn, false, false);
       int stage = 0;
       uint32_t phase = 0;
@@ -146,16 +146,20 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
           const uint32_t sa = smem_u32(smem + stage * stage_bytes);
           const uint64_t adesc = make_smem_desc(sa, 16u, 1024);
           const uint64_t bdesc = make_smem_desc(sa + kABytes, 16u, 1024);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < kBK / 16; ++k)
-            umma_bf16(d_tmem, adesc + uint64_t(k * 2), bdesc + uint64_t(k * 2), idesc, (kb > 0 || k > 0) ? 1u : 0u);
-          umma_commit(&empty[stage]);
+            for (int k = 0; k < kBK / 16; ++k)
+              umma_bf16(d_tmem, adesc + uint64_t(k * 2), bdesc + uint64_t(k * 2), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            umma_commit(&empty[stage]);
+          }
+          __syncwarp();
           if (++stage == g.stages) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit(&tfull[acc]);
+        if (elect_one()) umma_commit(&tfull[acc]);
+        __syncwarp();
       }
     }
   } else if (warp >= 4) {

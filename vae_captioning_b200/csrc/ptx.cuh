@@ -149,6 +149,11 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// elect_one() (top of this file) picks one lane of a CONVERGED warp, the same lane every time for a full mask. The
+// MMA-issuing warps run their loops with all 32 lanes and gate only the tcgen05 instructions with it: descriptors and
+// loop state then live in uniform registers, whereas a loop under `if (lane == 0)` makes ptxas shuttle every descriptor
+// through R2UR inside an ELECT / BRA.U.ANY loop -- about 14 instructions per MMA, more than a 32-cycle N = 64 MMA leaves
+// room for.
 // Arrive on an mbarrier once all previously issued tcgen05.mma of this thread have completed.
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
