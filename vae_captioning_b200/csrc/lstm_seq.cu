@@ -11,6 +11,9 @@
 // the gate pre-activation accumulates into the other TMEM buffer while the previous step's epilogue is still running.
 //
 // Roles (384 threads) as in gemm_tc_kernel; the two epilogue groups split the tile's 64 hidden units 32 / 32.
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
 #include "ops.h"
 #include "lstm_epi.cuh"
 
@@ -24,11 +27,13 @@ struct SeqCore {
   int N;          // rows per step (tensor-map row of step s = s * N)
   int reverse;    // 0: step = it (forward), 1: step = iters - 1 - it
   int* flags;     // [m_tiles, iters + 1] zero-initialised; flags[m][it] = CTAs of row tile m that finished iteration it-1
+  long long* trace;  // debug (VC_LSTM_TRACE=1): [iters][4] clock64() stamps of CTA 0: flag seen, accumulator complete,
+                     // epilogue done, published
 };
 
-// StepEpi: struct State (per-thread registers carried across steps);
+// StepEpi: struct State (per-thread registers carried across steps); static constexpr int kSmemBytes (staging);
 //          __device__ void init(State&, int m_blk, int n_blk, int row, int grp) const / finish(...) const;
-//          __device__ void step(uint32_t taddr, int st, int m_blk, int n_blk, int row, int grp, State&) const
+//          __device__ void step(uint32_t taddr, int st, int m_blk, int n_blk, int row, int grp, State&, uint8_t* smem) const
 template <class StepEpi>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 lstm_seq_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmR,
@@ -36,7 +41,8 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int stage_bytes = gemm_stage_bytes(g.bn);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + g.stages * stage_bytes);
+  uint8_t* epi_smem = smem + g.stages * stage_bytes;  // StepEpi::kSmemBytes of epilogue staging, then the barriers
+  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_smem + StepEpi::kSmemBytes);
   uint64_t* full = bars;
   uint64_t* empty = bars + kMaxStages;
   uint64_t* tfull = bars + 2 * kMaxStages;
@@ -91,6 +97,7 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
             }
             fence_acq_rel_gpu();
             fence_proxy_async_all();
+            if (g.trace && blockIdx.x == 0) g.trace[it * 4 + 0] = clock64();
             ready = true;
             for (int i = 0; i < pend; ++i) {
               const int ps = (pend_stage0 + i) % g.stages;
@@ -172,14 +179,20 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       const int acc = it & 1;
       mbar_wait(&tfull[acc], (it >> 1) & 1);
       tc_fence_after();
-      epi.step(tmem_base + acc * 256 + (uint32_t(q * 32) << 16), st, m_blk, n_blk, q * 32 + lane, grp, state);
+      const bool tr = g.trace && blockIdx.x == 0 && warp == 4 && lane == 0;
+      if (tr) g.trace[it * 4 + 1] = clock64();
+      epi.step(tmem_base + acc * 256 + (uint32_t(q * 32) << 16), st, m_blk, n_blk, q * 32 + lane, grp, state, epi_smem);
+      if (tr) g.trace[it * 4 + 2] = clock64();
       tc_fence_before();
-      // publish: every epilogue thread's stores -> gpu-scope fence -> CTA barrier -> one release increment
-      __threadfence();
+      // publish: the CTA barrier orders every epilogue thread's stores before the elected thread, whose gpu-scope fence
+      // is cumulative over them (the pattern of a cooperative-groups grid barrier); then one release increment. A
+      // __threadfence() in each of the 256 threads did the same job 256 times.
       named_bar_sync(1, 256);
       if (warp == 4 && lane == 0) {
+        fence_acq_rel_gpu();
         fence_proxy_async_all();
         red_release_gpu_add(g.flags + m_blk * (g.iters + 1) + it + 1, 1);
+        if (tr) g.trace[it * 4 + 3] = clock64();
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[acc]);
@@ -209,24 +222,149 @@ struct SeqFwdEpi {
     for (int j = 0; j < 32; ++j) s.c[j] = 0.f;  // cell_0.zero_state
   }
   __device__ __forceinline__ void finish(State&, int, int, int, int) const {}
-  __device__ __forceinline__ void step(uint32_t taddr, int st, int m_blk, int n_blk, int row, int grp, State& state) const {
-    EpiLstmFwd s = e;
+  // A TMEM lane is a tile row, so an epilogue thread owns one row x 32 hidden units and every plane it produces (h, the
+  // emitted output, the four activated gates, the cell state) leaves it in 16 / 32-byte pieces 1 KB apart: a warp-wide
+  // 16-byte store touches 32 cache lines, and 32 such stores per thread per step kept the load/store unit busy for
+  // ~16 k cycles per step (a timeline of CTA 0 showed the epilogue at 19 k of the 32 k cycles of a step). So the pieces
+  // go through shared memory first: the two warps that share 32 rows (same TMEM lane quarter, unit halves 16 | 16) stage
+  // 32 units of every plane per pass, meet at a 64-thread barrier, and write the planes out as whole 64-byte (bf16) /
+  // 128-byte (fp32) row segments -- 8 resp. 4 lines per store instruction. Two passes cover the CTA's 64 units.
+  static constexpr int kPairBytes = 6 * 2048 + 4096;  // per 32-row pair: six bf16 planes [32 x 64 B] + cell state [32 x 128 B]
+  static constexpr int kSmemBytes = 4 * kPairBytes;   // 64 KB
+  __device__ __forceinline__ void step(uint32_t taddr, int st, int m_blk, int n_blk, int row, int grp, State& state,
+                                       uint8_t* stage_smem) const {
     const int t = st - pre;
     const size_t nh = (size_t)e.N * e.H;
-    s.c_prev = Cs + (size_t)st * nh;
-    s.c_out = const_cast<float*>(Cs) + (size_t)(st + 1) * nh;
-    s.h_prev = Hs + (size_t)st * nh;
-    s.h_out = Hs + (size_t)(st + 1) * nh;
-    s.gates = G + (size_t)st * nh * 4;
-    s.out = (out != nullptr && t >= 0) ? out + (size_t)t * nh : nullptr;
-    s.lengths = t >= 0 ? lengths : nullptr;
-    s.out_keep = (out_keep != nullptr && t >= 0) ? out_keep + (size_t)t * e.H : nullptr;
-    s.t = t;
+    float* c_out = const_cast<float*>(Cs) + (size_t)(st + 1) * nh;
+    const __nv_bfloat16* h_prev = Hs + (size_t)st * nh;
+    __nv_bfloat16* h_out = Hs + (size_t)(st + 1) * nh;
+    __nv_bfloat16* gates = G + (size_t)st * nh * 4;
+    __nv_bfloat16* outp = (out != nullptr && t >= 0) ? out + (size_t)t * nh : nullptr;
+    const float* keep = (out_keep != nullptr && t >= 0) ? out_keep + (size_t)t * e.H : nullptr;
+    const int lane = row & 31, q = row >> 5;
     const int m = m_blk * kBM + row;
     const bool row_ok = m < e.N;
-    const bool live = row_ok && (s.lengths == nullptr || t < s.lengths[m]);
-    s.template chunk<true>(taddr, m, row_ok, live, n_blk * kUPT, grp * 32, state.c);
-    s.template chunk<true>(taddr, m, row_ok, live, n_blk * kUPT, grp * 32 + 16, state.c + 16);
+    const bool live = row_ok && (t < 0 || lengths == nullptr || t < lengths[m]);
+    uint8_t* sb = stage_smem + q * kPairBytes;
+    const int pt = grp * 32 + lane;  // thread index inside the pair
+#pragma unroll 1
+    for (int ps = 0; ps < 2; ++ps) {
+      const int ul = ps * 32 + grp * 16;  // this thread's 16 units inside the CTA's 64
+      float* cp = state.c + ps * 16;
+      float gi[16], gj[16], gf[16], go[16];
+      __syncwarp();
+      tmem_ld16(taddr + 0 * kUPT + ul, gi);
+      tmem_ld16(taddr + 1 * kUPT + ul, gj);
+      tmem_ld16(taddr + 2 * kUPT + ul, gf);
+      tmem_ld16(taddr + 3 * kUPT + ul, go);
+      const int u0 = n_blk * kUPT + ul;
+      float bi[16], bj[16], bf[16], bo[16];
+#pragma unroll
+      for (int j = 0; j < 16; j += 4) {
+        *reinterpret_cast<float4*>(bi + j) = __ldg(reinterpret_cast<const float4*>(e.bias + u0 + j));
+        *reinterpret_cast<float4*>(bj + j) = __ldg(reinterpret_cast<const float4*>(e.bias + e.H + u0 + j));
+        *reinterpret_cast<float4*>(bf + j) = __ldg(reinterpret_cast<const float4*>(e.bias + 2 * e.H + u0 + j));
+        *reinterpret_cast<float4*>(bo + j) = __ldg(reinterpret_cast<const float4*>(e.bias + 3 * e.H + u0 + j));
+      }
+      tmem_ld_wait();
+      uint32_t hp[8], op[8], gp[4][8];
+      if (live) {
+        float hn[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float i_ = sigmoid_fast(gi[j] + bi[j]);
+          const float j_ = tanh_fast(gj[j] + bj[j]);
+          const float f_ = sigmoid_fast(gf[j] + bf[j] + 1.0f);
+          const float o_ = sigmoid_fast(go[j] + bo[j]);
+          const float cn = f_ * cp[j] + i_ * j_;
+          hn[j] = o_ * tanh_fast(cn);
+          cp[j] = cn;
+          gi[j] = i_; gj[j] = j_; gf[j] = f_; go[j] = o_;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          hp[j] = pack_bf16(hn[2 * j], hn[2 * j + 1]);
+          gp[0][j] = pack_bf16(gi[2 * j], gi[2 * j + 1]);
+          gp[1][j] = pack_bf16(gj[2 * j], gj[2 * j + 1]);
+          gp[2][j] = pack_bf16(gf[2 * j], gf[2 * j + 1]);
+          gp[3][j] = pack_bf16(go[2 * j], go[2 * j + 1]);
+        }
+        if (keep != nullptr) {  // the emitted value is the bf16 state scaled by the keep mask (the state itself is untouched)
+          const float* kp = keep + (long long)m * e.out_keep_ld + u0;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) hn[j] = __bfloat162float(__float2bfloat16(hn[j])) * kp[j] * e.inv_keep;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) op[j] = pack_bf16(hn[2 * j], hn[2 * j + 1]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) op[j] = hp[j];
+        }
+      } else {
+        // past the end of the sequence (or a padding row of the tile): state copied through, emitted output zero
+        // (SURVEY 5.2); the gate planes of such rows are never read by BPTT and are written as zeros
+        if (row_ok) {
+          const uint4* hsrc = reinterpret_cast<const uint4*>(h_prev + (long long)m * e.H + u0);
+          *reinterpret_cast<uint4*>(hp) = hsrc[0];
+          *reinterpret_cast<uint4*>(hp + 4) = hsrc[1];
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (!row_ok) hp[j] = 0u;
+          op[j] = 0u;
+          gp[0][j] = gp[1][j] = gp[2][j] = gp[3][j] = 0u;
+        }
+      }
+      // ---- stage: bf16 planes with 64-byte rows (16-byte chunk c of row r at c ^ ((r >> 1) & 3)), cell state with
+      // 128-byte rows (chunk c at c ^ (r & 7)): every warp-wide 16-byte access is four conflict-free wavefronts
+      {
+        const int sw = (lane >> 1) & 3;
+        uint8_t* rb = sb + lane * 64;
+        const int c0 = ((grp * 2) ^ sw) << 4, c1 = ((grp * 2 + 1) ^ sw) << 4;
+        *reinterpret_cast<uint4*>(rb + 0 * 2048 + c0) = *reinterpret_cast<uint4*>(hp);
+        *reinterpret_cast<uint4*>(rb + 0 * 2048 + c1) = *reinterpret_cast<uint4*>(hp + 4);
+        *reinterpret_cast<uint4*>(rb + 1 * 2048 + c0) = *reinterpret_cast<uint4*>(op);
+        *reinterpret_cast<uint4*>(rb + 1 * 2048 + c1) = *reinterpret_cast<uint4*>(op + 4);
+#pragma unroll
+        for (int gg = 0; gg < 4; ++gg) {
+          *reinterpret_cast<uint4*>(rb + (2 + gg) * 2048 + c0) = *reinterpret_cast<uint4*>(gp[gg]);
+          *reinterpret_cast<uint4*>(rb + (2 + gg) * 2048 + c1) = *reinterpret_cast<uint4*>(gp[gg] + 4);
+        }
+        uint8_t* cb = sb + 6 * 2048 + lane * 128;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          *reinterpret_cast<uint4*>(cb + (((grp * 4 + j) ^ (lane & 7)) << 4)) = *reinterpret_cast<uint4*>(cp + 4 * j);
+      }
+      named_bar_sync(2 + q, 64);
+      // ---- write out whole row segments: 32 contiguous units of 32 rows per plane
+      {
+        const long long m0 = (long long)m_blk * kBM + q * 32;
+        const int ucol = n_blk * kUPT + ps * 32;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const int e16 = pt + 64 * i;
+          const int r = e16 >> 2, c = e16 & 3;
+          if (m0 + r < e.N) {
+            const uint8_t* src = sb + r * 64 + ((c ^ ((r >> 1) & 3)) << 4);
+            const long long o = (m0 + r) * e.H + ucol + c * 8;
+            *reinterpret_cast<uint4*>(h_out + o) = *reinterpret_cast<const uint4*>(src);
+            if (outp != nullptr) *reinterpret_cast<uint4*>(outp + o) = *reinterpret_cast<const uint4*>(src + 2048);
+            __nv_bfloat16* gdst = gates + (m0 + r) * 4 * e.H + ucol + c * 8;
+#pragma unroll
+            for (int gg = 0; gg < 4; ++gg)
+              *reinterpret_cast<uint4*>(gdst + (long long)gg * e.H) = *reinterpret_cast<const uint4*>(src + (2 + gg) * 2048);
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int e16 = pt + 64 * i;
+          const int r = e16 >> 3, c = e16 & 7;
+          if (m0 + r < e.N)
+            *reinterpret_cast<uint4*>(c_out + (m0 + r) * e.H + ucol + c * 4) =
+                *reinterpret_cast<const uint4*>(sb + 6 * 2048 + r * 128 + ((c ^ (r & 7)) << 4));
+        }
+      }
+      named_bar_sync(2 + q, 64);  // the staging buffer is rewritten by the next pass / step
+    }
   }
 };
 
@@ -239,6 +377,7 @@ struct SeqBwdEpi {
   __nv_bfloat16* dG;         // [steps, N, 4H]
   const int* lengths;
   int pre;
+  static constexpr int kSmemBytes = 0;
   struct State {
     float dh[32], dc[32];  // pass-through dh / dc of this thread's row x 32 hidden units
   };
@@ -266,7 +405,7 @@ struct SeqBwdEpi {
       }
     }
   }
-  __device__ __forceinline__ void step(uint32_t taddr, int st, int m_blk, int n_blk, int row, int grp, State& state) const {
+  __device__ __forceinline__ void step(uint32_t taddr, int st, int m_blk, int n_blk, int row, int grp, State& state, uint8_t*) const {
     LstmBwdCommon s = c;
     const int t = st - pre;
     const size_t nh = (size_t)c.N * c.H;
@@ -299,14 +438,33 @@ static int launch_seq(const CUtensorMap& tmX, const CUtensorMap& tmR, const CUte
     VC_CUDA(cudaFuncSetAttribute(lstm_seq_kernel<Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured = true;
   }
-  core.stages = gemm_pick_stages(core.bn, 0);
-  const int smem = gemm_smem_bytes(core.bn, core.stages, 0);
+  core.stages = gemm_pick_stages(core.bn, Epi::kSmemBytes);
+  const int smem = gemm_smem_bytes(core.bn, core.stages, Epi::kSmemBytes);
   VC_CUDA(cudaMemsetAsync(core.flags, 0, (size_t)core.m_tiles * (core.iters + 1) * sizeof(int), stream));
+  static const bool trace_on = [] { const char* e = getenv("VC_LSTM_TRACE"); return e && e[0] == '1'; }();
+  static int traced = 0;
+  core.trace = nullptr;
+  if (trace_on && traced < 8) {
+    VC_CUDA(cudaMalloc((void**)&core.trace, (size_t)core.iters * 4 * sizeof(long long)));
+    VC_CUDA(cudaMemsetAsync(core.trace, 0, (size_t)core.iters * 4 * sizeof(long long), stream));
+  }
   {
     ProfScope ps(stream, tag);
     lstm_seq_kernel<Epi><<<core.m_tiles * core.n_tiles, kGemmThreads, smem, stream>>>(tmX, tmR, tmB, core, epi);
   }
   VC_CUDA(cudaGetLastError());
+  if (core.trace) {  // debug only: synchronous dump of CTA 0's per-step timeline (cycles)
+    std::vector<long long> h((size_t)core.iters * 4);
+    VC_CUDA(cudaStreamSynchronize(stream));
+    VC_CUDA(cudaMemcpy(h.data(), core.trace, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+    cudaFree(core.trace);
+    fprintf(stderr, "[lstm trace %s #%d] grid %dx%d iters %d kx %d kh %d bn %d: it: flag->acc  acc->epi  epi->pub  pub->nextflag (cycles)\n", tag,
+            traced, core.m_tiles, core.n_tiles, core.iters, core.kx_blocks, core.kh_blocks, core.bn);
+    for (int it = 1; it + 1 < core.iters; ++it)
+      fprintf(stderr, "  %2d: %6lld %6lld %6lld %6lld\n", it, h[it * 4 + 1] - h[it * 4 + 0], h[it * 4 + 2] - h[it * 4 + 1],
+              h[it * 4 + 3] - h[it * 4 + 2], h[(it + 1) * 4 + 0] - h[it * 4 + 3]);
+    ++traced;
+  }
   return VC_OK;
 }
 
