@@ -33,6 +33,8 @@ struct SeqCore {
 
 // StepEpi: struct State (per-thread registers carried across steps); static constexpr int kSmemBytes (staging);
 //          __device__ void init(State&, int m_blk, int n_blk, int row, int grp) const / finish(...) const;
+//          __device__ void prefetch(int st, int m_blk, int n_blk, int row, int grp, uint8_t* smem) const  (before the
+//          accumulator of the step is awaited: stage whatever the step needs that earlier kernels produced)
 //          __device__ void step(uint32_t taddr, int st, int m_blk, int n_blk, int row, int grp, State&, uint8_t* smem) const
 template <class StepEpi>
 __global__ void __launch_bounds__(kGemmThreads, 1)
@@ -177,6 +179,7 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     for (int it = 0; it < g.iters; ++it) {
       const int st = g.reverse ? g.iters - 1 - it : it;
       const int acc = it & 1;
+      epi.prefetch(st, m_blk, n_blk, q * 32 + lane, grp, epi_smem);  // operands that do not depend on the recurrence
       mbar_wait(&tfull[acc], (it >> 1) & 1);
       tc_fence_after();
       const bool tr = g.trace && blockIdx.x == 0 && warp == 4 && lane == 0;
@@ -231,6 +234,7 @@ struct SeqFwdEpi {
   // 128-byte (fp32) row segments -- 8 resp. 4 lines per store instruction. Two passes cover the CTA's 64 units.
   static constexpr int kPairBytes = 6 * 2048 + 4096;  // per 32-row pair: six bf16 planes [32 x 64 B] + cell state [32 x 128 B]
   static constexpr int kSmemBytes = 4 * kPairBytes;   // 64 KB
+  __device__ __forceinline__ void prefetch(int, int, int, int, int, uint8_t*) const {}
   __device__ __forceinline__ void step(uint32_t taddr, int st, int m_blk, int n_blk, int row, int grp, State& state,
                                        uint8_t* stage_smem) const {
     const int t = st - pre;
@@ -377,56 +381,214 @@ struct SeqBwdEpi {
   __nv_bfloat16* dG;         // [steps, N, 4H]
   const int* lengths;
   int pre;
-  static constexpr int kSmemBytes = 0;
+  // Same thread-per-row problem as the forward epilogue, on the load side too: per step a thread read the four gate
+  // planes, c_{t-1} and c_t of its row in 16-byte pieces 1-4 KB apart (40 uncoalesced loads) and wrote dG the same way.
+  // None of those inputs depends on the recurrence, so the two warps that share 32 rows fetch them as whole row segments
+  // into shared memory BEFORE the step's accumulator is awaited (the loads hide under the MMA), each thread then reads
+  // its own row from shared memory, and dG leaves through the same staging area as whole row segments.
+  static constexpr int kPassBytes = 4 * 2048 + 2 * 4096;  // four bf16 gate planes [32 x 64 B] + c_prev, c_cur [32 x 128 B]
+  static constexpr int kPairBytes = 2 * kPassBytes;       // both 32-unit passes
+  static constexpr int kSmemBytes = 4 * kPairBytes;       // 128 KB
   struct State {
-    float dh[32], dc[32];  // pass-through dh / dc of this thread's row x 32 hidden units
+    float dh[32], dc[32];  // pass-through dh / dc of this thread's row: index ps * 16 + j <-> unit ps * 32 + grp * 16 + j
   };
   __device__ __forceinline__ void init(State& s, int m_blk, int n_blk, int row, int grp) const {
     const int m = m_blk * kBM + row;
 #pragma unroll
     for (int j = 0; j < 32; ++j) s.dh[j] = s.dc[j] = 0.f;
     if (m < c.N) {
-      const long long o = (long long)m * c.H + n_blk * 64 + grp * 32;
 #pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        *reinterpret_cast<float4*>(s.dh + j) = *reinterpret_cast<const float4*>(c.dh_carry + o + j);
-        *reinterpret_cast<float4*>(s.dc + j) = *reinterpret_cast<const float4*>(c.dc_carry + o + j);
+      for (int ps = 0; ps < 2; ++ps) {
+        const long long o = (long long)m * c.H + n_blk * 64 + ps * 32 + grp * 16;
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) {
+          *reinterpret_cast<float4*>(s.dh + ps * 16 + j) = *reinterpret_cast<const float4*>(c.dh_carry + o + j);
+          *reinterpret_cast<float4*>(s.dc + ps * 16 + j) = *reinterpret_cast<const float4*>(c.dc_carry + o + j);
+        }
       }
     }
   }
   __device__ __forceinline__ void finish(State& s, int m_blk, int n_blk, int row, int grp) const {
     const int m = m_blk * kBM + row;
     if (m < c.N) {
-      const long long o = (long long)m * c.H + n_blk * 64 + grp * 32;
 #pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        *reinterpret_cast<float4*>(c.dh_carry + o + j) = *reinterpret_cast<float4*>(s.dh + j);
-        *reinterpret_cast<float4*>(c.dc_carry + o + j) = *reinterpret_cast<float4*>(s.dc + j);
+      for (int ps = 0; ps < 2; ++ps) {
+        const long long o = (long long)m * c.H + n_blk * 64 + ps * 32 + grp * 16;
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) {
+          *reinterpret_cast<float4*>(c.dh_carry + o + j) = *reinterpret_cast<float4*>(s.dh + ps * 16 + j);
+          *reinterpret_cast<float4*>(c.dc_carry + o + j) = *reinterpret_cast<float4*>(s.dc + ps * 16 + j);
+        }
       }
     }
   }
-  __device__ __forceinline__ void step(uint32_t taddr, int st, int m_blk, int n_blk, int row, int grp, State& state, uint8_t*) const {
-    LstmBwdCommon s = c;
+  __device__ __forceinline__ void prefetch(int st, int m_blk, int n_blk, int row, int grp, uint8_t* stage_smem) const {
+    const size_t nh = (size_t)c.N * c.H;
+    const __nv_bfloat16* gates = G + (size_t)st * nh * 4;
+    const float* c_prev = Cs + (size_t)st * nh;
+    const float* c_cur = Cs + (size_t)(st + 1) * nh;
+    const int lane = row & 31, q = row >> 5;
+    uint8_t* sb = stage_smem + q * kPairBytes;
+    const int pt = grp * 32 + lane;
+    const long long m0 = (long long)m_blk * kBM + q * 32;
+#pragma unroll
+    for (int ps = 0; ps < 2; ++ps) {
+      uint8_t* pb = sb + ps * kPassBytes;
+      const int ucol = n_blk * 64 + ps * 32;
+      uint4 v[8];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {  // gate planes: 32 rows x 4 chunks of 16 bytes each
+        const int e16 = pt + 64 * i;
+        const int r = e16 >> 2, ch = e16 & 3;
+        const bool ok = m0 + r < c.N;
+        const __nv_bfloat16* src = gates + (m0 + r) * 4 * c.H + ucol + ch * 8;
+#pragma unroll
+        for (int gg = 0; gg < 4; ++gg) v[i * 4 + gg] = ok ? *reinterpret_cast<const uint4*>(src + (long long)gg * c.H) : make_uint4(0, 0, 0, 0);
+      }
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int e16 = pt + 64 * i;
+        const int r = e16 >> 2, ch = e16 & 3;
+        uint8_t* dst = pb + r * 64 + ((ch ^ ((r >> 1) & 3)) << 4);
+#pragma unroll
+        for (int gg = 0; gg < 4; ++gg) *reinterpret_cast<uint4*>(dst + gg * 2048) = v[i * 4 + gg];
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {  // cell states: 32 rows x 8 chunks
+        const int e16 = pt + 64 * i;
+        const int r = e16 >> 3, ch = e16 & 7;
+        const bool ok = m0 + r < c.N;
+        const long long o = (m0 + r) * c.H + ucol + ch * 4;
+        v[i] = ok ? *reinterpret_cast<const uint4*>(c_prev + o) : make_uint4(0, 0, 0, 0);
+        v[4 + i] = ok ? *reinterpret_cast<const uint4*>(c_cur + o) : make_uint4(0, 0, 0, 0);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int e16 = pt + 64 * i;
+        const int r = e16 >> 3, ch = e16 & 7;
+        uint8_t* dst = pb + 8192 + r * 128 + ((ch ^ (r & 7)) << 4);
+        *reinterpret_cast<uint4*>(dst) = v[i];
+        *reinterpret_cast<uint4*>(dst + 4096) = v[4 + i];
+      }
+    }
+    named_bar_sync(2 + q, 64);
+  }
+  __device__ __forceinline__ void step(uint32_t taddr, int st, int m_blk, int n_blk, int row, int grp, State& state,
+                                       uint8_t* stage_smem) const {
     const int t = st - pre;
     const size_t nh = (size_t)c.N * c.H;
-    s.gates = G + (size_t)st * nh * 4;
-    s.c_prev = Cs + (size_t)st * nh;
-    s.c_cur = Cs + (size_t)(st + 1) * nh;
-    s.d_out = (d_out != nullptr && t >= 0) ? d_out + (size_t)t * nh : nullptr;
-    s.out_keep = (out_keep != nullptr && t >= 0) ? out_keep + (size_t)t * c.H : nullptr;
-    s.d_gates = dG + (size_t)st * nh * 4;
-    s.lengths = t >= 0 ? lengths : nullptr;
-    s.t = t;
+    const float* dout = (d_out != nullptr && t >= 0) ? d_out + (size_t)t * nh : nullptr;
+    const float* keep = (out_keep != nullptr && t >= 0) ? out_keep + (size_t)t * c.H : nullptr;
+    __nv_bfloat16* dgates = dG + (size_t)st * nh * 4;
+    const int lane = row & 31, q = row >> 5;
     const int m = m_blk * kBM + row;
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int col = grp * 32 + h * 16;
+    const bool row_ok = m < c.N;
+    const bool live = row_ok && (t < 0 || lengths == nullptr || t < lengths[m]);
+    uint8_t* sb = stage_smem + q * kPairBytes;
+    const int pt = grp * 32 + lane;
+    const long long m0 = (long long)m_blk * kBM + q * 32;
+#pragma unroll 1
+    for (int ps = 0; ps < 2; ++ps) {
+      uint8_t* pb = sb + ps * kPassBytes;
+      const int ul = ps * 32 + grp * 16;
+      const int u0 = n_blk * 64 + ul;
+      float* dhc = state.dh + ps * 16;
+      float* dcc = state.dc + ps * 16;
       float acc[16];
       __syncwarp();
-      tmem_ld16(taddr + col, acc);
+      tmem_ld16(taddr + ul, acc);
+      uint32_t dgp[4][8];
+      // this thread's row of the staged planes (same swizzles as the forward epilogue's staging)
+      const int sw = (lane >> 1) & 3;
+      const uint8_t* rb = pb + lane * 64;
+      const int c0 = ((grp * 2) ^ sw) << 4, c1 = ((grp * 2 + 1) ^ sw) << 4;
       tmem_ld_wait();
-      if (m < c.N) s.core(acc, m, n_blk * 64 + col, state.dh + h * 16, state.dc + h * 16);
+      if (live) {
+        float dov[16];
+        if (dout != nullptr) {
+          const long long o = (long long)m * c.H + u0;
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(dov + j) = *reinterpret_cast<const float4*>(dout + o + j);
+          if (keep != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {
+              const float4 k = *reinterpret_cast<const float4*>(keep + (long long)m * c.out_keep_ld + u0 + j);
+              dov[j] *= k.x * c.inv_keep; dov[j + 1] *= k.y * c.inv_keep; dov[j + 2] *= k.z * c.inv_keep; dov[j + 3] *= k.w * c.inv_keep;
+            }
+          }
+        }
+        float gv[4][16], cp[16], cc[16];
+#pragma unroll
+        for (int gg = 0; gg < 4; ++gg) {
+          const uint4 a = *reinterpret_cast<const uint4*>(rb + gg * 2048 + c0), b = *reinterpret_cast<const uint4*>(rb + gg * 2048 + c1);
+          const __nv_bfloat162* ha = reinterpret_cast<const __nv_bfloat162*>(&a);
+          const __nv_bfloat162* hb = reinterpret_cast<const __nv_bfloat162*>(&b);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 fa = __bfloat1622float2(ha[j]), fb = __bfloat1622float2(hb[j]);
+            gv[gg][2 * j] = fa.x; gv[gg][2 * j + 1] = fa.y;
+            gv[gg][8 + 2 * j] = fb.x; gv[gg][8 + 2 * j + 1] = fb.y;
+          }
+        }
+        const uint8_t* cb = pb + 8192 + lane * 128;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int off = ((grp * 4 + j) ^ (lane & 7)) << 4;
+          *reinterpret_cast<uint4*>(cp + 4 * j) = *reinterpret_cast<const uint4*>(cb + off);
+          *reinterpret_cast<uint4*>(cc + 4 * j) = *reinterpret_cast<const uint4*>(cb + 4096 + off);
+        }
+        float dg[4][16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float gi = gv[0][j], gj = gv[1][j], gf = gv[2][j], go = gv[3][j];
+          float dh = acc[j] + dhc[j];
+          if (dout != nullptr) dh += dov[j];
+          const float tc = tanh_fast(cc[j]);
+          const float dc = dcc[j] + dh * go * (1.f - tc * tc);
+          dg[3][j] = dh * tc * go * (1.f - go);
+          dg[0][j] = dc * gj * gi * (1.f - gi);
+          dg[1][j] = dc * gi * (1.f - gj * gj);
+          dg[2][j] = dc * cp[j] * gf * (1.f - gf);
+          dcc[j] = dc * gf;
+          dhc[j] = 0.f;
+        }
+#pragma unroll
+        for (int gg = 0; gg < 4; ++gg)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) dgp[gg][j] = pack_bf16(dg[gg][2 * j], dg[gg][2 * j + 1]);
+      } else {
+        if (row_ok) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) dhc[j] += acc[j];
+        }
+#pragma unroll
+        for (int gg = 0; gg < 4; ++gg)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) dgp[gg][j] = 0u;
+      }
+      named_bar_sync(2 + q, 64);  // both warps have read this pass's inputs: the gate planes become the dG staging
+      {
+        uint8_t* wb = pb + lane * 64;
+#pragma unroll
+        for (int gg = 0; gg < 4; ++gg) {
+          *reinterpret_cast<uint4*>(wb + gg * 2048 + c0) = *reinterpret_cast<uint4*>(dgp[gg]);
+          *reinterpret_cast<uint4*>(wb + gg * 2048 + c1) = *reinterpret_cast<uint4*>(dgp[gg] + 4);
+        }
+      }
+      named_bar_sync(2 + q, 64);
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int e16 = pt + 64 * i;
+        const int r = e16 >> 2, ch = e16 & 3;
+        if (m0 + r < c.N) {
+          const uint8_t* src = pb + r * 64 + ((ch ^ ((r >> 1) & 3)) << 4);
+          __nv_bfloat16* dst = dgates + (m0 + r) * 4 * c.H + n_blk * 64 + ps * 32 + ch * 8;
+#pragma unroll
+          for (int gg = 0; gg < 4; ++gg) *reinterpret_cast<uint4*>(dst + (long long)gg * c.H) = *reinterpret_cast<const uint4*>(src + gg * 2048);
+        }
+      }
     }
+    named_bar_sync(2 + q, 64);  // the staging area is refilled by the next step's prefetch
   }
 };
 
