@@ -156,7 +156,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    // (whole warp walks the schedule with uniform control flow; one elected lane issues the copies)
+    {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -170,6 +171,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* sa = smem + stage * stage_bytes;
           uint8_t* sb = sa + kABytes;
+          if (elect_one()) {
           mbar_expect_tx(&full[stage], stage_bytes);
           if (g.a_mode == A_KMAJOR) {
             if (g.a_switch >= 0 && kb >= g.a_switch)
@@ -213,6 +215,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           } else if (g.b_mn == 0) {
             tma_load_2d(sb, &tmB, &full[stage], kb * kBK, t.n_blk * g.bn);
           }
+          }
+          __syncwarp();
           if (++stage == g.stages) {
             stage = 0;
             phase ^= 1;
