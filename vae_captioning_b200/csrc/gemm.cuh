@@ -548,16 +548,22 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
-      mbar_expect_tx(wfull, kHaloWBytes);
-      for (int tap = 0; tap < 9; ++tap) tma_load_2d(wres + tap * 8192, &tmB, wfull, tap * 64, n_blk * 64);
+    {  // whole warp, one elected lane issues (see elect_one)
+      if (elect_one()) {
+        mbar_expect_tx(wfull, kHaloWBytes);
+        for (int tap = 0; tap < 9; ++tap) tma_load_2d(wres + tap * 8192, &tmB, wfull, tap * 64, n_blk * 64);
+      }
+      __syncwarp();
       int stage = 0;
       uint32_t phase = 0;
       for (int m_blk = m_first; m_blk < g.m_tiles; m_blk += m_step) {
         const PatchOrigin po = conv_patch_origin(g, m_blk, 0);
         mbar_wait(&hempty[stage], phase ^ 1);
-        mbar_expect_tx(&hfull[stage], kHaloBytes);
-        tma_load_4d(halo + stage * kHaloBytes, &tmA, &hfull[stage], 0, po.w - 1, po.h - 1, po.n);
+        if (elect_one()) {
+          mbar_expect_tx(&hfull[stage], kHaloBytes);
+          tma_load_4d(halo + stage * kHaloBytes, &tmA, &hfull[stage], 0, po.w - 1, po.h - 1, po.n);
+        }
+        __syncwarp();
         if (++stage == kHaloStages) {
           stage = 0;
           phase ^= 1;
@@ -712,15 +718,18 @@ conv_halo_stream_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
 
   if (warp == 0) {
     // ------------------------------------------------------------ halo producer: one box per (tile, channel slice)
-    if (lane == 0) {
+    {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const PatchOrigin po = conv_patch_origin(g, tile / g.n_tiles, 0);
         for (int c = 0; c < g.cpk; ++c) {
           mbar_wait(&hempty[stage], phase ^ 1);
-          mbar_expect_tx(&hfull[stage], kHaloBytes);
-          tma_load_4d(halo + stage * kHaloBytes, &tmA, &hfull[stage], c * 64, po.w - 1, po.h - 1, po.n);
+          if (elect_one()) {
+            mbar_expect_tx(&hfull[stage], kHaloBytes);
+            tma_load_4d(halo + stage * kHaloBytes, &tmA, &hfull[stage], c * 64, po.w - 1, po.h - 1, po.n);
+          }
+          __syncwarp();
           if (++stage == kHaloSStages) {
             stage = 0;
             phase ^= 1;
@@ -730,7 +739,7 @@ conv_halo_stream_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
     }
   } else if (warp == 3) {
     // ------------------------------------------------------------ filter producer: one [bn x 64] block per (slice, tap)
-    if (lane == 0) {
+    {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -738,8 +747,11 @@ conv_halo_stream_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
         for (int c = 0; c < g.cpk; ++c) {
           for (int tap = 0; tap < 9; ++tap) {
             mbar_wait(&bempty[stage], phase ^ 1);
-            mbar_expect_tx(&bfull[stage], b_bytes);
-            tma_load_2d(bring + stage * b_bytes, &tmB, &bfull[stage], tap * cin + c * 64, n0);
+            if (elect_one()) {
+              mbar_expect_tx(&bfull[stage], b_bytes);
+              tma_load_2d(bring + stage * b_bytes, &tmB, &bfull[stage], tap * cin + c * 64, n0);
+            }
+            __syncwarp();
             if (++stage == b_stages) {
               stage = 0;
               phase ^= 1;
@@ -889,7 +901,7 @@ conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
+    {
       int stage = 0;
       uint32_t phase = 0;
       for (int kb = kb_begin; kb < kb_end; ++kb) {
@@ -898,9 +910,12 @@ conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
         const int w0 = tiw * 8, h0 = (r % a.tiles_h) * 8, n0 = r / a.tiles_h;
         mbar_wait(&empty[stage], phase ^ 1);
         uint8_t* sx = smem + stage * kWgStageBytes;
-        mbar_expect_tx(&full[stage], kWgStageBytes);
-        tma_load_4d(sx, &tmX, &full[stage], c_chunk * 64, w0 - 1, h0 - 1, n0);
-        tma_load_4d(sx + kWgHaloBytes, &tmDy, &full[stage], n_chunk * 64, w0, h0, n0);
+        if (elect_one()) {
+          mbar_expect_tx(&full[stage], kWgStageBytes);
+          tma_load_4d(sx, &tmX, &full[stage], c_chunk * 64, w0 - 1, h0 - 1, n0);
+          tma_load_4d(sx + kWgHaloBytes, &tmDy, &full[stage], n_chunk * 64, w0, h0, n0);
+        }
+        __syncwarp();
         if (++stage == kWgStages) {
           stage = 0;
           phase ^= 1;
