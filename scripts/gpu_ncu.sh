@@ -6,7 +6,7 @@ for spec in "$@"; do
   IFS=: read name rx skip wl <<< "$spec"
   wl=${wl:-cfg2_vgg_normal_b256}
   timeout 900 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k "regex:$rx" -s $skip -c 1 -f -o /tmp/ncu/$name \
-     python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu-baseline --no-profile --workload $wl > gpurun_out/ncu_$name.log 2>&1
+     python bench.py --steps ${NCU_STEPS:-1} --warmup 3 --no-e2e --no-cpu-baseline --no-profile --workload $wl > gpurun_out/ncu_$name.log 2>&1
   echo "ncu $name rc=$?"
   python scripts/ncu_summary.py /tmp/ncu/$name.ncu-rep > gpurun_out/ncu_$name.txt 2>&1
   python scripts/ncu_hot.py /tmp/ncu/$name.ncu-rep 40 > gpurun_out/hot_$name.txt 2>&1
