@@ -398,10 +398,9 @@ int Model::decode_advance(int M, cudaStream_t s) {
   VC_TRY(lstm_fwd_step(s, a));
   w->cur ^= 1;
   Operand A{w->h[w->cur], M, H, H, false}, Bw{wo_t, V, H, H, false};
-  EpiStore e{};
-  e.out = w->logits; e.ld = VP; e.bias = pp(pidx("decoder/rnn_logits/bias")); e.alpha = 1.f;
   ProfTag ptag("logits_decode");
-  return gemm_store(s, A, nullptr, 0, Bw, M, V, H, e, 128, 1);
+  // fp32 logits (token ties are decided at the 1e-4 level) through the TMA-store epilogue: whole 128-byte row segments
+  return gemm_tma_rows_f32(s, A, Bw, M, V, H, w->logits, VP, pp(pidx("decoder/rnn_logits/bias")), 256);
 }
 
 static int launch_topk(cudaStream_t s, const float* logits, long long ld, int V, int M, int k, int* idx, float* p, float* probs,

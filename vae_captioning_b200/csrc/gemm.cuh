@@ -479,6 +479,54 @@ struct EpiTma {
 };
 
 // ------------------------------------------------------------------------------------------
+// fp32 row-matrix tile store through shared memory + TMA: out[m, n] = acc * alpha + bias[n], 32 columns (128 bytes) at
+// a time. Same reason as EpiTma: a TMEM lane is a tile row, so EpiStore's per-thread 16-byte stores touch 32 cache lines
+// per warp instruction; for the [rows, vocab] fp32 logits of the decode step (232 MB per step at 5120 rows) that made
+// the vocab projection run at 0.4 PFLOP/s. TMA clips the ragged last column block and the last rows.
+struct EpiTmaF32 {
+  CUtensorMap tm;     // fp32 [M, N] map, box {32, 128}, 128-byte swizzle
+  const float* bias;  // nullable, indexed by n
+  int N, bn;
+  float alpha;
+  static constexpr int kSmemBytes = 32 * 1024;  // 2 groups x (128 rows x 128 B)
+
+  __device__ __forceinline__ void finish() const {
+    if ((threadIdx.x & 127) == 0) bulk_wait_all();
+  }
+  __device__ __forceinline__ void operator()(uint32_t taddr, const GemmCore&, const TileCoord& t, int row, uint8_t* buf, int grp,
+                                             int& phase) const {
+    const int n_base = t.n_blk * bn;
+#pragma unroll 1
+    for (int c = 0; c < bn; c += 32) {
+      const int n0 = n_base + c;
+      if (n0 >= N) break;  // warp-uniform
+      float v[32];
+      __syncwarp();
+      tmem_ld32(taddr + c, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float b = (bias != nullptr && n0 + j < N) ? __ldg(bias + n0 + j) : 0.f;
+        v[j] = fmaf(v[j], alpha, b);
+      }
+      if (row == 0) bulk_wait_read<0>();  // the staging buffer was handed to a bulk store one chunk ago
+      named_bar_sync(1 + grp, 128);
+      uint8_t* rp = buf + row * 128;
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        *reinterpret_cast<uint4*>(rp + ((j ^ (row & 7)) << 4)) = *reinterpret_cast<uint4*>(v + 4 * j);
+      fence_proxy_async();
+      named_bar_sync(1 + grp, 128);
+      if (row == 0) {
+        tma_store_2d(&tm, buf, n0, t.m_blk * kBM);
+        bulk_commit();
+      }
+      phase ^= 1;
+    }
+  }
+};
+
+// ------------------------------------------------------------------------------------------
 // 3x3 SAME convolution for Cin == 64 with the input patch staged ONCE per tile ("halo" form).
 //
 // gemm_tc_kernel's A_CONV3x3 mode re-reads the 128-pixel input patch from L2 for each of the 9 filter taps

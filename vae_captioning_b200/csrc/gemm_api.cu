@@ -37,6 +37,21 @@ int gemm_tma_rows(cudaStream_t stream, const Operand& A, const Operand& B, int M
   return launch_gemm(plan, epi, stream);
 }
 
+// out[M, N] (fp32, row pitch ldo) = A x B + bias through the fp32 TMA-store epilogue (decode: vocab logits per step).
+int gemm_tma_rows_f32(cudaStream_t stream, const Operand& A, const Operand& B, int M, int N, int K, float* out, long long ldo,
+                      const float* bias, int bn) {
+  if (bn % 32 != 0) return set_error(VC_E_ARG, "gemm_tma_rows_f32: bn=%d must be a multiple of 32", bn);
+  GemmPlan plan;
+  VC_TRY(plan_gemm(&plan, A, nullptr, 0, B, M, N, K, bn, 1));
+  EpiTmaF32 epi{};
+  epi.bias = bias;
+  epi.N = N;
+  epi.bn = bn;
+  epi.alpha = 1.f;
+  VC_TRY(make_tmap_2d_f32(&epi.tm, out, (uint64_t)N, (uint64_t)M, (uint64_t)ldo, 128));
+  return launch_gemm(plan, epi, stream);
+}
+
 }  // namespace vc
 
 extern "C" int vc_gemm_bf16(const void* A, int a_mn, long long lda, const void* B, int b_mn, long long ldb, void* out,

@@ -145,6 +145,25 @@ int make_tmap_2d(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t out
   return VC_OK;
 }
 
+int make_tmap_2d_f32(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_outer) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return set_error(VC_E_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || ((ld * 4) & 15))
+    return set_error(VC_E_ARG, "TMA operand must be 16-byte aligned with a 16-byte row pitch (ptr=%p ld=%llu)", ptr,
+                     (unsigned long long)ld);
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {ld * 4};
+  cuuint32_t box[2] = {32, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return set_error(VC_E_CUDA, "cuTensorMapEncodeTiled(f32 inner=%llu outer=%llu ld=%llu) -> %d", (unsigned long long)inner,
+                     (unsigned long long)outer, (unsigned long long)ld, (int)r);
+  return VC_OK;
+}
+
 int make_tmap_nhwc(CUtensorMap* out, const void* ptr, int C, int W, int H, int N, int bw, int bh, int bi) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return set_error(VC_E_CUDA, "cuTensorMapEncodeTiled entry point unavailable");

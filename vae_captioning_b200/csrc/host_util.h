@@ -54,6 +54,8 @@ struct ProfScope {
 // ld = row pitch in elements (ld*2 must be a multiple of 16 bytes).
 int make_tmap_2d(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner,
                  uint32_t box_outer);
+// fp32 [outer, inner] row-major (row pitch ld floats), box {32, box_outer}, 128B swizzle (store side of EpiTmaF32)
+int make_tmap_2d_f32(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_outer);
 // 4-D bf16 NHWC tensor map {C, W, H, N} with box {64, bw, bh, bi}, 128B swizzle.
 int make_tmap_nhwc(CUtensorMap* out, const void* ptr, int C, int W, int H, int N, int bw, int bh, int bi);
 

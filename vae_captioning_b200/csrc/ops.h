@@ -10,6 +10,8 @@ int gemm_store(cudaStream_t stream, const Operand& A, const Operand* A2, long lo
 
 int gemm_tma_rows(cudaStream_t stream, const Operand& A, const Operand& B, int M, int N, int K, void* out, long long ldo,
                   const float* bias, int relu, int bn);
+int gemm_tma_rows_f32(cudaStream_t stream, const Operand& A, const Operand& B, int M, int N, int K, float* out, long long ldo,
+                      const float* bias, int bn);
 
 // lstm.cu ----------------------------------------------------------------------------------
 struct LstmFwdArgs {
