@@ -454,9 +454,11 @@ int dz_reduce(cudaStream_t s, const float* dz, const float* eps, unsigned long l
 // Vocab softmax cross-entropy over bf16 logits rows [rows, ld] (row = t*N + n, time-major), labels
 // lbl[n*T + t]. One CTA per row; the row lives in registers between the two passes, so logits are
 // read once and (optionally) overwritten in place by dlogits = (softmax - onehot) * mask * gscale.
-// Accumulates sums[0] += ce*mask, sums[1] += mask. gscale = loss_scale / count[0] (count = sum mask).
+// Rows are 16-byte aligned (ld % 8 == 0): every thread moves its share as 16-byte vectors, all of
+// them in flight before the first use. Accumulates sums[0] += ce*mask, sums[1] += mask.
+// gscale = loss_scale / count[0] (count = sum mask).
 constexpr int kCeThreads = 256;
-constexpr int kCeMaxPerThread = 48;  // supports V up to 256*48*... (bf16x2 pairs): 24576
+constexpr int kCeVecs = 6;  // 8-element vectors per thread: V <= 256 * 6 * 8 = 12288
 
 __global__ void __launch_bounds__(kCeThreads)
 k_ce(__nv_bfloat16* __restrict__ logits, long long ld, const int* __restrict__ lbl, int N, int T, int V,
@@ -465,21 +467,33 @@ k_ce(__nv_bfloat16* __restrict__ logits, long long ld, const int* __restrict__ l
   const int row = blockIdx.x;
   const int t = row / N, n = row - t * N;
   const int label = lbl[(long long)n * T + t];
-  __nv_bfloat162* p = reinterpret_cast<__nv_bfloat162*>(logits + (long long)row * ld);
-  const int pairs = (V + 1) / 2;
-  constexpr int kPairs = kCeMaxPerThread / 2;
-  float2 v[kPairs];
+  uint4* p = reinterpret_cast<uint4*>(logits + (long long)row * ld);
+  const int vecs = (V + 7) / 8;
+  uint4 raw[kCeVecs];
+#pragma unroll
+  for (int c = 0; c < kCeVecs; ++c) {
+    const int i = threadIdx.x + c * kCeThreads;
+    raw[c] = make_uint4(0xff80ff80u, 0xff80ff80u, 0xff80ff80u, 0xff80ff80u);  // bf16 -inf pairs
+    if (i < vecs) raw[c] = p[i];
+  }
+  float v[kCeVecs * 8];
   float mx = -INFINITY;
 #pragma unroll
-  for (int c = 0; c < kPairs; ++c) {
+  for (int c = 0; c < kCeVecs; ++c) {
     const int i = threadIdx.x + c * kCeThreads;
-    float2 f = make_float2(-INFINITY, -INFINITY);
-    if (i < pairs) {
-      f = __bfloat1622float2(p[i]);
-      if (2 * i + 1 >= V) f.y = -INFINITY;
+    const uint32_t w[4] = {raw[c].x, raw[c].y, raw[c].z, raw[c].w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {  // bf16 -> fp32 is a 16-bit shift
+      v[c * 8 + 2 * k] = __uint_as_float(w[k] << 16);
+      v[c * 8 + 2 * k + 1] = __uint_as_float(w[k] & 0xffff0000u);
     }
-    v[c] = f;
-    mx = fmaxf(mx, fmaxf(f.x, f.y));
+    if (i == vecs - 1) {  // the row's last vector may run into the pitch padding
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        if (8 * i + k >= V) v[c * 8 + k] = -INFINITY;
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) mx = fmaxf(mx, v[c * 8 + k]);
   }
   __shared__ float red[kCeThreads / 32];
   __shared__ float bcast;
@@ -495,10 +509,9 @@ k_ce(__nv_bfloat16* __restrict__ logits, long long ld, const int* __restrict__ l
   mx = bcast;
   float sum = 0.f;
 #pragma unroll
-  for (int c = 0; c < kPairs; ++c) {
-    v[c].x = __expf(v[c].x - mx);
-    v[c].y = __expf(v[c].y - mx);
-    sum += v[c].x + v[c].y;
+  for (int j = 0; j < kCeVecs * 8; ++j) {
+    v[j] = __expf(v[j] - mx);
+    sum += v[j];
   }
   __syncthreads();
   sum = warp_sum(sum);
@@ -524,25 +537,29 @@ k_ce(__nv_bfloat16* __restrict__ logits, long long ld, const int* __restrict__ l
   }
   if (write_grad) {
     __syncthreads();  // the label logit was read above before anyone overwrites it
-    const float g = mask * loss_scale / fmaxf(count[0], 1.f) / sum;
     const float gm = mask * loss_scale / fmaxf(count[0], 1.f);
+    const float g = gm / sum;
 #pragma unroll
-    for (int c = 0; c < kPairs; ++c) {
+    for (int c = 0; c < kCeVecs; ++c) {
       const int i = threadIdx.x + c * kCeThreads;
-      if (i < pairs) {
-        float a = v[c].x * g, b = v[c].y * g;
-        if (2 * i == label) a -= gm;
-        if (2 * i + 1 == label) b -= gm;
-        if (2 * i + 1 >= V) b = 0.f;
-        p[i] = __floats2bfloat162_rn(a, b);
+      if (i < vecs) {
+        float a[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int col = 8 * i + k;
+          a[k] = v[c * 8 + k] * g - (col == label ? gm : 0.f);
+          if (col >= V) a[k] = 0.f;
+        }
+        p[i] = make_uint4(pack_bf16(a[0], a[1]), pack_bf16(a[2], a[3]), pack_bf16(a[4], a[5]), pack_bf16(a[6], a[7]));
       }
     }
   }
 }
 int ce_rows(cudaStream_t s, void* logits, long long ld, const int* lbl, int N, int T, int V, float* sums, float* ce_out,
             const float* count, float loss_scale, int write_grad) {
-  if (V > kCeThreads * kCeMaxPerThread) return set_error(VC_E_SHAPE, "vocab_size %d exceeds CE kernel limit", V);
-  if (ld % 2 != 0) return set_error(VC_E_SHAPE, "logits pitch must be even");
+  if (V > kCeThreads * kCeVecs * 8) return set_error(VC_E_SHAPE, "vocab_size %d exceeds CE kernel limit", V);
+  if (ld % 8 != 0 || (reinterpret_cast<uintptr_t>(logits) & 15) != 0)
+    return set_error(VC_E_SHAPE, "logits rows must be 16-byte aligned (pitch multiple of 8)");
   {
     ProfScope ps(s, "ce");
     k_ce<<<N * T, kCeThreads, 0, s>>>((__nv_bfloat16*)logits, ld, lbl, N, T, V, sums, ce_out, count, loss_scale, write_grad);

@@ -315,14 +315,17 @@ struct EpiStore {
   int out_bf16;
   int atomic;  // fp32 atomicAdd (bias added by split 0 only)
   float alpha;
-  static constexpr int kSmemBytes = 0;
+  // staging for the atomic path: one 32 x 32 fp32 block per epilogue warp (2 groups x 4 warps x 4 KB)
+  static constexpr int kSmemBytes = 32 * 1024;
   __device__ __forceinline__ void finish() const {}
 
-  __device__ __forceinline__ void operator()(uint32_t taddr, const GemmCore&, const TileCoord& t, int row, uint8_t*,
-                                             int, int&) const {
+  __device__ __forceinline__ void operator()(uint32_t taddr, const GemmCore&, const TileCoord& t, int row,
+                                             uint8_t* grp_smem, int, int&) const {
     const int m = t.m_blk * kBM + row;
     const int n_base = t.n_blk * bn;
     const bool row_ok = m < M;
+    const int lane = row & 31;
+    float* stage = reinterpret_cast<float*>(grp_smem) + (row >> 5) * 1024;
     for (int c = 0; c < bn; c += 32) {
       if (n_base + c >= N) break;  // warp-uniform
       float v[32];
@@ -338,34 +341,53 @@ struct EpiStore {
         if (relu) x = fmaxf(x, 0.f);
         v[j] = x;
       }
-      if (row_ok) {
-        if (atomic) {
-          float* o = reinterpret_cast<float*>(out) + (long long)m * ld + n0;
-          for (int j = 0; j < nv; ++j) atomicAdd(o + j, v[j]);
-        } else if (out_bf16) {
-          __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out) + (long long)m * ld + n0;
-          if (nv == 32 && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
+      // vector stores need every row of the block 16-byte aligned (warp-uniform test)
+      const int esize = out_bf16 ? 2 : 4;
+      const bool vec_ok = nv == 32 && ((ld * esize) & 15) == 0 &&
+                          ((reinterpret_cast<uintptr_t>(out) + (uintptr_t)n0 * esize) & 15) == 0;
+      if (atomic || !vec_ok) {
+        // A TMEM lane is a tile row, so thread-per-row atomics (or scalar stores) would touch 32 cache lines per warp
+        // instruction, one 4-byte piece per 32-byte sector. Transpose the warp's 32 x 32 block through shared memory
+        // (XOR-swizzled columns: conflict-free both ways) so each instruction covers 32 consecutive elements of ONE
+        // output row. Also the path for ragged / unaligned blocks: no dynamically indexed register array anywhere.
 #pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              uint4 u;
-              u.x = pack_bf16(v[j], v[j + 1]);
-              u.y = pack_bf16(v[j + 2], v[j + 3]);
-              u.z = pack_bf16(v[j + 4], v[j + 5]);
-              u.w = pack_bf16(v[j + 6], v[j + 7]);
-              *reinterpret_cast<uint4*>(o + j) = u;
-            }
+        for (int j = 0; j < 32; ++j) stage[lane * 32 + (j ^ lane)] = v[j];
+        __syncwarp();
+        const int m0 = t.m_blk * kBM + (row & ~31);
+        const int rows_ok = min(32, M - m0);
+        if (lane < nv) {
+          const long long o0 = (long long)m0 * ld + n0 + lane;
+          if (atomic) {
+            float* o = reinterpret_cast<float*>(out) + o0;
+#pragma unroll 4
+            for (int r = 0; r < rows_ok; ++r) atomicAdd(o + (long long)r * ld, stage[r * 32 + (lane ^ r)]);
+          } else if (out_bf16) {
+            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out) + o0;
+#pragma unroll 4
+            for (int r = 0; r < rows_ok; ++r) o[(long long)r * ld] = __float2bfloat16(stage[r * 32 + (lane ^ r)]);
           } else {
-            for (int j = 0; j < nv; ++j) o[j] = __float2bfloat16(v[j]);
+            float* o = reinterpret_cast<float*>(out) + o0;
+#pragma unroll 4
+            for (int r = 0; r < rows_ok; ++r) o[(long long)r * ld] = stage[r * 32 + (lane ^ r)];
+          }
+        }
+      } else if (row_ok) {
+        if (out_bf16) {
+          __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out) + (long long)m * ld + n0;
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            uint4 u;
+            u.x = pack_bf16(v[j], v[j + 1]);
+            u.y = pack_bf16(v[j + 2], v[j + 3]);
+            u.z = pack_bf16(v[j + 4], v[j + 5]);
+            u.w = pack_bf16(v[j + 6], v[j + 7]);
+            *reinterpret_cast<uint4*>(o + j) = u;
           }
         } else {
           float* o = reinterpret_cast<float*>(out) + (long long)m * ld + n0;
-          if (nv == 32 && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-          } else {
-            for (int j = 0; j < nv; ++j) o[j] = v[j];
-          }
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
         }
       }
     }
@@ -1006,14 +1028,17 @@ conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
     // ------------------------------------------------------------ epilogue: 128 threads, one accumulator row each
     if (kb_end > kb_begin) {
       const int q = warp & 3;
-      const int row = q * 32 + lane;
       mbar_wait(tfull, 0);
       tc_fence_after();
+      // tfull fires after the last MMA has read shared memory and every TMA load has landed: the operand ring is idle
+      // and serves as the transpose staging (one 32 x 32 fp32 block per warp, see EpiStore), so that each atomic
+      // instruction adds 32 consecutive floats of one dW row instead of one float in each of 32 rows.
+      float* stage = reinterpret_cast<float*>(smem) + q * 1024;
 #pragma unroll 1
       for (int p = 0; p < 5; ++p) {
-        const int tap = 2 * p + (row >> 6);
-        const bool keep = p < 4 || row < 64;  // the second half of the last pair is a copy of tap 8
-        float* o = a.dw + ((long long)tap * a.Cin + c_chunk * 64 + (row & 63)) * a.Cout + n_chunk * 64;
+        const int tap = 2 * p + (q >> 1);
+        const bool keep = p < 4 || q < 2;  // the second half of the last pair is a copy of tap 8 (warp-uniform)
+        float* o = a.dw + ((long long)tap * a.Cin + c_chunk * 64 + (q & 1) * 32) * a.Cout + n_chunk * 64 + lane;
 #pragma unroll 1
         for (int c = 0; c < 64; c += 32) {
           float v[32];
@@ -1022,7 +1047,10 @@ conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
           tmem_ld_wait();
           if (keep) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) atomicAdd(o + c + j, v[j]);
+            for (int j = 0; j < 32; ++j) stage[lane * 32 + (j ^ lane)] = v[j];
+            __syncwarp();
+#pragma unroll 4
+            for (int r = 0; r < 32; ++r) atomicAdd(o + (long long)r * a.Cout + c, stage[r * 32 + (lane ^ r)]);
           }
         }
       }
