@@ -378,12 +378,34 @@ __global__ void k_sample_z(const float* __restrict__ mu, const float* __restrict
     }
   }
 }
+// Same for N*Z % 4 == 0 and 16-byte aligned operands: grid.y = s, one thread per quad of [N*Z] (the Philox quad index
+// s * NZ/4 + q is the one k_sample_z and k_dz_reduce use), float4 loads of mu / sd / eps, one 8-byte store of 4 bf16.
+__global__ void k_sample_z_v4(const float4* __restrict__ mu, const float4* __restrict__ sd, const float4* __restrict__ eps,
+                              unsigned long long seed, unsigned long long offset, uint2* __restrict__ z,
+                              float4* __restrict__ z_f32, long long NZ4) {
+  const long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (q >= NZ4) return;
+  const long long quad = (long long)blockIdx.y * NZ4 + q;
+  const float4 e = eps != nullptr ? eps[quad] : philox_normal4(seed, offset, quad);
+  const float4 m = __ldg(mu + q), d = __ldg(sd + q);
+  const float4 v = make_float4(fmaf(d.x, e.x, m.x), fmaf(d.y, e.y, m.y), fmaf(d.z, e.z, m.z), fmaf(d.w, e.w, m.w));
+  z[quad] = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+  if (z_f32 != nullptr) z_f32[quad] = v;
+}
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 int sample_z(cudaStream_t s, const float* mu, const float* sd, const float* eps, unsigned long long seed,
              unsigned long long offset, void* z, float* z_f32, int S, long long NZ) {
   {
     ProfScope ps(s, "sample_z");
-    k_sample_z<<<grid_for(((long long)S * NZ + 3) / 4, 256), 256, 0, s>>>(mu, sd, eps, seed, offset, (__nv_bfloat16*)z, z_f32,
-                                                                          S, NZ);
+    if (NZ % 4 == 0 && S <= 65535 && aligned16(mu) && aligned16(sd) && aligned16(eps) && aligned16(z) && aligned16(z_f32)) {
+      const long long nz4 = NZ / 4;
+      dim3 grid((unsigned)((nz4 + 255) / 256), (unsigned)S);
+      k_sample_z_v4<<<grid, 256, 0, s>>>((const float4*)mu, (const float4*)sd, (const float4*)eps, seed, offset, (uint2*)z,
+                                         (float4*)z_f32, nz4);
+    } else {
+      k_sample_z<<<grid_for(((long long)S * NZ + 3) / 4, 256), 256, 0, s>>>(mu, sd, eps, seed, offset, (__nv_bfloat16*)z,
+                                                                            z_f32, S, NZ);
+    }
   }
   VC_CUDA(cudaGetLastError());
   return VC_OK;
@@ -435,6 +457,56 @@ __global__ void k_dz_reduce(const float* __restrict__ dz, const float* __restric
     }
   }
 }
+// Same for N*Z % 4 == 0 and 16-byte aligned dz / eps: the sum over the S samples is split over the four warps of a
+// CTA (warp w takes s = w, w+4, ...; 32 lanes = 32 consecutive quads, 512 contiguous bytes per load instruction) and
+// folded through shared memory in a fixed order, so the result does not depend on scheduling.
+__global__ void __launch_bounds__(128)
+k_dz_reduce_v4(const float4* __restrict__ dz, const float4* __restrict__ eps, unsigned long long seed,
+               unsigned long long offset, const float* __restrict__ sd, const float* __restrict__ dkl_dmu,
+               const float* __restrict__ dkl_dsd, float kl_scale, __nv_bfloat16* __restrict__ dheads, long long ld, int zp,
+               float* __restrict__ dmu_out, float* __restrict__ dsd_out, int S, long long NZ4, int Z) {
+  __shared__ float4 part[2][3][32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const long long q = blockIdx.x * 32ll + lane;
+  float4 am = make_float4(0.f, 0.f, 0.f, 0.f), as = am;
+  if (q < NZ4) {
+#pragma unroll 2
+    for (int s = w; s < S; s += 4) {
+      const long long quad = (long long)s * NZ4 + q;
+      const float4 g = dz[quad];
+      const float4 e = eps != nullptr ? eps[quad] : philox_normal4(seed, offset, quad);
+      am.x += g.x; am.y += g.y; am.z += g.z; am.w += g.w;
+      as.x = fmaf(g.x, e.x, as.x); as.y = fmaf(g.y, e.y, as.y); as.z = fmaf(g.z, e.z, as.z); as.w = fmaf(g.w, e.w, as.w);
+    }
+  }
+  if (w > 0) {
+    part[0][w - 1][lane] = am;
+    part[1][w - 1][lane] = as;
+  }
+  __syncthreads();
+  if (w != 0 || q >= NZ4) return;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const float4 a = part[0][k][lane], b = part[1][k][lane];
+    am.x += a.x; am.y += a.y; am.z += a.z; am.w += a.w;
+    as.x += b.x; as.y += b.y; as.z += b.z; as.w += b.w;
+  }
+  const float m4[4] = {am.x, am.y, am.z, am.w}, s4[4] = {as.x, as.y, as.z, as.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const long long r = q * 4 + j;
+    const float gm = m4[j] + kl_scale * dkl_dmu[r];
+    const float gs = s4[j] + kl_scale * dkl_dsd[r];
+    if (dheads) {
+      const long long n = r / Z;
+      const int k = (int)(r - n * Z);
+      dheads[n * ld + k] = __float2bfloat16(gm);
+      dheads[n * ld + zp + k] = __float2bfloat16(gs * sd[r]);
+    }
+    if (dmu_out) dmu_out[r] = gm;
+    if (dsd_out) dsd_out[r] = gs;
+  }
+}
 int dz_reduce(cudaStream_t s, const float* dz, const float* eps, unsigned long long seed, unsigned long long offset,
               const float* sd, const float* dkl_dmu, const float* dkl_dsd, float kl_scale, void* dheads, long long ld,
               int zp, float* dmu_out, float* dsd_out, int S, int N, int Z) {
@@ -442,9 +514,16 @@ int dz_reduce(cudaStream_t s, const float* dz, const float* eps, unsigned long l
     return set_error(VC_E_SHAPE, "Philox sampling needs N*Z to be a multiple of 4");
   {
     ProfScope ps(s, "dz_reduce");
-    k_dz_reduce<<<grid_for(((long long)N * Z + 3) / 4, 128), 128, 0, s>>>(dz, eps, seed, offset, sd, dkl_dmu, dkl_dsd, kl_scale,
-                                                                         (__nv_bfloat16*)dheads, ld, zp, dmu_out, dsd_out,
-                                                                         S, N, Z);
+    const long long NZ = (long long)N * Z;
+    if (NZ % 4 == 0 && aligned16(dz) && aligned16(eps)) {
+      const long long nz4 = NZ / 4;
+      k_dz_reduce_v4<<<(unsigned)((nz4 + 31) / 32), 128, 0, s>>>((const float4*)dz, (const float4*)eps, seed, offset, sd,
+                                                                 dkl_dmu, dkl_dsd, kl_scale, (__nv_bfloat16*)dheads, ld, zp,
+                                                                 dmu_out, dsd_out, S, nz4, Z);
+    } else {
+      k_dz_reduce<<<grid_for((NZ + 3) / 4, 128), 128, 0, s>>>(dz, eps, seed, offset, sd, dkl_dmu, dkl_dsd, kl_scale,
+                                                              (__nv_bfloat16*)dheads, ld, zp, dmu_out, dsd_out, S, N, Z);
+    }
   }
   VC_CUDA(cudaGetLastError());
   return VC_OK;
