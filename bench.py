@@ -88,6 +88,9 @@ def family_work(p, B, has_enc=True):
         "sample_z": ("hbm", S * N * Z * 2.0 + 2 * N * Z * 4.0),
         "dz_reduce": ("hbm", S * N * Z * 4.0),
     }
+    # the whole-sequence LSTM kernels run every step's 4-gate GEMM in one launch: same algorithmic FLOPs
+    w["lstm_fwd_seq"] = w["lstm_fwd_step"]
+    w["lstm_bwd_seq"] = w["lstm_bwd_step"]
     names = ["conv1_1", "conv1_2", "conv2_1", "conv2_2", "conv3_1", "conv3_2", "conv3_3", "conv4_1", "conv4_2", "conv4_3",
              "conv5_1", "conv5_2", "conv5_3"]
     for nm, (hw, ci, co) in zip(names, VGG):
@@ -525,6 +528,7 @@ def main():
 
     # per-kernel-family timing with CUDA events on the launching stream (extra steps after the timed region)
     roofline = None
+    lstm_roofline = None
     families = {}
     if rank == 0 and world == 1 and not args.no_profile:  # extra steps on one rank only would strand its all-reduce
         peaks = {}
@@ -563,6 +567,17 @@ def main():
                 families[agg] = {"ms_per_step": ms_c, "launches_per_step": sum(families[k]["launches_per_step"] for k in parts),
                                  "bound": "tensor", "achieved": work[agg][1] / (ms_c / 1e3) / 1e12}
                 layer_fams += parts
+        # the LSTM 4-gate GEMMs as one group (north_star: "achieved fraction of the LSTM-GEMM roofline"): recurrence
+        # forward + backward, weight gradient and input gradient over the time spent in those kernels
+        lstm_parts = [k for k in ("lstm_fwd_seq", "lstm_fwd_step", "lstm_bwd_seq", "lstm_bwd_step", "lstm_wgrad", "lstm_dx")
+                      if k in families and k in work]
+        lstm_roofline = None
+        if lstm_parts:
+            ms_l = sum(families[k]["ms_per_step"] for k in lstm_parts)
+            fl = sum(work[k][1] for k in lstm_parts)
+            pk = peaks.get("bf16_tflops_sustained", 1590.0)
+            lstm_roofline = {"kernels": lstm_parts, "bound": "tensor", "achieved": fl / (ms_l / 1e3) / 1e12, "peak": pk,
+                             "unit": "TFLOP/s", "frac": fl / (ms_l / 1e3) / 1e12 / pk, "ms_per_step": ms_l}
         if families:
             top = max((k for k in families if k not in layer_fams), key=lambda k: families[k]["ms_per_step"])
             f = families[top]
@@ -609,8 +624,8 @@ def main():
                            "l2_policy": "per-step working set (>= 0.6 GB logits + 80 MB weights/optimizer state) exceeds the 126 MB L2"},
                 "e2e": {"value": e2e_val, "unit": "captions/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 64,
                         "ms_per_step": ms_e2e / args.steps, "last_step": last},
-                "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
-                "serial_ms_per_step": (ms_serial / args.steps) if ms_serial else None,
+                "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "lstm_roofline": lstm_roofline,
+                "cpu_baseline": cpu_baseline, "serial_ms_per_step": (ms_serial / args.steps) if ms_serial else None,
                 "step_tflops": tf, "step_tensor_frac": (tf / world / peaks_tf) if peaks_tf else None,
                 "families": families}
         emit(line)
