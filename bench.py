@@ -588,8 +588,9 @@ def main():
                 if peak is None:
                     peak, src = (1590.0 if tensor else 6650.0), "fallback"
                 traffic = None
-                try:
-                    traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(top)
+                try:  # profiles/traffic.json holds ncu DRAM bytes per launch of the DEFAULT workload only
+                    if args.workload == DEFAULT_WORKLOAD:
+                        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(top)
                 except Exception:
                     pass
                 roofline = {"kernel": top, "bound": f["bound"], "achieved": f["achieved"], "peak": peak,
