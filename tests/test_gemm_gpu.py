@@ -10,7 +10,7 @@ from vae_captioning_b200 import lib as L
 pytestmark = pytest.mark.gpu
 
 
-def run_gemm(M, N, K, a_mn, b_mn, bn, splits=1, relu=0, out_bf16=0, bias=True, seed=0):
+def run_gemm(M, N, K, a_mn, b_mn, bn, splits=1, relu=0, out_bf16=0, bias=True, seed=0, ldo=None, force_atomic=False):
     lib = L.load()
     g = torch.Generator(device="cpu").manual_seed(seed)
     # pitches padded to 8 elements so rows are 16-byte aligned
@@ -29,8 +29,8 @@ def run_gemm(M, N, K, a_mn, b_mn, bn, splits=1, relu=0, out_bf16=0, bias=True, s
     A_d = A_buf.to(torch.bfloat16).cuda()
     B_d = B_buf.to(torch.bfloat16).cuda()
     bias_d = torch.randn(N, generator=g).cuda() if bias else None
-    ldo = pad8(N)
-    atomic = 1 if splits > 1 else 0
+    ldo = pad8(N) if ldo is None else ldo
+    atomic = 1 if (splits > 1 or force_atomic) else 0
     out = torch.zeros(M, ldo, dtype=torch.bfloat16 if out_bf16 else torch.float32, device="cuda")
     st = lib.vc_gemm_bf16(L.ptr(A_d), a_mn, ctypes.c_longlong(lda), L.ptr(B_d), b_mn, ctypes.c_longlong(ldb),
                           L.ptr(out), ctypes.c_longlong(ldo), L.ptr(bias_d), M, N, K, bn, splits, relu, out_bf16,
@@ -86,3 +86,20 @@ def test_gemm_many_tiles_persistent():
     # more tiles than SMs: exercises the persistent loop, the smem ring wrap and the TMEM double buffer
     run_gemm(4096, 2048, 192, 0, 0, 64)
     run_gemm(2048, 4096, 1024, 0, 0, 256)
+
+
+@pytest.mark.parametrize("out_bf16", [0, 1])
+def test_gemm_unaligned_output_pitch(out_bf16):
+    # an output pitch that is not a multiple of 16 bytes (the vocab-projection weight gradient is [H, V] with V = 11313):
+    # rows cannot take vector stores, the epilogue transposes the block through shared memory and writes row segments
+    run_gemm(300, 203, 320, 0, 0, 64, out_bf16=out_bf16, ldo=203)
+    run_gemm(130, 77, 192, 1, 1, 64, out_bf16=out_bf16, ldo=81)
+    run_gemm(257, 333, 128, 0, 0, 256, out_bf16=out_bf16, ldo=333)
+
+
+def test_gemm_splitk_ragged_atomic():
+    # split-K partial sums meet in coalesced fp32 atomics: ragged rows (M % 32 != 0), ragged columns, odd pitch
+    run_gemm(203, 301, 2048, 0, 0, 64, splits=5, ldo=301)
+    run_gemm(70, 45, 4096, 1, 1, 64, splits=8, bias=False, ldo=45)
+    run_gemm(512, 1000, 1536, 1, 1, 256, splits=3, ldo=1001)
+    run_gemm(97, 130, 256, 0, 0, 128, force_atomic=True)
