@@ -47,3 +47,23 @@ def test_native_arm_refuses_to_run_on_cpu():
     r = run(["--gpus", "1", "--steps", "1", "--warmup", "1"])
     assert r.returncode != 0
     assert "no CPU fallback" in (r.stderr + r.stdout)
+
+
+def test_algorithmic_work_matches_the_survey():
+    """The FLOP / byte counts behind `roofline.achieved` are SURVEY 8(d)'s per-unit figures times the units of a cfg 2 step."""
+    sys.path.insert(0, ROOT)
+    import bench as B
+    w = B.WORKLOADS[B.DEFAULT_WORKLOAD]
+    p = B.params_for(w)
+    work = B.family_work(p, w["B"])
+    n_img, n_cap = w["B"], w["B"] * B.C
+    assert abs(work["conv"][1] / n_img - 30.69e9) < 0.05e9              # 13 convolutions of VGG16, forward, per image
+    assert abs((work["conv"][1] + work["fc"][1]) / n_img - 30.932e9) < 0.01e9
+    assert abs(work["logits_fwd"][1] / n_cap - 231.69e6) < 0.01e6       # 11.5845 MFLOP x 20 tokens
+    assert abs(work["z_rnn"][1] / n_cap - 7.68e6) < 1e3
+    assert abs(work["lstm_fwd_step"][1] / n_cap - 135.3e6) < 0.1e6      # 3.1457 MFLOP x (21 encoder + 22 decoder steps)
+    assert work["lstm_fwd_seq"] == work["lstm_fwd_step"] and work["lstm_bwd_seq"] == work["lstm_bwd_step"]
+    assert abs(work["adam"][1] / 28 - 19.79e6) < 0.01e6                 # 19.79 M non-CNN parameters, 28 B each
+    assert abs(work["ce"][1] / (n_cap * B.T) - 2 * 2 * B.V) < 1         # bf16 logits read once, dlogits written once
+    # whole step, Normal prior, frozen VGG16 forward: 1.131 GFLOP per caption + 30.932 GFLOP per image
+    assert abs(B.total_flops(p, w["B"], True) - (n_cap * 1.131e9 + n_img * 30.932e9)) < 0.005 * n_img * 30.932e9
