@@ -12,6 +12,8 @@
  *    copies asynchronous). The caller owns every I/O buffer; the handle owns parameters, optimiser
  *    state and the activation workspace (sized at vc_create from max_batch / max_len).
  *  - `stream` is a cudaStream_t passed as void*. Calls on one handle are not re-entrant.
+ *  - one process drives ONE GPU (one rank per GPU under torchrun, as the data-parallel path does): per-kernel launch
+ *    attributes and the SM count are cached per process, so handles on different devices of one process are unsupported.
  *  - all floating-point I/O is fp32 in TensorFlow layouts (dense kernels [in,out], conv HWIO,
  *    LSTM kernel [x;h] x [i|j|f|o]); token ids and lengths are int32.
  */
