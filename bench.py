@@ -56,12 +56,14 @@ VGG = [(224, 3, 64), (224, 64, 64), (112, 64, 128), (112, 128, 128), (56, 128, 2
        (28, 256, 512), (28, 512, 512), (28, 512, 512), (14, 512, 512), (14, 512, 512), (14, 512, 512)]
 
 
-def family_work(p, B, has_enc=True):
+def family_work(p, B, has_enc=True, n_params=None):
     N, E, He, Hd, Z, S, F = B * C, p.embed_size, p.encoder_hidden, p.decoder_hidden, p.latent_size, p.gen_z_samples, 4096
     cv = 1 if p.use_c_v else 0
     enc_steps, dec_steps = T + 1 + cv, T + 2 + cv
     n_adam = (F * E + E + (E + He) * 4 * He + 4 * He + 2 * (He * Z + Z) + (E + Hd) * 4 * Hd + 4 * Hd + Z * S * E + E +
               Hd * V + V + 2 * V * E)
+    if n_params is not None:  # every variable an optimiser updates (GMM / AG heads, cv_emb, the cnn/ scope when fine-tuning)
+        n_adam = n_params
     w = {
         "conv": ("tensor", sum(2.0 * hw * hw * 9 * ci * co for hw, ci, co in VGG) * B),
         "fc": ("tensor", 2.0 * B * (25088 * 4096 + 4096 * 4096)),
@@ -340,56 +342,38 @@ def emit(line):
         os.write(_REAL_STDOUT, data)
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
-    ap.add_argument("--ref-batch", type=int, default=32, help="images per step of the bounded CPU sample")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-profile", action="store_true")
-    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (used under ncu only)")
-    args = ap.parse_args()
-    quiet_stdout()
-    w = WORKLOADS[args.workload]
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+def _crc_state(eng):
+    """crc32 over every variable of the handle (host copy): equal on all ranks iff the replicas stayed in lock step."""
+    import zlib
+    crc = 0
+    for name, _, _ in eng.variables():
+        crc = zlib.crc32(eng.get_variable(name).tobytes(), crc)
+    return crc
 
-    if args.impl == "reference":
-        if rank == 0:
-            fn = run_decode_reference if w.get("decode") else run_reference
-            emit(fn(args, w, args.workload))
-        return 0
-    if w.get("decode"):
-        import torch
-        if not torch.cuda.is_available():
-            raise SystemExit("bench.py: no CUDA device -- the hot path has no CPU fallback")
-        return run_decode(args, w, args.workload, rank, world, local_rank)
 
+def run_train(args, name, rank, world, local_rank, steps, warmup, full):
+    """One workload through the CUDA path: device-resident leg (`value`), host-buffer leg (`e2e`), at world > 1 the
+    all-reduce accounting and the replica check; with `full` also the per-kernel-family roofline legs and the CPU
+    baseline. Returns the JSON line (rank 0) or None."""
     import torch
     import torch.distributed as dist
     from vae_captioning_b200 import lib as L
     from vae_captioning_b200.engine import Engine
     from vae_captioning_b200 import synthetic
 
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device -- the hot path has no CPU fallback")
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    w = WORKLOADS[name]
     lib = L.load()
     lib.vc_launch_count.restype = ctypes.c_ulonglong
-
     p = params_for(w)
     B = w["B"]
     N = B * C
     eng = Engine(p, vocab_size=V, max_batch=B, max_len=T, device=local_rank, with_cnn=w["vgg"])
     eng.load_state(synthetic.init_weights(eng.variables(), seed=1))
+    n_params = sum(int(np.prod(sh)) for _, sh, tr in eng.variables() if tr)
     if w["prior"] == "AG":  # init_clusters (utils/vae_utils.py:6-31): seeded stand-in for ./pickles/cluster_means.pickle
         eng.set_cluster_means(np.random.Generator(np.random.PCG64(2)).standard_normal((90, p.latent_size)).astype(np.float32))
+    if world > 1:  # the handle's own NCCL communicator: bucketed all-reduce inside every train step (include/vaecap.h)
+        eng.attach_comm(rank, world)
     feed = synthetic.make_batch(B, C, T, V, seed=rank, images=w["vgg"], cluster_vectors=w["c_v"] or w["prior"] != "Normal")
 
     # pinned host buffers (e2e leg) and device-resident copies (value leg)
@@ -398,10 +382,6 @@ def main():
     if w["vgg"]:  # the e2e leg feeds the pixels as uint8, the dtype of the reference's HDF5 image store (batch_gen.py:278-294)
         host["image_f_inputs"] = torch.from_numpy(feed["image_f_inputs"].astype(np.uint8)).pin_memory()
     torch.cuda.synchronize()
-    grad_ptr, grad_n = eng.grad_buffer()
-    grad_t = None
-    if world > 1:
-        grad_t = L.alias_tensor(grad_ptr, grad_n, torch.float32, local_rank)
 
     step_no = [0]
     e2e_primed = []
@@ -436,58 +416,38 @@ def main():
             main.wait_event(fc2_ready[i & 1])
             feats = fc2_buf[i & 1]
             vgg_ahead(i + 1)
-        if world == 1:
-            eng.train_step_device(feats, dev["ann_inputs_enc"], dev["ann_inputs_dec"], dev["ann_lengths"], step_no[0],
-                                  c_i=dev.get("c_i"), rng={"seed": 1234}, fetch=False)
-        else:
-            eng.forward_backward_device(feats, dev["ann_inputs_enc"], dev["ann_inputs_dec"], dev["ann_lengths"],
-                                        step_no[0], c_i=dev.get("c_i"), rng={"seed": 1234 + rank})
-            dist.all_reduce(grad_t)
-            eng.apply_gradients(1.0 / world, fetch=False)
+        # at world > 1 this same call all-reduces the gradient buckets under the backward pass and applies the mean
+        eng.train_step_device(feats, dev["ann_inputs_enc"], dev["ann_inputs_dec"], dev["ann_lengths"], step_no[0],
+                              c_i=dev.get("c_i"), rng={"seed": 1234 + rank}, fetch=False)
         if pipelined and not serial:
             fc2_free[step_no[0] & 1].record(torch.cuda.current_stream())
         step_no[0] += 1
 
     def step_e2e():
-        # public API with HOST buffers: H2D of the step's inputs and D2H of the loss inside the timed region
-        if world == 1:
-            # double-buffered feed (vc_stage_batch / vc_train_step_staged): every call copies ONE batch from pinned host
-            # memory (the next step's, on the copy stream, overlapping this step's compute) and runs ONE step whose
-            # scalars are read back; the first batch is staged by the untimed warm-up calls
-            i = step_no[0]
-            stage = lambda slot: eng.stage_batch(slot, host["image_f_inputs"].numpy(), host["ann_inputs_enc"].numpy(),
-                                                 host["ann_inputs_dec"].numpy(), host["ann_lengths"].numpy(),
-                                                 c_i=host["c_i"].numpy() if "c_i" in host else None,
-                                                 images=w["vgg"] and not w.get("fine_tune"))
-            if not e2e_primed:
-                stage(i & 1)
-                e2e_primed.append(True)
-            stage((i + 1) & 1)
-            out = eng.train_step_staged(i & 1, i, rng={"seed": 1234})
-        else:
-            # same double-buffered feed per rank; the gradient all-reduce sits between the two halves of the step
-            i = step_no[0]
-            stage = lambda slot: eng.stage_batch(slot, host["image_f_inputs"].numpy(), host["ann_inputs_enc"].numpy(),
-                                                 host["ann_inputs_dec"].numpy(), host["ann_lengths"].numpy(),
-                                                 c_i=host["c_i"].numpy() if "c_i" in host else None,
-                                                 images=w["vgg"] and not w.get("fine_tune"))
-            if not e2e_primed:
-                stage(i & 1)
-                e2e_primed.append(True)
-            stage((i + 1) & 1)
-            eng.forward_backward_staged(i & 1, i, rng={"seed": 1234 + rank})
-            dist.all_reduce(grad_t)
-            out = eng.apply_gradients(1.0 / world, fetch=True)
+        # public API with HOST buffers: H2D of the step's inputs and D2H of the loss inside the timed region.
+        # Double-buffered feed (vc_stage_batch / vc_train_step_staged): every call copies ONE batch from pinned host
+        # memory (the next step's, on the copy stream, overlapping this step's compute) and runs ONE step whose
+        # scalars are read back; the first batch is staged by the untimed warm-up calls
+        i = step_no[0]
+        stage = lambda slot: eng.stage_batch(slot, host["image_f_inputs"].numpy(), host["ann_inputs_enc"].numpy(),
+                                             host["ann_inputs_dec"].numpy(), host["ann_lengths"].numpy(),
+                                             c_i=host["c_i"].numpy() if "c_i" in host else None,
+                                             images=w["vgg"] and not w.get("fine_tune"))
+        if not e2e_primed:
+            stage(i & 1)
+            e2e_primed.append(True)
+        stage((i + 1) & 1)
+        out = eng.train_step_staged(i & 1, i, rng={"seed": 1234 + rank})
         step_no[0] += 1
         return out
 
-    def timed(fn, steps):
+    def timed(fn, k):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(steps):
+        for _ in range(k):
             fn()
         if side is not None:
             torch.cuda.current_stream().wait_stream(side)  # the look-ahead forward of the last step is inside the region
@@ -501,36 +461,65 @@ def main():
             ms = float(t.item())
         return ms
 
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(max(warmup, 3)):
         step_device()
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
     l0 = lib.vc_launch_count()
-    ms = timed(step_device, args.steps)
+    ms = timed(step_device, steps)
     launches = int(lib.vc_launch_count() - l0)
     clocks = sampler.stop() if sampler else None
-    value = world * N * args.steps / (ms / 1e3)
+    value = world * N * steps / (ms / 1e3)
+    comm = eng.comm_stats() if world > 1 else None
     ms_serial = None
-    if pipelined:  # the same K steps on one stream, for the record (explains what the overlap buys)
+    if pipelined and full:  # the same K steps on one stream, for the record (explains what the overlap buys)
         torch.cuda.synchronize()
         fc2_primed.clear()
-        ms_serial = timed(lambda: step_device(serial=True), args.steps)
+        ms_serial = timed(lambda: step_device(serial=True), steps)
 
     # e2e leg
     last, ms_e2e, e2e_val = None, float("nan"), None
     if not args.no_e2e:
         for _ in range(2):
             last = step_e2e()
-        ms_e2e = timed(step_e2e, args.steps)
-        e2e_val = world * N * args.steps / (ms_e2e / 1e3)
+        ms_e2e = timed(step_e2e, steps)
+        e2e_val = world * N * steps / (ms_e2e / 1e3)
     h2d = sum(v.numel() * v.element_size() for v in host.values())
+
+    # data-parallel correctness and what the collective costs (world > 1)
+    dp_check, allreduce, loss_mean = None, None, None
+    if world > 1:
+        torch.cuda.synchronize()
+        crcs = [None] * world
+        dist.all_gather_object(crcs, _crc_state(eng))
+        dp_check = "ok" if len(set(crcs)) == 1 else "MISMATCH %s" % (crcs,)
+        if last is not None:  # every rank reports its tower's loss; the job's loss is their mean
+            losses = [None] * world
+            dist.all_gather_object(losses, float(last["rec_loss"]))
+            loss_mean = float(np.mean(losses))
+        k2 = max(3, min(steps, 10))
+        fc2_primed.clear()
+        eng.comm_set_mode(2)  # one all-reduce of the whole buffer behind the backward pass (round 1's schedule)
+        for _ in range(2):
+            step_device()
+        ms_m2 = timed(step_device, k2) / k2
+        eng.comm_set_mode(0)  # no reduction at all: the ranks diverge from here on, timing only (last leg)
+        for _ in range(2):
+            step_device()
+        ms_m0 = timed(step_device, k2) / k2
+        eng.comm_set_mode(1)
+        allreduce = {"bytes": comm["bytes"], "buckets": comm["buckets"], "span_ms": comm["span_ms"],
+                     "exposed_ms": ms / steps - ms_m0, "exposed_ms_unbucketed": ms_m2 - ms_m0,
+                     "ms_per_step_no_allreduce": ms_m0, "ms_per_step_unbucketed": ms_m2, "transport": "fp32",
+                     "note": "span = first bucket start to last bucket end on the communication stream of the last timed "
+                             "step; exposed = step time minus the same step with the reduction switched off"}
 
     # per-kernel-family timing with CUDA events on the launching stream (extra steps after the timed region)
     roofline = None
     lstm_roofline = None
     families = {}
-    if rank == 0 and world == 1 and not args.no_profile:  # extra steps on one rank only would strand its all-reduce
+    if full and rank == 0 and world == 1 and not args.no_profile:  # extra steps on one rank only would strand its all-reduce
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -548,7 +537,7 @@ def main():
         n = lib.vc_profile_collect(names, 8192, msb, cnt, 256)
         lib.vc_profile_enable(0)
         fam_names = names.value.decode().split(",") if n else []
-        work = family_work(p, B)
+        work = family_work(p, B, n_params=n_params)
         for i, fn in enumerate(fam_names):
             families[fn] = {"ms_per_step": msb[i] / psteps, "launches_per_step": cnt[i] / psteps}
             if fn in work:
@@ -589,7 +578,7 @@ def main():
                     peak, src = (1590.0 if tensor else 6650.0), "fallback"
                 traffic = None
                 try:  # profiles/traffic.json holds ncu DRAM bytes per launch of the DEFAULT workload only
-                    if args.workload == DEFAULT_WORKLOAD:
+                    if name == DEFAULT_WORKLOAD:
                         traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(top)
                 except Exception:
                     pass
@@ -600,39 +589,112 @@ def main():
                                                                       if k not in layer_fams)}
 
     cpu_baseline = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if full and rank == 0 and world == 1 and not args.no_cpu_baseline:
         ra = argparse.Namespace(**vars(args))
         ra.steps, ra.warmup = 3, 1
-        r = run_reference(ra, w, args.workload)
+        r = run_reference(ra, w, name)
         cpu_baseline = r["cpu_baseline"]
 
+    line = None
     if rank == 0:
         peaks_tf = None
         try:
             peaks_tf = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("bf16_tflops_sustained")
         except Exception:
             pass
-        tf = total_flops(p, B, w["vgg"]) * world / (ms / args.steps / 1e3) / 1e12
+        tf = total_flops(p, B, w["vgg"]) * world / (ms / steps / 1e3) / 1e12
         line = {"metric": "captions/sec (ELBO train step)", "value": value, "unit": "captions/s", "n_gpus": world,
-                "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
+                "steps": steps, "warmup": max(warmup, 3), "ms_per_step": ms / steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-                "config": {"workload": args.workload, "images_per_step_per_gpu": B, "captions_per_step_per_gpu": N,
+                "config": {"workload": name, "images_per_step_per_gpu": B, "captions_per_step_per_gpu": N,
                            "seq_len": T, "vocab": V, "prior": w["prior"], "on_device_vgg16_forward": w["vgg"],
                            "fine_tune": bool(w.get("fine_tune")), "c_v": w["c_v"],
                            "parallelism": "dp%d" % world,
                            "pipeline": ("frozen VGG16 forward of batch i+1 on a second stream overlaps the caption-model "
                                         "step of batch i (one forward and one step per timed step)") if pipelined else "none",
-                           "l2_policy": "per-step working set (>= 0.6 GB logits + 80 MB weights/optimizer state) exceeds the 126 MB L2"},
+                           "l2_policy": "per-step working set (>= 0.3 GB logits + 80 MB weights/optimizer state) exceeds the 126 MB L2"},
                 "e2e": {"value": e2e_val, "unit": "captions/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 64,
-                        "ms_per_step": ms_e2e / args.steps, "last_step": last},
-                "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "lstm_roofline": lstm_roofline,
-                "cpu_baseline": cpu_baseline, "serial_ms_per_step": (ms_serial / args.steps) if ms_serial else None,
-                "step_tflops": tf, "step_tensor_frac": (tf / world / peaks_tf) if peaks_tf else None,
-                "families": families}
+                        "ms_per_step": ms_e2e / steps, "last_step": last},
+                "gpu_launches": launches, "clocks": clocks, "step_tflops": tf,
+                "step_tensor_frac": (tf / world / peaks_tf) if peaks_tf else None}
+        if world > 1:
+            line.update(allreduce=allreduce, dp_check=dp_check, rec_loss_mean_over_ranks=loss_mean)
+        if full:
+            line.update(roofline=roofline, lstm_roofline=lstm_roofline, cpu_baseline=cpu_baseline,
+                        serial_ms_per_step=(ms_serial / steps) if ms_serial else None, families=families)
+    eng.close()
+    del dev, host
+    torch.cuda.empty_cache()
+    return line
+
+
+# BASELINE.json configs[2] / configs[3] ride along with the headline workload at every N: their
+# per-GPU shapes, fewer steps, reported under the line's `configs` key
+EXTRA_CONFIGS = ("cfg3_feats_gmm_cv_b128", "cfg4_finetune_ag_cv_b256")
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument("--ref-batch", type=int, default=32, help="images per step of the bounded CPU sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-profile", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (used under ncu only)")
+    ap.add_argument("--no-extra-configs", action="store_true",
+                    help="default workload only: do not also time BASELINE configs 3 and 4 (`configs` key)")
+    args = ap.parse_args()
+    quiet_stdout()
+    w = WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        if rank == 0:
+            fn = run_decode_reference if w.get("decode") else run_reference
+            emit(fn(args, w, args.workload))
+        return 0
+    if w.get("decode"):
+        import torch
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device -- the hot path has no CPU fallback")
+        return run_decode(args, w, args.workload, rank, world, local_rank)
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the hot path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    line = run_train(args, args.workload, rank, world, local_rank, args.steps, args.warmup, full=True)
+    if args.workload == DEFAULT_WORKLOAD and not args.no_extra_configs and not args.no_e2e:
+        extra = {}
+        for name in EXTRA_CONFIGS:
+            try:
+                sub = run_train(args, name, rank, world, local_rank, max(3, min(args.steps, 10)), 3, full=False)
+            except Exception as e:  # the headline line must survive a failing side workload
+                sub = {"error": "%s: %s" % (type(e).__name__, e)}
+                if world > 1:
+                    raise
+            if rank == 0:
+                keep = ("value", "unit", "ms_per_step", "steps", "e2e", "allreduce", "dp_check", "rec_loss_mean_over_ranks",
+                        "step_tflops", "step_tensor_frac", "gpu_launches", "error")
+                extra[name] = {k: sub[k] for k in keep if k in sub}
+                if "config" in sub:
+                    extra[name]["config"] = {k: sub["config"][k] for k in ("images_per_step_per_gpu", "captions_per_step_per_gpu",
+                                                                          "prior", "fine_tune", "c_v", "parallelism")}
+        if rank == 0:
+            line["configs"] = extra
+    if rank == 0:
         emit(line)
     if world > 1:
         dist.destroy_process_group()
-    eng.close()
     return 0
 
 

@@ -157,6 +157,29 @@ int vc_forward_backward_dev(vc_handle* h, const float* feats_dev, const int32_t*
 int vc_grad_buffer(vc_handle* h, float** dev_ptr, int64_t* count);
 int vc_apply_gradients(vc_handle* h, float grad_scale, vc_step_out* out, void* stream);
 
+/* ---- data parallelism (no reference counterpart: the reference is single-device, utils/parameters.py:163-164; the
+ * step shards by minibatch). One process per GPU. Rank 0 obtains a 128-byte NCCL unique id with
+ * vc_comm_unique_id and hands it to the other ranks by any means (the Python side broadcasts it with
+ * torch.distributed); every rank then calls vc_comm_init(handle, id, rank, world) -- collective, creates the handle's
+ * communicator over NVLink / NVSwitch. From then on EVERY train-step entry point above (vc_train_step*,
+ * vc_train_step_staged, vc_train_step_dev) is the data-parallel step: the backward pass hands each group of gradients
+ * to an in-place sum all-reduce on a communication stream as soon as its last producer kernel is enqueued (vocabulary
+ * projection first, encoder / CNN last), the optimiser waits for the last bucket and applies the MEAN of the towers
+ * (grad scale 1/world; the global norm of Q4 is over every tower's embedding slices, whose squared norms travel in the
+ * same buffer). With a communicator attached vc_forward_backward_* already reduce: callers of the split form must not
+ * all-reduce vc_grad_buffer again and pass 1/world to vc_apply_gradients. libnccl is bound with dlopen at the first
+ * call (VC_E_NCCL if it cannot be found); without vc_comm_init nothing here is touched.
+ * vc_allreduce_gradients: the un-overlapped form for callers that fill vc_grad_buffer themselves.
+ * vc_comm_stats: after a step, wall time on the communication stream from the first to the last bucket of that step
+ * (milliseconds), the bytes it summed and the number of buckets (synchronises the communication stream). */
+int vc_comm_unique_id(void* id128);
+int vc_comm_init(vc_handle* h, const void* id128, int rank, int world);
+int vc_allreduce_gradients(vc_handle* h, void* stream);
+int vc_comm_stats(vc_handle* h, float* ms, long long* bytes, int* calls);
+/* Measurement switch: 1 (default) bucketed + overlapped, 2 one all-reduce of the whole buffer behind the backward pass
+ * (the baseline the overlap is compared with), 0 no reduction at all (the ranks diverge: timing only). */
+int vc_comm_set_mode(vc_handle* h, int mode);
+
 /* validate(): sess.run([rec_loss]) on the training graph (main.py:262-284, dropout stays on, Q12). */
 int vc_eval_step(vc_handle* h, const float* feats_host, const int32_t* cap_lbl_host, const int32_t* cap_in_host,
                  const int32_t* len_host, const float* c_v_host, int B, int T, const vc_rng* rng, vc_step_out* out,

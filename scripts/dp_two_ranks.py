@@ -1,0 +1,146 @@
+#!/usr/bin/env python
+"""Multi-rank correctness of the in-library gradient all-reduce ON HARDWARE.
+
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29520 \
+      scripts/dp_two_ranks.py
+
+Every rank drives its own GPU through the C ABI with a communicator attached (vc_comm_init): ONE data-parallel train
+step on its shard of a seeded batch. Checked, for the bucketed/overlapped mode and the single-all-reduce mode, Normal
+and AG + cluster vectors:
+  * the summed gradient every rank holds afterwards equals the sum of the per-shard gradients of the fp64 oracle
+    (tolerance of the single-device gradient tests: 4e-2 of each tensor's max-abs);
+  * it equals, to fp32 rounding, what ONE process gets when it runs the shards back to back on one GPU and adds the
+    buffers (the construction tests/test_dp_gpu.py uses) -- i.e. NCCL moved exactly the bytes the alias-sum moves;
+  * the global norm is the Q4 norm over the concatenated towers, and all ranks hold bit-identical variables after
+    the update (crc32 over every variable).
+Prints one JSON line on rank 0; exit code 1 on any mismatch.
+"""
+import json
+import math
+import os
+import sys
+import zlib
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+from helpers import O, SMALL, engine_for, make_case, rng_for  # noqa: E402
+from vae_captioning_b200 import dp  # noqa: E402
+from vae_captioning_b200 import lib as L  # noqa: E402
+
+
+def shard(cfg, batch, r, W):
+    B = batch["feats"].shape[0]
+    lo, hi = dp.shard_range(B, r, W)
+    C = cfg.num_captions
+    out = {}
+    for k, v in batch.items():
+        if k == "feats":
+            out[k] = v[lo:hi]
+        elif k == "eps":
+            out[k] = v[:, lo * C:hi * C].contiguous()
+        elif torch.is_tensor(v) and v.dim() >= 1 and v.shape[0] == B * C:
+            out[k] = v[lo * C:hi * C]
+        else:
+            out[k] = v
+    return out
+
+
+def dev(a, dt):
+    return torch.tensor(np.ascontiguousarray(a)).to(dt).cuda()
+
+
+def fb(eng, sb, step=True):
+    cv = dev(sb["c_v"].float().numpy(), torch.float32) if "c_v" in sb else None
+    args = (dev(sb["feats"].float().numpy(), torch.float32), dev(sb["cap_lbl"].numpy(), torch.int32),
+            dev(sb["cap_in"].numpy(), torch.int32), dev(sb["lengths"].numpy(), torch.int32), 0)
+    if step:
+        return eng.train_step_device(*args, c_i=cv, rng=rng_for(sb))
+    eng.forward_backward_device(*args, c_i=cv, rng=rng_for(sb))
+    return None
+
+
+def main():
+    rank, local_rank, W = dp.world_from_env()
+    torch.cuda.set_device(local_rank)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    report, ok = {}, True
+    for tag, kw in (("normal", {}), ("ag_cv", dict(prior="AG", use_c_v=True))):
+        for mode in (1, 2):
+            B, T = 4 * W, 6
+            cfg, params, batch = make_case(SMALL, B, T, seed=17, ragged=True, **kw)
+            sb = shard(cfg, batch, rank, W)
+            eng = engine_for(cfg, params, B // W, T, device=local_rank)
+            eng.attach_comm(rank, W)
+            eng.comm_set_mode(mode)
+            out = fb(eng, sb)
+            torch.cuda.synchronize()
+            names = [n for n in O.trainable_names(cfg, params)]
+            got = {n: eng.get_gradient(n).astype(np.float64) for n in names}
+            crc = 0
+            for n, _, _ in eng.variables():
+                crc = zlib.crc32(eng.get_variable(n).tobytes(), crc)
+            crcs = [None] * W
+            dist.all_gather_object(crcs, crc)
+            stats = eng.comm_stats()
+            eng.close()
+            entry = {"crc_equal": len(set(crcs)) == 1, "buckets": stats["buckets"], "bytes": stats["bytes"]}
+            if rank == 0:
+                # (a) oracle: sum of the per-shard gradients, Q4 norm over the concatenated towers
+                ref_sum, slice_sq = {}, 0.0
+                for r in range(W):
+                    res, grads, _ = O.compute_grads(params, cfg, shard(cfg, batch, r, W))
+                    for n in names:
+                        if grads[n] is not None:
+                            ref_sum[n] = ref_sum.get(n, 0) + grads[n]
+                    slice_sq += float((res["x_enc"].grad ** 2).sum()) + float((res["x_dec"].grad ** 2).sum())
+                sq = slice_sq / (W * W)
+                for n, g in ref_sum.items():
+                    if not n.endswith("embeddings"):
+                        sq += float(((g / W) ** 2).sum())
+                norm = math.sqrt(sq)
+                worst = 0.0
+                for n, g in ref_sum.items():
+                    g = g.numpy()
+                    e = float(np.max(np.abs(got[n] - g)) / max(1e-30, float(np.max(np.abs(g)))))
+                    worst = max(worst, e)
+                entry["grad_vs_oracle_max_rel"] = worst
+                entry["norm"] = [out["global_norm"], norm]
+                # (b) one process, shards back to back, buffers added through the alias
+                e1 = engine_for(cfg, params, B // W, T, device=local_rank)
+                ptr, count = e1.grad_buffer()
+                alias = L.alias_tensor(ptr, count, torch.float32, local_rank)
+                total = torch.zeros_like(alias)
+                for r in range(W):
+                    fb(e1, shard(cfg, batch, r, W), step=False)
+                    torch.cuda.synchronize()
+                    total += alias
+                alias.copy_(total)
+                sim = {n: e1.get_gradient(n).astype(np.float64) for n in names}
+                e1.close()
+                worst_sim = 0.0
+                for n in names:
+                    d = float(np.max(np.abs(got[n] - sim[n])) / max(1e-30, float(np.max(np.abs(sim[n])))))
+                    worst_sim = max(worst_sim, d)
+                entry["grad_vs_alias_sum_max_rel"] = worst_sim
+                # split-K partial sums meet in fp32 atomics, so two runs of the same shard differ in the last bits
+                good = (entry["crc_equal"] and worst <= 4e-2 and worst_sim <= 2e-3 and
+                        abs(out["global_norm"] - norm) <= 3e-2 * norm)
+                entry["ok"] = bool(good)
+                ok = ok and good
+            report["%s_mode%d" % (tag, mode)] = entry
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    dist.broadcast(flag, src=0)
+    if rank == 0:
+        print(json.dumps({"dp_two_ranks": "ok" if ok else "FAILED", "world": W, "cases": report}))
+    dist.destroy_process_group()
+    return 0 if int(flag.item()) == 1 else 1
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -137,7 +137,40 @@ int vc_apply_gradients(vc_handle* h, float grad_scale, vc_step_out* out, void* s
 int vc_train_step_dev(vc_handle* h, const float* feats, const int32_t* lbl, const int32_t* inp, const int32_t* len,
                       const float* cv, int B, int T, int64_t gs, const vc_rng* rng, vc_step_out* out, void* stream) {
   VC_TRY(vc_forward_backward_dev(h, feats, lbl, inp, len, cv, B, T, gs, rng, stream));
-  return vc_apply_gradients(h, 1.f, out, stream);
+  return vc_apply_gradients(h, h->m.step_scale(), out, stream);
+}
+
+int vc_comm_unique_id(void* id128) {
+  VC_GUARD_BEGIN
+  if (!id128) return set_error(VC_E_ARG, "vc_comm_unique_id: null argument");
+  return comm_unique_id(id128);
+  VC_GUARD_END
+}
+int vc_comm_init(vc_handle* h, const void* id128, int rank, int world) {
+  VC_GUARD_BEGIN
+  if (!h || !id128) return set_error(VC_E_ARG, "vc_comm_init: null argument");
+  return h->m.comm_init(id128, rank, world);
+  VC_GUARD_END
+}
+int vc_allreduce_gradients(vc_handle* h, void* stream) {
+  VC_GUARD_BEGIN
+  if (!h) return set_error(VC_E_ARG, "null handle");
+  cudaSetDevice(h->m.device);
+  return h->m.comm_allreduce_all((cudaStream_t)stream);
+  VC_GUARD_END
+}
+int vc_comm_set_mode(vc_handle* h, int mode) {
+  VC_GUARD_BEGIN
+  if (!h) return set_error(VC_E_ARG, "null handle");
+  return h->m.comm_set_mode(mode);
+  VC_GUARD_END
+}
+int vc_comm_stats(vc_handle* h, float* ms, long long* bytes, int* calls) {
+  VC_GUARD_BEGIN
+  if (!h) return set_error(VC_E_ARG, "null handle");
+  cudaSetDevice(h->m.device);
+  return h->m.comm_stats(ms, bytes, calls);
+  VC_GUARD_END
 }
 
 int vc_train_step(vc_handle* h, const float* feats, const int32_t* lbl, const int32_t* inp, const int32_t* len,
@@ -152,7 +185,7 @@ int vc_train_step(vc_handle* h, const float* feats, const int32_t* lbl, const in
   if (rng) in.rng = *rng;
   VC_TRY(h->m.forward(in, true, s));
   VC_TRY(h->m.backward(in, s));
-  VC_TRY(h->m.apply(1.f, s));
+  VC_TRY(h->m.apply(h->m.step_scale(), s));
   return h->m.fetch(out, s);
   VC_GUARD_END
 }
@@ -173,7 +206,7 @@ static int train_step_images_impl(vc_handle* h, const void* images, bool u8, con
     if (rng) in.rng = *rng;
     VC_TRY(m.forward(in, true, s));
     VC_TRY(m.backward(in, s));
-    VC_TRY(m.apply(1.f, s));
+    VC_TRY(m.apply(m.step_scale(), s));
     return m.fetch(out, s);
   }
   if (B < 1 || B > m.cfg.max_batch) return set_error(VC_E_SHAPE, "batch %d exceeds max_batch %d", B, m.cfg.max_batch);
@@ -187,7 +220,7 @@ static int train_step_images_impl(vc_handle* h, const void* images, bool u8, con
   if (rng) in.rng = *rng;
   VC_TRY(m.forward(in, true, s));
   VC_TRY(m.backward(in, s));
-  VC_TRY(m.apply(1.f, s));
+  VC_TRY(m.apply(m.step_scale(), s));
   return m.fetch(out, s);
   VC_GUARD_END
 }

@@ -9,6 +9,7 @@ namespace vc {
 static inline int64_t round_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
 
 Model::~Model() {
+  comm_release();
   decode_release();
   for (void* p : allocs) cudaFree(p);
   for (StageSlot& q : slots) {
@@ -418,7 +419,7 @@ int Model::step_from_slot(int slot, int64_t gs, const vc_rng* rng, cudaStream_t 
   VC_CUDA(cudaEventRecord(q.consumed, s));
   q.in_use = true;
   q.filled = false;
-  return apply_update ? apply(1.f, s) : VC_OK;
+  return apply_update ? apply(step_scale(), s) : VC_OK;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -695,6 +696,9 @@ int Model::backward(const StepInputs& in, cudaStream_t s) {
     }
     VC_TRY(colsum_bf16(s, logits, rows, V, VP, gp(pidx("decoder/rnn_logits/bias"))));
   }
+  // data parallel: each group of gradients is summed over the ranks as soon as its last producer is enqueued
+  // (comm.cu); the vocabulary projection's 23 MB travel under the decoder's BPTT
+  VC_TRY(grad_ready_params({pidx("decoder/rnn_logits/kernel"), pidx("decoder/rnn_logits/bias")}, s));
   // decoder BPTT
   VC_CUDA(cudaMemsetAsync(dec.dh_carry, 0, (size_t)N * Hd * sizeof(float), s));
   VC_CUDA(cudaMemsetAsync(dec.dc_carry, 0, (size_t)N * Hd * sizeof(float), s));
@@ -702,6 +706,7 @@ int Model::backward(const StepInputs& in, cudaStream_t s) {
   VC_TRY(embed_scatter(s, dec.dX + (size_t)dec.pre * N * E, in.cap_in, gp(pidx("decoder/net/dec_embeddings")),
                        cfg.dec_keep_rate < 1.f ? in.rng.emb_keep_dev : nullptr, 1.f / cfg.dec_keep_rate, g_tail + 1, N, T,
                        E, V));
+  VC_TRY(grad_ready_params({dec.p_kernel, dec.p_bias, pidx("decoder/net/dec_embeddings")}, s));
   if (!cfg.no_encoder) {
     const int He = cfg.encoder_hidden;
     const int SZ = S * Z;
@@ -754,6 +759,7 @@ int Model::backward(const StepInputs& in, cudaStream_t s) {
       VC_TRY(gemm_store(s, A2, nullptr, 0, B2, He, heads_cols, N, e2, heads_cols >= 1024 ? 256 : 64, 1));
       VC_TRY(colsum_bf16(s, dheads, N, heads_cols, heads_cols, gp(p_heads_b)));
     }
+    VC_TRY(grad_ready_params({p_heads_w, p_heads_b, pidx("decoder/net/z_rnn/kernel"), pidx("decoder/net/z_rnn/bias")}, s));
     VC_CUDA(cudaMemsetAsync(enc.dc_carry, 0, (size_t)N * He * sizeof(float), s));
     VC_TRY(lstm_backward(enc, N, T, in.len, nullptr, nullptr, s));
     VC_TRY(embed_scatter(s, enc.dX + (size_t)enc.pre * N * E, in.cap_lbl, gp(pidx("encoder/enc_embeddings")), nullptr, 1.f,
@@ -789,12 +795,22 @@ int Model::backward(const StepInputs& in, cudaStream_t s) {
     }
     VC_TRY(vgg_backward(dfeats_f, B, s));
   }
-  // squared norm of the dense (non-embedding) gradients -> tail[2]; embedding slices are in tail[0..1] (Q4)
+  if (comm != nullptr) {
+    // last bucket: encoder LSTM + table, the two small projections, and the 64-float tail whose first two entries are
+    // the per-token embedding-slice squared norms of this rank (Q4: the norm is over every tower's slices)
+    if (!cfg.no_encoder) VC_TRY(grad_ready_params({enc.p_kernel, enc.p_bias, pidx("encoder/enc_embeddings")}, s));
+    VC_TRY(grad_ready_params({pidx("imf_emb/kernel"), pidx("imf_emb/bias"), cfg.use_c_v ? pidx("cv_emb/kernel") : -1,
+                              cfg.use_c_v ? pidx("cv_emb/bias") : -1}, s));
+    const int64_t tail[1][2] = {{n_adam, 64}};
+    VC_TRY(grad_ready(tail, 1, s));
+  }
+  // squared norm of the dense (non-embedding) gradients -> tail[2] (apply); embedding slices are in tail[0..1] (Q4)
   return VC_OK;
 }
 
 int Model::apply(float grad_scale, cudaStream_t s) {
   // ops/optimizers.py:13-40: clip_by_global_norm(5.0) then Adam(lr, beta1=0.8); TF Adam form (Q5)
+  VC_TRY(comm_join(s));  // data parallel: every bucket of the gradient all-reduce has landed
   VC_CUDA(cudaMemsetAsync(g_tail + 2, 0, sizeof(float), s));
   VC_TRY(sumsq(s, Gf, n_dense, g_tail + 2));
   adam_t += 1;

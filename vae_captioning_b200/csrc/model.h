@@ -1,6 +1,7 @@
 // The CVAE captioning model state behind vc_handle: parameter store (TF names), bf16 weight
 // shadows, time-major activation workspace, and the train / eval step orchestration.
 #pragma once
+#include <initializer_list>
 #include <map>
 #include <string>
 #include <vector>
@@ -49,6 +50,7 @@ struct VggLayer {
 };
 
 struct DecodeWs;  // decode.cu
+struct Comm;      // comm.cu
 
 struct StepInputs {
   const float* feats;     // device fp32 [B, F] (or images when fine_tune; uint8 pixels when feats_u8)
@@ -157,6 +159,20 @@ class Model {
   int decode_open(const float* feats_dev, const float* c_v_dev, int B, const vc_rng* rng, cudaStream_t s);
   int decode_step(const int32_t* tok_host, int M, float* probs_host, cudaStream_t s);
   int decode_state(float* c_host, float* h_host, const float* c_in, const float* h_in, cudaStream_t s);
+
+  // --- data-parallel gradient all-reduce (comm.cu); null = single device
+  Comm* comm = nullptr;
+  int comm_init(const void* id128, int rank, int world);
+  void comm_release();
+  int comm_world() const;
+  int grad_ready(const int64_t (*ranges)[2], int n_ranges, cudaStream_t s);
+  int grad_ready_params(std::initializer_list<int> ids, cudaStream_t s);
+  int comm_reduce(const int64_t (*ranges)[2], int n_ranges, cudaStream_t s);
+  int comm_set_mode(int mode);
+  int comm_join(cudaStream_t s);
+  int comm_allreduce_all(cudaStream_t s);
+  int comm_stats(float* ms, long long* bytes, int* calls);
+  float step_scale() const { return 1.f / (float)comm_world(); }  // towers are averaged
 
   std::vector<void*> allocs;
 

@@ -93,6 +93,9 @@ int conv3x3_dgrad(cudaStream_t s, const void* dy, const void* wt_d, void* dx, in
 int dgrad_shadow(cudaStream_t s, const float* w_hwio, void* wt_d, int cin, int cout);
 int relu_pool_bwd(cudaStream_t s, const void* dA, const void* out, void* dY, int B, int hw, int C, bool pooled, float* db);
 
+// comm.cu ----------------------------------------------------------------------------------
+int comm_unique_id(void* id128);
+
 // elementwise.cu ---------------------------------------------------------------------------
 int cast_f32_bf16(cudaStream_t s, const float* src, void* dst, long long rows, int cols, long long ld_src,
                   long long ld_dst);

@@ -256,6 +256,7 @@ int Model::vgg_backward(const float* dfeats, int B, cudaStream_t s) {
     VC_TRY(gemm_store(s, A, nullptr, 0, Bm, 4096, 4096, B, e, 256, 1));
   }
   VC_TRY(colsum_bf16(s, dfc2_pre, B, 4096, 4096, gp(p_fc2b)));
+  VC_TRY(grad_ready_params({p_fc2w, p_fc2b}, s));  // data parallel: the cnn/ gradients travel layer group by layer group
   {
     ProfTag pt("fc_dgrad");
     Operand A{dfc2_pre, B, 4096, 4096, false}, Bm{fc2_w, 4096, 4096, 4096, false};
@@ -277,6 +278,7 @@ int Model::vgg_backward(const float* dfeats, int B, cudaStream_t s) {
     VC_TRY(gemm_store(s, A, nullptr, 0, Bm, 25088, 4096, B, e, 256, 1));
   }
   VC_TRY(colsum_bf16(s, dfc1_pre, B, 4096, 4096, gp(p_fc1b)));
+  VC_TRY(grad_ready_params({p_fc1w, p_fc1b}, s));  // 411 MB, under the whole convolutional backward pass
   uint16_t* dA = (uint16_t*)vgg_bwd_a;  // gradient w.r.t. the (pooled) output of the current layer
   uint16_t* dY = (uint16_t*)vgg_bwd_b;  // gradient w.r.t. its pre-activation, un-pooled
   {
@@ -306,6 +308,7 @@ int Model::vgg_backward(const float* dfeats, int B, cudaStream_t s) {
         k_conv1_fold<<<7, 256, 0, s>>>(conv1_wg, gp(L.p_w));
       }
       VC_CUDA(cudaGetLastError());
+      VC_TRY(grad_ready_params({vgg[0].p_w, vgg[0].p_b, vgg[1].p_w, vgg[1].p_b}, s));
       break;
     }
     const void* x_in = vgg[l - 1].pool ? vgg[l - 1].pooled : vgg[l - 1].out;
@@ -315,6 +318,10 @@ int Model::vgg_backward(const float* dfeats, int B, cudaStream_t s) {
                                   "dgrad4_2", "dgrad4_3", "dgrad5_1", "dgrad5_2", "dgrad5_3"};
     VC_TRY(conv3x3_wgrad(s, x_in, dY, gp(L.p_w), B, L.hw, L.cin, L.cout, kWg[l]));
     VC_TRY(conv3x3_dgrad(s, dY, L.wt_d, dA, B, L.hw, L.cin, L.cout, kDg[l]));
+    // one bucket per VGG block (conv5_x, conv4_x, conv3_x, conv2_x; conv1_x after the loop's last iteration)
+    if (l == 10 || l == 7 || l == 4)
+      VC_TRY(grad_ready_params({vgg[l].p_w, vgg[l].p_b, vgg[l + 1].p_w, vgg[l + 1].p_b, vgg[l + 2].p_w, vgg[l + 2].p_b}, s));
+    if (l == 2) VC_TRY(grad_ready_params({vgg[2].p_w, vgg[2].p_b, vgg[3].p_w, vgg[3].p_b}, s));
   }
   return VC_OK;
 }

@@ -67,7 +67,8 @@ class DataParallelStep(object):
 
     def __call__(self, local_feed, fetch=True):
         self.backend.forward_backward(local_feed)
-        if self.world > 1:
+        # an Engine with its own communicator (Engine.attach_comm) has already summed the buckets inside forward_backward
+        if self.world > 1 and not getattr(self.backend, "reduces_internally", False):
             self.dist.all_reduce(self.backend.grad_tensor(), op=self.dist.ReduceOp.SUM, group=self.group)
         return self.backend.apply(1.0 / self.world, fetch)
 
@@ -79,7 +80,8 @@ class EngineBackend(object):
         from . import lib as L
         import torch
         self.engine = engine
-        self.seed = seed
+        self.reduces_internally = bool(getattr(engine, "reduces_internally", False))
+        self.seed = seed + world_from_env()[0]  # every tower draws its own noise
         self.step = 0
         ptr, count = engine.grad_buffer()
         self._grad = L.alias_tensor(ptr, count, torch.float32, device_index)

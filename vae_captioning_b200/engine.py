@@ -129,6 +129,12 @@ class Engine(object):
         lib.vc_vgg_forward_dev.argtypes = [vp, vp, vp, ci, vp]
         lib.vc_vgg_activation.argtypes = [vp, ctypes.c_char_p, vp]
         lib.vc_vgg_keep_activations.argtypes = [vp, ci]
+        lib.vc_comm_unique_id.argtypes = [vp]
+        lib.vc_comm_init.argtypes = [vp, vp, ci, ci]
+        lib.vc_allreduce_gradients.argtypes = [vp, vp]
+        lib.vc_comm_set_mode.argtypes = [vp, ci]
+        lib.vc_comm_stats.argtypes = [vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_longlong),
+                                      ctypes.POINTER(ctypes.c_int)]
         lib._vc_declared = True
 
     # ------------------------------------------------------------------ lifetime
@@ -142,6 +148,39 @@ class Engine(object):
             self.close()
         except Exception:
             pass
+
+    # ------------------------------------------------------------------ data parallelism
+    def attach_comm(self, rank=None, world=None, group=None):
+        """vc_comm_init: gives this handle its NCCL communicator. Rank 0 draws the unique id, torch.distributed (any
+        backend; only used as the bootstrap channel) broadcasts it. From then on every train_step* call is the
+        data-parallel step: bucketed gradient all-reduce overlapped with the backward pass, mean of the towers."""
+        import torch.distributed as dist
+        rank = dist.get_rank(group) if rank is None else rank
+        world = dist.get_world_size(group) if world is None else world
+        buf = ctypes.create_string_buffer(128)
+        if rank == 0:
+            L.check(self.lib.vc_comm_unique_id(buf))
+        box = [bytes(buf.raw) if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0, group=group)
+        L.check(self.lib.vc_comm_init(self._h, box[0], int(rank), int(world)))
+        self.world = int(world)
+        return self
+
+    @property
+    def reduces_internally(self):
+        return getattr(self, "world", 1) > 1
+
+    def comm_set_mode(self, mode):
+        """1 bucketed + overlapped (default), 2 one all-reduce behind the backward pass, 0 none (timing only)."""
+        L.check(self.lib.vc_comm_set_mode(self._h, int(mode)))
+
+    def comm_stats(self):
+        ms, nb, calls = ctypes.c_float(), ctypes.c_longlong(), ctypes.c_int()
+        L.check(self.lib.vc_comm_stats(self._h, ctypes.byref(ms), ctypes.byref(nb), ctypes.byref(calls)))
+        return {"span_ms": float(ms.value), "bytes": int(nb.value), "buckets": int(calls.value)}
+
+    def allreduce_gradients(self):
+        L.check(self.lib.vc_allreduce_gradients(self._h, self._stream()))
 
     # ------------------------------------------------------------------ variables (tf.train.Saver surface)
     def variables(self):
