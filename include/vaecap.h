@@ -29,6 +29,7 @@ extern "C" {
 
 enum { VC_OK = 0, VC_E_ARG = -1, VC_E_SHAPE = -2, VC_E_CUDA = -3, VC_E_NCCL = -4, VC_E_STATE = -5, VC_E_NOMEM = -6 };
 enum { VC_PRIOR_NORMAL = 0, VC_PRIOR_GMM = 1, VC_PRIOR_AG = 2 };
+enum { VC_OPT_ADAM = 0, VC_OPT_SGD = 1, VC_OPT_MOMENTUM = 2 };
 
 /* Mirrors the fields of the reference's Parameters (utils/parameters.py:3-66) that shape the graph
  * built in main.py:43-191. */
@@ -50,6 +51,10 @@ typedef struct vc_config {
   int32_t with_cnn;         /* allocate VGG16 parameters (needed for fine_tune and vc_vgg_forward) */
   int32_t max_batch;        /* images per step (B) */
   int32_t max_len;          /* padded caption length (T) */
+  int32_t optimizer;        /* --optimizer: VC_OPT_ADAM / VC_OPT_SGD / VC_OPT_MOMENTUM (ops/optimizers.py:33-46) */
+  int32_t cnn_optimizer;    /* Parameters.cnn_optimizer, same values (ops/optimizers.py:68-81) */
+  int32_t lr_decay_steps;   /* int(num_ex_per_epoch / (batch_size + 0.001) * num_epochs_per_decay): SGD / Momentum halve
+                               their rate every that many steps (staircase, ops/optimizers.py:24-31); Adam ignores it */
   float dec_keep_rate;      /* --dec_drop */
   float dec_lstm_drop;      /* --dec_lstm_drop */
   float cnn_dropout;
@@ -197,7 +202,8 @@ int vc_vgg_forward_dev(vc_handle* h, const float* images_dev, float* fc2_dev, in
 int vc_vgg_forward_u8(vc_handle* h, const uint8_t* images_host, float* fc2_host, int B, void* stream); /* uint8 pixels */
 /* Debug taps: vc_vgg_keep_activations(h, 1) makes later forwards materialise every conv output instead of fusing
  * the 2x2 max-pools into the conv epilogues; vc_vgg_activation then returns the NHWC activation of a layer
- * ("conv1_1".."conv5_3", post-ReLU; "pool1".."pool5") of the last forward as fp32. */
+ * ("conv1_1".."conv5_3", post-ReLU; "pool1".."pool5") of the last forward as fp32; "fc1" / "fc2" return the [B, 4096]
+ * outputs of the two dense layers (post-ReLU, post-dropout when fine-tuning). */
 int vc_vgg_keep_activations(vc_handle* h, int on);
 int vc_vgg_activation(vc_handle* h, const char* layer, float* dst_host);
 

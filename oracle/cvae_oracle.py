@@ -54,6 +54,11 @@ class Config:
         self.learning_rate = 0.0005
         self.cnn_lr = 0.00001
         self.lstm_clip_by_norm = 5.0
+        self.optimizer = "Adam"        # --optimizer {SGD, Adam, Momentum} (utils/parameters.py:34)
+        self.cnn_optimizer = "Adam"
+        self.batch_size = 32           # with the two below: the staircase decay period of SGD / Momentum
+        self.num_ex_per_epoch = 150000
+        self.num_epochs_per_decay = 5
         self.ann_param = 0.0
         self.std = 0.1
         self.temperature = 1.0
@@ -215,9 +220,14 @@ def dense(x, params, name, emulate=False):
     return x @ _r(params[name + "/kernel"], emulate) + params[name + "/bias"]
 
 
-def vgg16_fc2(params, images, cfg=None, fc_keep_masks=None, keep=1.0, emulate=False, taps=None):
+def vgg16_fc2(params, images, cfg=None, fc_keep_masks=None, keep=1.0, emulate=False, taps=None, branches=None):
     """utils/image_embeddings.py:26-238. images [B,224,224,3] RGB 0..255 -> fc2 [B,4096].
-    fc_keep_masks: optional (mask_fc1, mask_fc2) for cnn dropout when fine-tuning (:225-237)."""
+    fc_keep_masks: optional (mask_fc1, mask_fc2) for cnn dropout when fine-tuning (:225-237).
+    branches (parity-test aid, not a reference feature): {layer: activation [B,H,W,C] (conv) or [B,4096] (fc1, fc2)} of
+    ANOTHER implementation's forward pass. Where given, the ReLU passes exactly the units that are positive there and
+    the 2x2 max-pool routes exactly the window element that is largest there, instead of deciding from this pass's own
+    values: the piecewise-linear network is then the SAME linear map in both implementations, so gradients can be
+    compared tensor by tensor without the branch flips that rounding noise near zero / near ties causes."""
     import torch.nn.functional as F
     dt = images.dtype
     mean = torch.tensor([123.68, 116.779, 103.939], dtype=dt)
@@ -226,19 +236,37 @@ def vgg16_fc2(params, images, cfg=None, fc_keep_masks=None, keep=1.0, emulate=Fa
         suffix = "_conv" if name.startswith("conv5") else ""
         w = _r(params["cnn/%s/weights%s" % (name, suffix)], emulate).permute(3, 2, 0, 1)  # HWIO -> OIHW
         b = params["cnn/%s/biases%s" % (name, suffix)]
-        x = _r(torch.relu(F.conv2d(x, w, b, padding=1)), emulate)
+        y = F.conv2d(x, w, b, padding=1)
+        other = None if branches is None or name not in branches else branches[name].to(dt).permute(0, 3, 1, 2)
+        x = _r(torch.relu(y) if other is None else y * (other > 0).to(dt), emulate)
         if taps is not None:
             taps[name] = x.permute(0, 2, 3, 1)
         if name in VGG_POOL_AFTER:
-            x = F.max_pool2d(x, 2, 2)
+            if other is None:
+                x = F.max_pool2d(x, 2, 2)
+            else:
+                _, idx = F.max_pool2d(other, 2, 2, return_indices=True)
+                x = x.flatten(2).gather(2, idx.flatten(2)).view(idx.shape)
     flat = x.permute(0, 2, 3, 1).reshape(x.shape[0], -1)  # NHWC flatten, image_embeddings.py:222
-    fc1 = torch.relu(flat @ _r(params["cnn/fc1/weights"], emulate) + params["cnn/fc1/biases"])
+    fc1 = flat @ _r(params["cnn/fc1/weights"], emulate) + params["cnn/fc1/biases"]
+    if branches is not None and "fc1" in branches:  # positive there <=> ReLU open and the unit kept by the dropout
+        fc1 = fc1 * ((branches["fc1"] > 0) | (fc_keep_masks is not None and fc_keep_masks[0] == 0)).to(dt)
+    else:
+        fc1 = torch.relu(fc1)
     if fc_keep_masks is not None:
         fc1 = fc1 * fc_keep_masks[0] / keep
     fc1 = _r(fc1, emulate)
-    fc2 = torch.relu(fc1 @ _r(params["cnn/fc2/weights"], emulate) + params["cnn/fc2/biases"])
+    if taps is not None:
+        taps["fc1"] = fc1
+    fc2 = fc1 @ _r(params["cnn/fc2/weights"], emulate) + params["cnn/fc2/biases"]
+    if branches is not None and "fc2" in branches:
+        fc2 = fc2 * ((branches["fc2"] > 0) | (fc_keep_masks is not None and fc_keep_masks[1] == 0)).to(dt)
+    else:
+        fc2 = torch.relu(fc2)
     if fc_keep_masks is not None:
         fc2 = fc2 * fc_keep_masks[1] / keep
+    if taps is not None:
+        taps["fc2"] = fc2
     return fc2
 
 
@@ -335,7 +363,8 @@ def forward(params, cfg, batch, emulate=False, c_means=None):
     l2 = 0.0
     if cfg.fine_tune:
         masks = batch.get("cnn_keep_masks") if cfg.mode == "training" else None
-        feats = vgg16_fc2(params, batch["images"].to(dt), cfg, masks, cfg.cnn_dropout, emulate)
+        feats = vgg16_fc2(params, batch["images"].to(dt), cfg, masks, cfg.cnn_dropout, emulate,
+                          branches=batch.get("vgg_branches"))
         if cfg.mode == "training":  # Q11: l2_regularizer(weight_decay) on every cnn/ variable
             for n, _ in vgg_param_names():
                 l2 = l2 + cfg.weight_decay * torch.sum(params[n] ** 2) / 2
@@ -424,6 +453,25 @@ def adam_update(p, g, m, v, lr, t, beta1=0.8, beta2=0.999, eps=1e-8):
     return p, m, v
 
 
+def decay_steps(cfg):
+    """ops/optimizers.py:24-26: int(num_ex_per_epoch / (batch_size + 0.001) * num_epochs_per_decay)."""
+    return int(cfg.num_ex_per_epoch / (cfg.batch_size + 0.001) * cfg.num_epochs_per_decay)
+
+
+def optimizer_update(kind, p, g, m, v, lr, t, cfg):
+    """One apply_gradients of ops/optimizers.py:33-46 / 68-81. t = 1-based step; the decayed rate reads global_step
+    BEFORE its increment (t - 1), staircase halving every decay_steps; Adam ignores the decay (Q5)."""
+    if kind == "Adam":
+        return adam_update(p, g, m, v, lr, t)
+    lr_d = lr * 0.5 ** ((t - 1) // max(decay_steps(cfg), 1))
+    if kind == "SGD":          # tf.train.GradientDescentOptimizer
+        return p - lr_d * g, m, v
+    if kind == "Momentum":     # tf.train.MomentumOptimizer(lr, 0.9): accum = 0.9 * accum + g ; p -= lr * accum
+        m = 0.9 * m + g
+        return p - lr_d * m, m, v
+    raise ValueError("unknown optimizer %r" % (kind,))
+
+
 def train_step(params, opt, cfg, batch, emulate=False, c_means=None):
     """One sess.run([kld, rec_loss, lower_bound, optimize, optimize_cnn, annealing]) (main.py:241-244).
     params/opt are updated in place (opt = {"t": int, "m": {}, "v": {}}). Returns the fetches."""
@@ -437,13 +485,14 @@ def train_step(params, opt, cfg, batch, emulate=False, c_means=None):
             continue
         m = opt["m"].get(n, torch.zeros_like(params[n]))
         v = opt["v"].get(n, torch.zeros_like(params[n]))
-        params[n], opt["m"][n], opt["v"][n] = adam_update(params[n], g * scale, m, v, cfg.learning_rate, opt["t"])
+        params[n], opt["m"][n], opt["v"][n] = optimizer_update(cfg.optimizer, params[n], g * scale, m, v, cfg.learning_rate,
+                                                               opt["t"], cfg)
     if cfg.fine_tune:  # ops/optimizers.py:49-82: no clipping, cnn_lr
         for n, _ in vgg_param_names():
             g = grads[n]
             m = opt["m"].get(n, torch.zeros_like(params[n]))
             v = opt["v"].get(n, torch.zeros_like(params[n]))
-            params[n], opt["m"][n], opt["v"][n] = adam_update(params[n], g, m, v, cfg.cnn_lr, opt["t"])
+            params[n], opt["m"][n], opt["v"][n] = optimizer_update(cfg.cnn_optimizer, params[n], g, m, v, cfg.cnn_lr, opt["t"], cfg)
     return {"kld": res["kld"].detach(), "rec_loss": float(res["rec_loss"].detach()), "lower_bound": res["lower_bound"].detach(),
             "annealing": res["annealing"], "global_norm": gnorm, "grads": grads, "res": res}
 

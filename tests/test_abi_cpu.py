@@ -53,3 +53,20 @@ def test_config_struct_layout_matches_header():
     assert [n for _, n in fields] == [n for n, _ in VcConfig._fields_]
     for (ty, _), (_, cty) in zip(fields, VcConfig._fields_):
         assert cty is (ctypes.c_int32 if ty == "int32_t" else ctypes.c_float)
+
+
+def test_comm_entry_points_without_gpu():
+    """The data-parallel entry points bind libnccl lazily: drawing a unique id needs no GPU (0, or VC_E_NCCL when no
+    libnccl can be loaded -- never a crash), and a null handle is an argument error, not a segfault."""
+    from vae_captioning_b200 import lib
+    h = lib.load()
+    h.vc_comm_unique_id.argtypes = [ctypes.c_void_p]
+    h.vc_comm_init.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
+    buf = ctypes.create_string_buffer(128)
+    rc = h.vc_comm_unique_id(buf)
+    assert rc in (0, -4), (rc, h.vc_last_error())
+    if rc == 0:
+        buf2 = ctypes.create_string_buffer(128)
+        assert h.vc_comm_unique_id(buf2) == 0 and buf.raw != buf2.raw  # ids are unique
+    assert h.vc_comm_init(None, buf, 0, 1) == -1
+    assert h.vc_comm_unique_id(None) == -1

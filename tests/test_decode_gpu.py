@@ -2,8 +2,9 @@
 vae_model/decoder.py gen mode + the reference-pinned loops) on the same seeded weights, features and latent draws.
 
 Tolerance (stated): bf16 operands / fp32 accumulate vs the oracle computing in float64 on the same bf16-rounded
-weights: next-word probabilities within 2e-2 of the row maximum; token sequences must be identical for at least 80 %
-of the images (a bf16-level perturbation can flip a near-tie), and every mismatching beam score must agree within 2e-2."""
+weights: next-word probabilities within 2e-2 of the row maximum; token sequences must be identical to the oracle's
+unless the oracle itself is at a near-tie at the first divergent step (its two candidates within that same 2e-2), which
+the tests assert image by image (64 images per case); beam scores must agree within 2e-2 relative."""
 import numpy as np
 import pytest
 import torch
@@ -89,22 +90,55 @@ def test_step_probabilities_and_state_feed(sizes, kw):
     eng.close()
 
 
+def _replay(step, sentence):
+    """Next-word probability rows of the oracle along `sentence` (ids after <BOS>), fed the way online_inference feeds
+    them: rows[i] = distribution from which sentence[i] was chosen."""
+    rows, state, prev = [], None, BOS
+    for w in sentence:
+        probs, state = step(prev, state)
+        rows.append(np.asarray(probs).ravel())
+        prev = w
+    return rows
+
+
+def _beam_score(step, sentence, len_norm=0.7):
+    """Score Decoder.beam_search gives `sentence` (ids incl. <BOS>): <BOS> is consumed by the initial call and fed again
+    by the first loop iteration (Q9); length normalisation for completed captions only."""
+    _, state = step(BOS, None)
+    logprob, prev = 0.0, sentence[0]
+    for w in sentence[1:]:
+        probs, state = step(prev, state)
+        logprob += float(np.log(np.asarray(probs).ravel()[w]))
+        prev = w
+    return logprob / len(sentence) ** len_norm if sentence[-1] == EOS else logprob
+
+
 @pytest.mark.parametrize("sizes,kw", CASES)
 def test_greedy_matches_oracle(sizes, kw):
-    B = 10
+    """64 images per case. Token sequences must be IDENTICAL to the oracle's, except where the oracle itself is at a
+    near-tie at the first divergent step: the probability it gives its own choice and the device's choice differ by
+    less than 2e-2 of the row maximum (the stated next-word probability tolerance). Anything else fails."""
+    B = 64
     cfg, params, feats, c_v, eps = make_decode_case(sizes, B, seed=2, **kw)
     eng, dec = device_decoder(cfg, params, B, 1)
     steps = oracle_steps(cfg, params, feats, c_v, eps)
     rng = {"eps": torch.tensor(eps).cuda()}
     ids = list(range(100, 100 + B))
     caps, raw = dec.online_inference(ids, feats, c_v, sample_gen="greedy", rng=rng)
-    same = 0
+    same, explained = 0, 0
     for b in range(B):
         want = D.online_inference(steps[b], "greedy", cfg.gen_max_len, cfg.temperature, BOS, EOS)
-        same += int(raw[b] == want)
         assert len(raw[b]) <= cfg.gen_max_len and (raw[b][-1] == EOS or len(raw[b]) == cfg.gen_max_len)
         assert caps[b]["image_id"] == ids[b]
-    assert same >= 0.8 * B, (kw, same)
+        if raw[b] == want:
+            same += 1
+            continue
+        i = next(k for k in range(min(len(raw[b]), len(want))) if raw[b][k] != want[k])
+        p = _replay(steps[b], want[:i + 1])[i]
+        gap = float(p[want[i]] - p[raw[b][i]])
+        assert 0 <= gap <= 2e-2 * float(p.max()), (kw, b, i, gap, float(p.max()))
+        explained += 1
+    assert same + explained == B and same >= 0.9 * B, (kw, same, explained)
     # the reference's test-split behaviour for sample_gen='beam_search' (Q9): gen_max_len x <PAD>
     caps, raw = dec.online_inference(ids, feats, c_v, sample_gen="beam_search")
     assert raw[0] == [0] * cfg.gen_max_len and caps[0]["caption"] == " ".join(["<PAD>"] * cfg.gen_max_len)
@@ -114,19 +148,35 @@ def test_greedy_matches_oracle(sizes, kw):
 @pytest.mark.parametrize("beam", [1, 2, 5, 10])
 @pytest.mark.parametrize("sizes,kw", [(TINY, {}), (SMALL, dict(use_c_v=True)), (SMALL, dict(prior="AG"))])
 def test_beam_search_matches_oracle(sizes, kw, beam):
-    B = 8
+    """64 images per case. For EVERY image the score the device reports for its best beam equals the score the oracle
+    gives that same sentence (2e-2 relative: the device's log-probabilities are right); the returned beam lists must
+    be identical to the oracle's, except where the oracle scores the device's best sentence within 2e-2 (relative) of
+    its own best -- a near-tie a bf16-level perturbation may flip."""
+    B = 64
     cfg, params, feats, c_v, eps = make_decode_case(sizes, B, seed=3, **kw)
     eng, dec = device_decoder(cfg, params, B, beam)
     steps = oracle_steps(cfg, params, feats, c_v, eps)
     rng = {"eps": torch.tensor(eps).cuda()}
     toks, lens, scores, nb = dec.beam_tokens(feats, c_v, beam_size=beam, rng=rng)
-    same = 0
+    same, explained = 0, 0
     for b in range(B):
         want = D.beam_search(steps[b], beam, cfg.gen_max_len, BOS, EOS, ret_beams=True)
         got = [[int(w) for w in toks[b, j, :lens[b, j]]] for j in range(int(nb[b]))]
         assert got[0][0] == BOS and all(scores[b, j] >= scores[b, j + 1] for j in range(int(nb[b]) - 1))
-        same += int(got == want)
-    assert same >= 0.75 * B, (kw, beam, same)
+        s_dev = _beam_score(steps[b], got[0])
+        assert abs(float(scores[b, 0]) - s_dev) <= 2e-2 * abs(s_dev) + 1e-3, (kw, beam, b, float(scores[b, 0]), s_dev)
+        if got == want:
+            same += 1
+            continue
+        if got[0] != want[0]:
+            s_ref = _beam_score(steps[b], want[0])
+            assert abs(s_ref - s_dev) <= 2e-2 * abs(s_ref), (kw, beam, b, s_ref, s_dev)
+        else:  # same caption, the tail of the list differs: every listed beam must still carry its oracle score
+            for j in range(int(nb[b])):
+                sj = _beam_score(steps[b], got[j])
+                assert abs(float(scores[b, j]) - sj) <= 2e-2 * abs(sj) + 1e-3, (kw, beam, b, j)
+        explained += 1
+    assert same + explained == B and same >= 0.75 * B, (kw, beam, same, explained)
     caps = dec.beam_search(list(range(B)), feats, c_v, beam_size=beam, rng=rng)
     assert caps[0]["caption"] == " ".join("w%d" % w for w in toks[0, 0, :lens[0, 0]] if w not in (BOS, EOS))
     eng.close()

@@ -94,6 +94,40 @@ def test_finetune_gradients(B):
     assert abs(out["global_norm"] - gnorm) <= 3e-2 * gnorm  # cnn/ gradients are not part of the clipped norm
 
 
+@pytest.mark.parametrize("B", [2, 3])
+def test_finetune_cnn_gradients_layer_by_layer_same_branches(B):
+    """Whole-network CNN gradients, tensor by tensor at 4e-2 of max-abs. The statistical test
+    above has to tolerate ReLU / max-pool branch flips between two roundings of the same forward pass; here the oracle is
+    told which branch the DEVICE took at every unit (vc_vgg_activation of all 13 conv layers + fc1 / fc2 -> the
+    `branches` argument of the oracle's VGG), so both sides differentiate the same piecewise-linear map and a wrong tap
+    order / channel mix-up in any dgrad or wgrad kernel shows up as an O(1) error in that layer's tensor."""
+    T = 5
+    cfg, params, batch, keep = finetune_case(B, T, seed=B)
+    eng = engine_for(cfg, params, B, T)
+    dev = lambda a, dt: torch.tensor(np.ascontiguousarray(a)).to(dt).cuda()
+    f = feed(batch)
+    eng.forward_backward_device(dev(f["image_f_inputs"], torch.float32), dev(f["ann_inputs_enc"], torch.int32),
+                                dev(f["ann_inputs_dec"], torch.int32), dev(f["ann_lengths"], torch.int32), 0,
+                                rng=rng_with_masks(batch, keep))
+    torch.cuda.synchronize()
+    layers = [n for n, _, _ in O.VGG_LAYERS] + ["fc1", "fc2"]
+    b2 = dict(batch)
+    b2["vgg_branches"] = {n: torch.tensor(eng.vgg_activation(n, B)) for n in layers}
+    res, grads, gnorm = O.compute_grads(params, cfg, b2, emulate=True)
+    worst = {}
+    for name, g in grads.items():
+        if g is None or not name.startswith("cnn/"):
+            continue
+        got, ref = eng.get_gradient(name), g.numpy()
+        worst[name] = float(np.max(np.abs(got - ref)) / max(float(np.max(np.abs(ref))), 1e-30))
+    eng.close()
+    if os.path.isdir(os.path.join(ROOT, "gpurun_out")):
+        json.dump(worst, open(os.path.join(ROOT, "gpurun_out", "finetune_branch_grad_err_B%d.json" % B), "w"), indent=1)
+    assert len(worst) == 30
+    bad = {k: v for k, v in worst.items() if v > 4e-2}
+    assert not bad, bad
+
+
 def test_finetune_l2_term_and_cnn_adam():
     """weight_decay * w enters the cnn gradient (Q11) and the cnn variables move by Adam(cnn_lr, beta1=0.8), un-clipped."""
     B, T = 2, 5

@@ -153,3 +153,77 @@ def test_decode_rows_independent_and_idempotent_at_1024_images(mode):
     # bf16-level near-tie may flip in rare rows, so at least 95 % of the sampled rows must be identical
     assert same >= int(0.95 * 96), same
     eng.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Backward pass at full size against the oracle: every gradient tensor within 4e-2 of its
+# max-abs (the tolerance of the small cases in test_train_step_gpu.py::test_gradients), global norm within 2e-2.
+def _device_feed(batch):
+    f = feed_of(batch)
+    dev = lambda a, dt: torch.tensor(np.ascontiguousarray(a)).to(dt).cuda()
+    return dict(feats=dev(f["image_f_inputs"], torch.float32), cap_lbl=dev(f["ann_inputs_enc"], torch.int32),
+                cap_in=dev(f["ann_inputs_dec"], torch.int32), lengths=dev(f["ann_lengths"], torch.int32),
+                c_i=dev(f["c_i"], torch.float32) if f["c_i"] is not None else None)
+
+
+def _grads_vs_oracle(cfg, params, batch, Bx):
+    eng = engine_for(cfg, params, Bx, T)
+    d = _device_feed(batch)
+    eng.forward_backward_device(d["feats"], d["cap_lbl"], d["cap_in"], d["lengths"], 0, c_i=d["c_i"], rng=rng_for(batch))
+    torch.cuda.synchronize()
+    res, grads, gnorm = O.compute_grads(params, cfg, batch, emulate=False)  # fp32 torch-CPU autograd of the restated graph
+    worst = {}
+    for name, g in grads.items():
+        if g is None:
+            continue
+        ref = g.numpy()
+        got = eng.get_gradient(name)
+        worst[name] = float(np.max(np.abs(got - ref)) / max(float(np.max(np.abs(ref))), 1e-12))
+    out = eng.apply_gradients(1.0)
+    eng.close()
+    return res, worst, out, gnorm
+
+
+def test_gradients_at_full_size_normal_prior(full_case):
+    """N = 1280 captions (BASELINE config 2's caption model): tf.gradients of every non-CNN variable."""
+    cfg, params, batch = full_case
+    res, worst, out, gnorm = _grads_vs_oracle(cfg, params, batch, B)
+    bad = {n: e for n, e in worst.items() if e > 4e-2}
+    assert not bad, bad
+    assert len(worst) == 16  # the 16 variables of the Normal-prior graph (SURVEY 8a13)
+    assert abs(out["global_norm"] - gnorm) <= 2e-2 * gnorm
+
+
+@pytest.mark.parametrize("prior", ["GMM", "AG"])
+def test_forward_and_gradients_at_config3_4_sizes(prior):
+    """BASELINE configs 3 / 4 per-GPU caption-model shapes: K = 90 heads ([N,512] x [512,27000]), Z = 150, S = 100,
+    E = 256, H = 512, cluster vectors, N = 640 captions: mu / std / KL (AG: per-row vector) / logits / rec_loss and every
+    gradient (374 variables) against the oracle. Reference: main.py:118-145, encoder.py:71-107."""
+    Bx = 128
+    cfg = O.Config(prior=prior, use_c_v=True)
+    params = O.init_params(cfg, seed=1, dtype=torch.float32)
+    g = np.random.Generator(np.random.PCG64(12))
+    for n in params:
+        if params[n].dim() == 1:
+            params[n] = torch.tensor(g.uniform(-0.1, 0.1, size=tuple(params[n].shape)).astype(np.float32))
+    batch = O.synthetic_batch(cfg, Bx, T, seed=6, dtype=torch.float32, ragged=True)
+    Nx = Bx * C
+    eng = engine_for(cfg, params, Bx, T)
+    out = eng.eval_step(rng=rng_for(batch), **feed_of(batch))
+    taps = eng.debug_taps(Nx, T)
+    eng.close()
+    res, worst, out_b, gnorm = _grads_vs_oracle(cfg, params, batch, Bx)
+    lx = res["logits"].detach().numpy()
+    assert np.max(np.abs(taps["logits"] - lx)) <= 2e-2 * max(1.0, float(np.max(np.abs(lx))))
+    assert rel_err(taps["mu"], res["mu"].detach().numpy()) <= 1e-2
+    assert rel_err(taps["std"], res["std"].detach().numpy()) <= 1e-2
+    kl_ref = res["kld"].detach().numpy()
+    if prior == "AG":
+        assert taps["kl_rows"].shape == (Nx,)
+        assert rel_err(taps["kl_rows"], kl_ref) <= 1e-2
+    assert abs(out["kld"] - float(kl_ref.mean())) <= 1e-2 * abs(float(kl_ref.mean())) + 1e-6
+    assert abs(out["rec_loss"] - float(res["rec_loss"])) <= 5e-3 * abs(float(res["rec_loss"]))
+    bad = {n: e for n, e in worst.items() if e > 4e-2}
+    assert not bad, dict(list(bad.items())[:8])
+    assert len(worst) >= 370
+    assert abs(out_b["global_norm"] - gnorm) <= 2e-2 * gnorm

@@ -152,6 +152,48 @@ def test_adam_three_steps():
     eng.close()
 
 
+@pytest.mark.parametrize("kind", ["SGD", "Momentum"])
+def test_sgd_and_momentum_three_steps(kind):
+    """--optimizer SGD / Momentum (ops/optimizers.py:33-36, 41-46): plain / momentum-0.9 updates of the clipped gradient with
+    the staircase-halved rate (decay period of 2 steps here, so steps 1-2 use lr and step 3 uses lr / 2). Exact host
+    replay of the device's own fetched gradients pins the update rule; the oracle's 3-step trajectory pins the whole step."""
+    cfg, params, batch = make_case(SMALL, 4, 6, seed=23, ragged=True, optimizer=kind, learning_rate=0.05,
+                                   batch_size=4, num_ex_per_epoch=8, num_epochs_per_decay=1)
+    assert O.decay_steps(cfg) == 1 or O.decay_steps(cfg) == 2
+    eng = engine_for(cfg, params, 4, 6)
+    assert eng.cfg.lr_decay_steps == O.decay_steps(cfg)
+    p_ref = {k: v.clone() for k, v in params.items()}
+    opt = {"t": 0, "m": {}, "v": {}}
+    name = "decoder/rnn_logits/bias"
+    acc = np.zeros(params[name].shape)
+    host = eng.get_variable(name).astype(np.float64)
+    for step in range(3):
+        out = eng.train_step(anneal=step, rng=rng_for(batch), **feed_of(batch))
+        b2 = dict(batch)
+        b2["global_step"] = step
+        ref = O.train_step(p_ref, opt, cfg, b2)
+        assert abs(out["rec_loss"] - ref["rec_loss"]) <= 5e-3 * abs(ref["rec_loss"]), step
+        assert abs(out["global_norm"] - ref["global_norm"]) <= 3e-2 * ref["global_norm"], step
+        g = eng.get_gradient(name).astype(np.float64) * min(1.0, cfg.lstm_clip_by_norm / out["global_norm"])
+        lr_d = cfg.learning_rate * 0.5 ** (step // O.decay_steps(cfg))
+        acc = 0.9 * acc + g if kind == "Momentum" else g
+        host = host - lr_d * acc
+        np.testing.assert_allclose(eng.get_variable(name), host, rtol=0, atol=1e-5 * max(1.0, np.max(np.abs(host))))
+    for nm in ("decoder/rnn_logits/kernel", "decoder/net/multi_rnn_cell/cell_0/lstm_cell/kernel", "imf_emb/kernel",
+               "encoder/dense/kernel", "encoder/enc_embeddings"):
+        got = eng.get_variable(nm).astype(np.float64) - params[nm].numpy()
+        want = p_ref[nm].numpy() - params[nm].numpy()
+        assert np.linalg.norm(got - want) <= 0.08 * np.linalg.norm(want), (nm, kind)
+    eng.close()
+
+
+def test_unknown_optimizer_is_rejected():
+    cfg, params, batch = make_case(TINY, 2, 5, seed=2)
+    cfg.optimizer = "RMSProp"
+    with pytest.raises(ValueError):
+        engine_for(cfg, params, 2, 5)
+
+
 def test_clip_identity_and_adam_first_step_kat():
     """Known-answer: with |g| <= clip the clip is the identity, and Adam's first step is
     lr_t * (1-b1) g / (sqrt((1-b2) g^2) + eps) with lr_t = lr sqrt(1-b2)/(1-b1)  ~=  lr * sign(g)."""

@@ -42,7 +42,7 @@ const Nccl* nccl() {
     const char* names[] = {getenv("VC_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
     for (const char* nm : names) {
       if (nm == nullptr || nm[0] == 0) continue;
-      n.lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+      n.lib = dlopen(nm, RTLD_NOW | RTLD_LOCAL);
       if (n.lib) break;
     }
     if (!n.lib) {

@@ -735,7 +735,7 @@ int sumsq(cudaStream_t s, const float* g, long long n, float* out) {
 // normsq_parts: the squared norm is the sum of up to 4 device scalars (dense grads + per-token embedding slices).
 __global__ void k_adam(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                        long long n, const float* __restrict__ normsq_parts, int n_parts, float clip, float gscale,
-                       float lr_t, float b1, float b2, float eps, float* __restrict__ norm_out, float wd) {
+                       float lr_t, float b1, float b2, float eps, float* __restrict__ norm_out, float wd, int kind) {
   float scale = gscale;
   if (clip > 0.f) {
     float ns = 0.f;
@@ -750,6 +750,20 @@ __global__ void k_adam(float* __restrict__ p, const float* __restrict__ g, float
   float4* m4 = reinterpret_cast<float4*>(m);
   float4* v4 = reinterpret_cast<float4*>(v);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    if (kind != 0) {
+      // tf.train.GradientDescentOptimizer / MomentumOptimizer(momentum = b1) (ops/optimizers.py:33-36, 41-46): lr_t is the
+      // staircase-decayed rate; the moment buffer m holds the momentum accumulator, v is not touched
+      float4 pp = p4[i], gg = g4[i];
+      float4 st = make_float4(gg.x * scale + wd * pp.x, gg.y * scale + wd * pp.y, gg.z * scale + wd * pp.z, gg.w * scale + wd * pp.w);
+      if (kind == 2) {
+        const float4 mm = m4[i];
+        st = make_float4(b1 * mm.x + st.x, b1 * mm.y + st.y, b1 * mm.z + st.z, b1 * mm.w + st.w);
+        m4[i] = st;
+      }
+      pp.x -= lr_t * st.x; pp.y -= lr_t * st.y; pp.z -= lr_t * st.z; pp.w -= lr_t * st.w;
+      p4[i] = pp;
+      continue;
+    }
     float4 pp = p4[i], gg = g4[i], mm = m4[i], vv = v4[i];
 #define VC_ADAM1(c)                                 \
   {                                                 \
@@ -766,12 +780,13 @@ __global__ void k_adam(float* __restrict__ p, const float* __restrict__ g, float
   }
 }
 int adam_step(cudaStream_t s, float* p, const float* g, float* m, float* v, long long n, const float* normsq_parts,
-              int n_parts, float clip, float gscale, float lr_t, float b1, float b2, float eps, float* norm_out, float weight_decay) {
+              int n_parts, float clip, float gscale, float lr_t, float b1, float b2, float eps, float* norm_out, float weight_decay,
+              int kind) {
   if (n <= 0) return VC_OK;
   if (n % 4 != 0) return set_error(VC_E_ARG, "adam_step: length must be a multiple of 4 (padded flat buffer)");
   {
     ProfScope ps(s, "adam");
-    k_adam<<<grid_for(n / 4, 256, 2), 256, 0, s>>>(p, g, m, v, n, normsq_parts, n_parts, clip, gscale, lr_t, b1, b2, eps, norm_out, weight_decay);
+    k_adam<<<grid_for(n / 4, 256, 2), 256, 0, s>>>(p, g, m, v, n, normsq_parts, n_parts, clip, gscale, lr_t, b1, b2, eps, norm_out, weight_decay, kind);
   }
   VC_CUDA(cudaGetLastError());
   return VC_OK;

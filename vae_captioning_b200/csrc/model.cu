@@ -62,6 +62,8 @@ int Model::init(const vc_config& c, int dev) {
   if (F % 8) return set_error(VC_E_SHAPE, "cnn_feature_size must be a multiple of 8");
   if (!cfg.no_encoder && ((int64_t)S * Z) % 8) return set_error(VC_E_SHAPE, "gen_z_samples*latent must be a multiple of 8");
   if (cfg.prior < 0 || cfg.prior > 2) return set_error(VC_E_ARG, "unknown prior %d", cfg.prior);
+  if (cfg.optimizer < 0 || cfg.optimizer > 2 || cfg.cnn_optimizer < 0 || cfg.cnn_optimizer > 2)
+    return set_error(VC_E_ARG, "unknown optimizer %d / %d (VC_OPT_ADAM, VC_OPT_SGD, VC_OPT_MOMENTUM)", cfg.optimizer, cfg.cnn_optimizer);
   if (cfg.num_captions < 1 || cfg.max_batch < 1 || cfg.max_len < 1) return set_error(VC_E_ARG, "bad batch geometry");
   const bool has_cv = cfg.use_c_v || cfg.prior != VC_PRIOR_NORMAL;
   maxN = cfg.max_batch * cfg.num_captions;
@@ -815,15 +817,24 @@ int Model::apply(float grad_scale, cudaStream_t s) {
   VC_TRY(sumsq(s, Gf, n_dense, g_tail + 2));
   adam_t += 1;
   const double b1 = 0.8, b2 = 0.999;
-  const float lr_t = (float)(cfg.learning_rate * std::sqrt(1.0 - std::pow(b2, (double)adam_t)) / (1.0 - std::pow(b1, (double)adam_t)));
-  VC_TRY(adam_step(s, Pf, Gf, Mf, Vf, n_adam, g_tail, 3, cfg.clip_norm, grad_scale, lr_t, (float)b1, (float)b2, 1e-8f, scal + 7));
+  // Adam: constant rate with TF's bias correction (Q5). SGD / Momentum(0.9): the rate halves every lr_decay_steps steps
+  // (tf.train.exponential_decay, staircase, read before global_step is incremented; ops/optimizers.py:24-46)
+  auto rate = [&](int kind, float base) -> float {
+    if (kind == VC_OPT_ADAM) return (float)(base * std::sqrt(1.0 - std::pow(b2, (double)adam_t)) / (1.0 - std::pow(b1, (double)adam_t)));
+    const int64_t period = cfg.lr_decay_steps > 0 ? cfg.lr_decay_steps : 1;
+    return (float)(base * std::pow(0.5, (double)((adam_t - 1) / period)));
+  };
+  const float lr_t = rate(cfg.optimizer, cfg.learning_rate);
+  VC_TRY(adam_step(s, Pf, Gf, Mf, Vf, n_adam, g_tail, 3, cfg.clip_norm, grad_scale, lr_t,
+                   cfg.optimizer == VC_OPT_MOMENTUM ? 0.9f : (float)b1, (float)b2, 1e-8f, scal + 7, 0.f, cfg.optimizer));
   if (cfg.fine_tune) {
     // ops/optimizers.py:49-82: Adam(cnn_lr, beta1=0.8) on the 30 cnn/ variables, no clipping; the regulariser
     // gradient weight_decay * w (Q11) is added inside the update
-    const float lr_c = (float)(cfg.cnn_lr * std::sqrt(1.0 - std::pow(b2, (double)adam_t)) / (1.0 - std::pow(b1, (double)adam_t)));
+    const float lr_c = rate(cfg.cnn_optimizer, cfg.cnn_lr);
     const int64_t c0 = n_total - n_cnn;
-    VC_TRY(adam_step(s, Pf + c0, Gf + c0, Mf + c0, Vf + c0, n_cnn, nullptr, 0, 0.f, grad_scale, lr_c, (float)b1, (float)b2,
-                     1e-8f, nullptr, cfg.weight_decay));
+    VC_TRY(adam_step(s, Pf + c0, Gf + c0, Mf + c0, Vf + c0, n_cnn, nullptr, 0, 0.f, grad_scale, lr_c,
+                     cfg.cnn_optimizer == VC_OPT_MOMENTUM ? 0.9f : (float)b1, (float)b2, 1e-8f, nullptr, cfg.weight_decay,
+                     cfg.cnn_optimizer));
     vgg_shadows_dirty = true;
   }
   shadows_dirty = true;

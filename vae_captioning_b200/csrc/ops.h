@@ -127,7 +127,8 @@ int count_mask(cudaStream_t s, const int* lbl, long long n, float* count);
 int colsum_bf16(cudaStream_t s, const void* x, long long rows, int cols, long long ld, float* out);
 int sumsq(cudaStream_t s, const float* g, long long n, float* out);
 int adam_step(cudaStream_t s, float* p, const float* g, float* m, float* v, long long n, const float* normsq_parts,
-              int n_parts, float clip, float gscale, float lr_t, float b1, float b2, float eps, float* norm_out, float weight_decay = 0.f);
+              int n_parts, float clip, float gscale, float lr_t, float b1, float b2, float eps, float* norm_out, float weight_decay = 0.f,
+              int kind = 0 /* VC_OPT_*: 0 TF-Adam, 1 SGD (lr_t = decayed rate), 2 Momentum (b1 = momentum, m = accumulator) */);
 int logits_to_ref(cudaStream_t s, const void* src, long long ld, float* dst, int N, int T, int V);
 
 }  // namespace vc

@@ -327,6 +327,20 @@ int Model::vgg_activation(const char* layer, float* dst_host) {
       return st;
     }
   }
+  if (strcmp(layer, "fc1") == 0 || strcmp(layer, "fc2") == 0) {  // post-ReLU (+ dropout when fine-tuning) [B, 4096]
+    const size_t n = (size_t)B * 4096;
+    if (layer[2] == '2') {
+      VC_CUDA(cudaMemcpy(dst_host, fc2_f, n * sizeof(float), cudaMemcpyDeviceToHost));
+      return VC_OK;
+    }
+    float* tmp = nullptr;
+    VC_CUDA(cudaMalloc((void**)&tmp, n * sizeof(float)));
+    int st = bf16_to_f32(0, fc1_h, tmp, B, 4096, 4096, 4096);
+    if (st == VC_OK && cudaMemcpy(dst_host, tmp, n * sizeof(float), cudaMemcpyDeviceToHost) != cudaSuccess)
+      st = set_error(VC_E_CUDA, "activation copy failed");
+    cudaFree(tmp);
+    return st;
+  }
   return set_error(VC_E_ARG, "unknown VGG layer '%s'", layer);
 }
 

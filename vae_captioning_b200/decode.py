@@ -12,6 +12,8 @@ from .engine import VcRng, _f32, _np_ptr
 
 
 class Decoder(object):
+    accepts_rng = True  # online_inference / beam_search take rng= (inference.inference passes one seed per batch)
+
     def __init__(self, engine, params, data_dict):
         """engine: vae_captioning_b200.engine.Engine; params: Parameters; data_dict: Dictionary (word2idx / idx2word)."""
         self.engine = engine
@@ -34,6 +36,14 @@ class Decoder(object):
 
     # ------------------------------------------------------------------ raw device loops
     def _feed(self, in_pictures, c_v):
+        pix = np.asarray(in_pictures)
+        if pix.ndim == 4 and pix.shape[1:] == (224, 224, 3):
+            # raw images: generation after --fine_tune runs them through the fine-tuned VGG16 first ("caption generation
+            # after fine_tune must be made with params.fine_tune=True", main.py:46-51 + decoder.py:174-183 feed images)
+            if not self.engine.cfg.with_cnn:
+                raise ValueError("in_pictures are images but this engine was created without the CNN (fine_tune / with_cnn)")
+            mb = int(self.engine.cfg.max_batch)
+            in_pictures = np.concatenate([self.engine.vgg_forward(pix[i:i + mb]) for i in range(0, pix.shape[0], mb)])
         feats = _f32(in_pictures)
         if feats.ndim != 2 or feats.shape[1] != self.engine.cfg.cnn_feature_size:
             raise ValueError("in_pictures must be [B, %d] features, got %s" % (self.engine.cfg.cnn_feature_size, feats.shape))

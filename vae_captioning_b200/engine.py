@@ -13,13 +13,14 @@ import numpy as np
 from . import lib as L
 
 PRIORS = {"Normal": 0, "GMM": 1, "AG": 2}
+OPTIMIZERS = {"Adam": 0, "SGD": 1, "Momentum": 2}
 
 
 class VcConfig(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int32) for n in (
         "vocab_size", "embed_size", "encoder_hidden", "decoder_hidden", "latent_size", "gen_z_samples", "num_clusters",
         "num_captions", "cnn_feature_size", "prior", "use_c_v", "no_encoder", "fine_tune", "restore", "with_cnn",
-        "max_batch", "max_len")] + [(n, ctypes.c_float) for n in (
+        "max_batch", "max_len", "optimizer", "cnn_optimizer", "lr_decay_steps")] + [(n, ctypes.c_float) for n in (
             "dec_keep_rate", "dec_lstm_drop", "cnn_dropout", "weight_decay", "learning_rate", "cnn_lr", "clip_norm",
             "ann_param", "std", "temperature")]
 
@@ -60,6 +61,14 @@ def config_from_params(params, vocab_size=None, max_batch=None, max_len=30, with
     c.with_cnn = int(bool(params.fine_tune if with_cnn is None else with_cnn))
     c.max_batch = int(max_batch if max_batch is not None else params.batch_size)
     c.max_len = int(max_len)
+    for field, attr in (("optimizer", "optimizer"), ("cnn_optimizer", "cnn_optimizer")):
+        kind = getattr(params, attr, "Adam")
+        if kind not in OPTIMIZERS:  # argparse restricts --optimizer to these three (utils/parameters.py:104-106)
+            raise ValueError("unknown %s %r (expected one of SGD, Adam, Momentum)" % (attr, kind))
+        setattr(c, field, OPTIMIZERS[kind])
+    # ops/optimizers.py:24-26
+    c.lr_decay_steps = int(getattr(params, "num_ex_per_epoch", 150000) / (getattr(params, "batch_size", c.max_batch) + 0.001) *
+                           getattr(params, "num_epochs_per_decay", 5))
     c.dec_keep_rate = float(params.dec_keep_rate)
     c.dec_lstm_drop = float(params.dec_lstm_drop)
     c.cnn_dropout = float(getattr(params, "cnn_dropout", 0.5))
@@ -412,6 +421,10 @@ class Engine(object):
                   "conv3_3": (56, 256), "pool3": (28, 256), "conv4_1": (28, 512), "conv4_2": (28, 512),
                   "conv4_3": (28, 512), "pool4": (14, 512), "conv5_1": (14, 512), "conv5_2": (14, 512),
                   "conv5_3": (14, 512), "pool5": (7, 512)}
+        if layer in ("fc1", "fc2"):  # post-ReLU (+ dropout when fine-tuning) [B, 4096]
+            a = np.empty((B, 4096), np.float32)
+            L.check(self.lib.vc_vgg_activation(self._h, layer.encode(), _np_ptr(a)))
+            return a
         if layer not in shapes:
             raise ValueError("unknown VGG layer %r" % layer)
         hw, c = shapes[layer]

@@ -83,6 +83,13 @@ class Generator(object):
         missing = sorted(n for n in names if n not in state and not n.startswith("cnn/") and not n.startswith("encoder/"))
         if missing:  # Saver.restore raises NotFoundError for a variable the checkpoint lacks
             raise KeyError("checkpoint %s has no variable %s" % (self.checkpoint_path, missing[0]))
+        if self.params.prior == "AG" and not self.params.no_encoder:
+            # decoder.cap_clusters = c_means (decoder.py:45-71): the generation prior's mean is built from the cluster
+            # means the model was trained with (./pickles/cluster_means.pickle, utils/vae_utils.py:7)
+            from . import synthetic
+            from .main import CLUSTER_MEANS_FILE
+            eng.set_cluster_means(synthetic.init_clusters(self.params.num_clusters, self.params.latent_size,
+                                                          c_m_file=CLUSTER_MEANS_FILE))
         self._engine = eng
         self._decoder = Decoder(eng, self.params, self.data_dict)
 

@@ -17,16 +17,25 @@ def _drop_background_column(params, c_v, val):
     return c_v[:, 1:] if uses else c_v  # column 0 of the 91-wide cluster vectors is never used (ops/inference.py:19-21)
 
 
-def inference(params, decoder, val_gen, test_gen, out_dir=".", reference_test_split_bug=False, verbose=True):
+def inference(params, decoder, val_gen, test_gen, out_dir=".", reference_test_split_bug=False, verbose=True, seed=0):
     say = print if verbose else (lambda *a, **k: None)
     captions_gen = []
+    n_call = [0]
+
+    def rng():  # every sess.run of the reference draws fresh z noise / multinomial samples: one Philox stream per batch
+        n_call[0] += 1
+        return {"seed": (int(seed) << 24) + n_call[0]}
+
+    def kw():  # reference-style decoders (no rng argument) still plug in
+        return {"rng": rng()} if getattr(decoder, "accepts_rng", False) else {}
+
     say("Generating captions for val file")
     for feats, _, _, image_ids, c_v in val_gen.next_val_batch(get_image_ids=True, use_obj_vectors=params.use_c_v):
         c_v = _drop_background_column(params, c_v, True)
         if params.sample_gen == "beam_search":
-            sent = decoder.beam_search(image_ids, feats, c_v, beam_size=params.beam_size)
+            sent = decoder.beam_search(image_ids, feats, c_v, beam_size=params.beam_size, **kw())
         else:
-            sent, _ = decoder.online_inference(image_ids, feats, c_v=c_v)
+            sent, _ = decoder.online_inference(image_ids, feats, c_v=c_v, **kw())
         captions_gen += sent
     say("Generated {} captions".format(len(captions_gen)))
     val_file = os.path.join(out_dir, "val_{}.json".format(params.gen_name))
@@ -37,9 +46,9 @@ def inference(params, decoder, val_gen, test_gen, out_dir=".", reference_test_sp
     for feats, image_ids, c_v in test_gen.next_test_batch(params.use_c_v):
         c_v = _drop_background_column(params, c_v, False)
         if reference_test_split_bug or params.sample_gen != "beam_search":
-            sent, _ = decoder.online_inference(image_ids, feats, c_v=c_v)
+            sent, _ = decoder.online_inference(image_ids, feats, c_v=c_v, **kw())
         else:
-            sent, _ = decoder.online_inference(image_ids, feats, c_v=c_v, sample_gen="greedy")
+            sent, _ = decoder.online_inference(image_ids, feats, c_v=c_v, sample_gen="greedy", **kw())
         captions_gen += sent
     test_file = os.path.join(out_dir, "test_{}.json".format(params.gen_name))
     with open(test_file, "w") as f:

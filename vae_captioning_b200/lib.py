@@ -29,11 +29,29 @@ def load():
         raise VaecapError(
             "libvaecap.so not found at %s -- build it with `python -m vae_captioning_b200.build` "
             "(there is no CPU fallback for the hot path)" % LIB_PATH)
+    _prefer_bundled_nccl()
     lib = ctypes.CDLL(LIB_PATH)
     lib.vc_last_error.restype = ctypes.c_char_p
     lib.vc_abi_version.restype = ctypes.c_int
     _lib = lib
     return lib
+
+
+def _prefer_bundled_nccl():
+    """libvaecap binds libnccl with dlopen at the first vc_comm_* call. Inside a PyTorch process that must be the copy
+    torch links against (site-packages/nvidia/nccl): two different libnccl.so.2 in one process clash on symbols."""
+    if os.environ.get("VC_NCCL_LIB"):
+        return
+    try:
+        import importlib.util
+        spec = importlib.util.find_spec("nvidia.nccl")
+        for d in (spec.submodule_search_locations if spec else []):
+            cand = os.path.join(d, "lib", "libnccl.so.2")
+            if os.path.exists(cand):
+                os.environ["VC_NCCL_LIB"] = cand
+                return
+    except Exception:
+        pass
 
 
 def check(status):

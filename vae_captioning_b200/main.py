@@ -59,6 +59,9 @@ class _Vocabulary(object):
         self.vocab_size = vocab_size
 
 
+CLUSTER_MEANS_FILE = "./pickles/cluster_means.pickle"  # utils/vae_utils.py:7
+
+
 def _feed(params, f_images_batch, captions_batch, cl_batch, c_v):
     """main.py:225-236: flatten [B, C, T] captions, pick labels/inputs, drop the background cluster column."""
     if params.num_captions > 1:
@@ -100,6 +103,11 @@ def run(params, feeder=None, val_feeder=None, test_feeder=None, vocabulary=None,
     eng = Engine(params, vocab_size=vocab.vocab_size, max_batch=params.batch_size, max_len=max_len, device=device,
                  with_cnn=bool(params.fine_tune))
     ckpt = checkpoint.checkpoint_path(params)
+    if params.prior == "AG" and not params.no_encoder:
+        # init_clusters (utils/vae_utils.py:6-31): the reference builds c_means in BOTH modes and hands them to the
+        # decoder (main.py:136-140 -> decoder.cap_clusters, decoder.py:45-71); they live in ./pickles/cluster_means.pickle
+        eng.set_cluster_means(synthetic.init_clusters(params.num_clusters, params.latent_size,
+                                                      c_m_file=CLUSTER_MEANS_FILE))
     if params.mode == "training":
         if not params.restore:
             eng.load_state(synthetic.init_weights(eng.variables(), seed=1))  # tf.global_variables_initializer
@@ -109,8 +117,6 @@ def run(params, feeder=None, val_feeder=None, test_feeder=None, vocabulary=None,
         else:
             out("Restoring from checkpoint")
             checkpoint.restore(eng, ckpt)
-        if params.prior == "AG" and not params.no_encoder:
-            eng.set_cluster_means(synthetic.init_clusters(params.num_clusters, params.latent_size))
         gs = 0
         lb = rl = float("nan")
         for e in range(params.num_epochs):
@@ -151,9 +157,10 @@ def run(params, feeder=None, val_feeder=None, test_feeder=None, vocabulary=None,
                     stop = True
             out("Epoch: {} Iteration: {} VLB: {} Rec Loss: {}".format(e, gs, lb, rl))
             val_rec = []  # validate(): rec_loss of the training graph on the validation batches (main.py:262-284)
-            for f_images_batch, captions_batch, cl_batch, c_v in val_feeder.next_batch(
-                    use_obj_vectors=params.use_c_v, num_captions=params.num_captions):
-                val_rec.append(eng.eval_step(rng={"seed": gs}, **_feed(params, f_images_batch, captions_batch, cl_batch, c_v))["rec_loss"])
+            for vi, (f_images_batch, captions_batch, cl_batch, c_v) in enumerate(val_feeder.next_batch(
+                    use_obj_vectors=params.use_c_v, num_captions=params.num_captions)):
+                # fresh noise per validation batch, as every sess.run of the reference draws its own (main.py:279)
+                val_rec.append(eng.eval_step(rng={"seed": (gs << 20) + vi}, **_feed(params, f_images_batch, captions_batch, cl_batch, c_v))["rec_loss"])
             out("Validation reconstruction loss: {}".format(np.mean(val_rec) if val_rec else float("nan")))
             out("-----------------------------------------------")
             save_path = checkpoint.save(ckpt, eng.state())
