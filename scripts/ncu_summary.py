@@ -26,9 +26,15 @@ def main(path):
         for i, h in enumerate(hdr):
             if any(k in h for k in KEYS):
                 print("   %-75s %s %s" % (h, r[i], units[i]))
-        rd = float(d.get("dram__bytes_read.sum", "0").replace(",", "") or 0)
-        wr = float(d.get("dram__bytes_write.sum", "0").replace(",", "") or 0)
-        print("   traffic(dram read+write) = %s %s" % (rd + wr, units[hdr.index("dram__bytes_read.sum")] if "dram__bytes_read.sum" in hdr else ""))
+        # ncu picks a unit per column (byte / Kbyte / Mbyte / Gbyte): convert both to bytes before adding
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+
+        def in_bytes(col):
+            if col not in hdr:
+                return 0.0
+            return float((d.get(col, "0") or "0").replace(",", "")) * scale.get(units[hdr.index(col)], 1.0)
+
+        print("   traffic(dram read+write) = %.3f MB" % ((in_bytes("dram__bytes_read.sum") + in_bytes("dram__bytes_write.sum")) / 1e6))
 
 
 if __name__ == "__main__":

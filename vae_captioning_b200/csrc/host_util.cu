@@ -164,6 +164,29 @@ int make_tmap_2d_f32(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t
   return VC_OK;
 }
 
+int make_tmap_3d(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t rows, uint64_t slots, uint64_t ld,
+                 uint64_t slot_pitch, uint32_t box_inner, uint32_t box_rows, bool f32) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return set_error(VC_E_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  const uint64_t es = f32 ? 4 : 2;
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || ((ld * es) & 15) || ((slot_pitch * es) & 15))
+    return set_error(VC_E_ARG, "TMA operand must be 16-byte aligned with 16-byte pitches (ptr=%p ld=%llu)", ptr,
+                     (unsigned long long)ld);
+  cuuint64_t dims[3] = {inner, rows, slots};
+  cuuint64_t strides[2] = {ld * es, slot_pitch * es};
+  if (box_inner * es != 128 && box_inner * es != 64) return set_error(VC_E_ARG, "make_tmap_3d: box rows must be 64 or 128 bytes");
+  cuuint32_t box[3] = {box_inner, box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(out, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr),
+                  dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  box_inner * es == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,  // swizzle span = box row
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return set_error(VC_E_CUDA, "cuTensorMapEncodeTiled(3d inner=%llu rows=%llu slots=%llu ld=%llu) -> %d",
+                     (unsigned long long)inner, (unsigned long long)rows, (unsigned long long)slots, (unsigned long long)ld, (int)r);
+  return VC_OK;
+}
+
 int make_tmap_nhwc(CUtensorMap* out, const void* ptr, int C, int W, int H, int N, int bw, int bh, int bi) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return set_error(VC_E_CUDA, "cuTensorMapEncodeTiled entry point unavailable");

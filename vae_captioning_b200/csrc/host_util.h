@@ -56,6 +56,11 @@ int make_tmap_2d(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t out
                  uint32_t box_outer);
 // fp32 [outer, inner] row-major (row pitch ld floats), box {32, box_outer}, 128B swizzle (store side of EpiTmaF32)
 int make_tmap_2d_f32(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_outer);
+// 3-D maps {inner, rows, slots} for tensors stored as [slots][rows][ld]: a box never crosses a slot, rows past `rows` are
+// zero on load and dropped on store (the 2-D maps above run straight into the next slot). Box {box_inner, box_rows, 1}
+// with rows of 128 bytes (128B swizzle) or 64 bytes (64B swizzle).
+int make_tmap_3d(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t rows, uint64_t slots, uint64_t ld,
+                 uint64_t slot_pitch, uint32_t box_inner, uint32_t box_rows, bool f32);
 // 4-D bf16 NHWC tensor map {C, W, H, N} with box {64, bw, bh, bi}, 128B swizzle.
 int make_tmap_nhwc(CUtensorMap* out, const void* ptr, int C, int W, int H, int N, int bw, int bh, int bi);
 

@@ -637,7 +637,14 @@ bool lstm_seq_applicable(int N, int H, int steps) {
 
 int lstm_seq_flag_count(int N, int steps) { return ((N + kBM - 1) / kBM) * (steps + 2); }
 
+// VC_LSTM_SEQ=1 selects the first form below (kept for A/B timing); the default is lstm_seq2.cu
+static bool use_seq2() {
+  static const bool v2 = [] { const char* e = getenv("VC_LSTM_SEQ"); return !(e && e[0] == '1'); }();
+  return v2;
+}
+
 int lstm_fwd_seq(cudaStream_t stream, const LstmSeqFwdArgs& a) {
+  if (use_seq2()) return lstm_fwd_seq2(stream, a);
   if (a.H % 64 != 0 || a.E % kBK != 0) return set_error(VC_E_SHAPE, "LSTM sizes must be multiples of 64 (E=%d H=%d)", a.E, a.H);
   const long long rows = (long long)a.steps * a.N;
   CUtensorMap tmX, tmH, tmW;
@@ -673,6 +680,7 @@ int lstm_fwd_seq(cudaStream_t stream, const LstmSeqFwdArgs& a) {
 
 // Steps steps-2 .. 0 of BPTT's recurrent part (the last step has no recurrent input and runs in k_lstm_bwd_last).
 int lstm_bwd_seq(cudaStream_t stream, const LstmSeqBwdArgs& a) {
+  if (use_seq2()) return lstm_bwd_seq2(stream, a);
   if (a.H % 64 != 0) return set_error(VC_E_SHAPE, "LSTM hidden size must be a multiple of 64");
   if (a.steps < 2) return VC_OK;
   const long long rows = (long long)a.steps * a.N;

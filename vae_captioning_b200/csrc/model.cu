@@ -162,6 +162,7 @@ int Model::init(const vc_config& c, int dev) {
     L.pre = pre;
     L.steps = pre + T;
     VC_TRY(dalloc((uint16_t**)&L.w_t_perm, (size_t)4 * H * (E + H)));
+    if (lstm_seq_units(N, H) == 32) VC_TRY(dalloc((uint16_t**)&L.w_t_perm32, (size_t)4 * H * (E + H)));
     VC_TRY(dalloc((uint16_t**)&L.w_nat, (size_t)4 * H * (E + H)));
     VC_TRY(dalloc((uint16_t**)&L.X, (size_t)L.steps * N * E));
     VC_TRY(dalloc((uint16_t**)&L.Hs, (size_t)(L.steps + 1) * N * H));
@@ -303,6 +304,7 @@ int Model::refresh_shadows(cudaStream_t s) {
   if (cv_wt) VC_TRY(transpose_cast(s, pp(pidx("cv_emb/kernel")), cv_wt, K, E, E, KP, 0, 0));
   auto lstm = [&](LstmNet& L) -> int {
     VC_TRY(transpose_cast(s, pp(L.p_kernel), L.w_t_perm, L.E + L.H, 4 * L.H, 4 * L.H, L.E + L.H, L.H, 64));
+    if (L.w_t_perm32) VC_TRY(transpose_cast(s, pp(L.p_kernel), L.w_t_perm32, L.E + L.H, 4 * L.H, 4 * L.H, L.E + L.H, L.H, 32));
     VC_TRY(cast_f32_bf16(s, pp(L.p_kernel), L.w_nat, L.E + L.H, 4 * L.H, 4 * L.H, 4 * L.H));
     return VC_OK;
   };
@@ -438,6 +440,7 @@ int Model::lstm_forward(LstmNet& L, int N, int T, const int32_t* len, void* out,
     LstmSeqFwdArgs a{};
     a.X = X; a.Hs = Hs; a.Cs = L.Cs; a.G = Gt; a.out = out;
     a.w_t_perm = L.w_t_perm;
+    a.w_t_perm32 = L.w_t_perm32;
     a.bias = pp(L.p_bias);
     a.lengths = len;
     a.out_keep = out_keep;

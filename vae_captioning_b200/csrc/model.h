@@ -28,6 +28,7 @@ struct LstmNet {
   int p_kernel = -1, p_bias = -1;
   int E = 0, H = 0, pre = 0, steps = 0;
   void* w_t_perm = nullptr;  // bf16 [4H interleaved, E+H]
+  void* w_t_perm32 = nullptr;  // interleaved per 32 units: lstm_seq2's 16-CTA-per-row-tile form (batches of <= 1152 rows)
   void* w_nat = nullptr;     // bf16 [E+H, 4H]
   void* X = nullptr;         // bf16 [steps, N, E]
   void* Hs = nullptr;        // bf16 [steps+1, N, H]

@@ -59,6 +59,7 @@ struct LstmSeqFwdArgs {
   void* G;               // bf16 [steps, N, 4H] activated gates (for BPTT)
   void* out;             // bf16 [T, N, H] emitted outputs of the caption steps (nullable)
   const void* w_t_perm;  // bf16 [4H gate-interleaved, E+H]
+  const void* w_t_perm32 = nullptr;  // the same, gate-interleaved per 32 hidden units (16-CTA-per-row-tile form; nullable)
   const float* bias;
   const int* lengths;    // nullable
   const float* out_keep; // nullable [N, T, H]
@@ -82,8 +83,11 @@ struct LstmSeqBwdArgs {
 };
 bool lstm_seq_applicable(int N, int H, int steps);
 int lstm_seq_flag_count(int N, int steps);
+int lstm_seq_units(int N, int H);  // hidden units per CTA the second form uses for N rows: 32 or 64
 int lstm_fwd_seq(cudaStream_t stream, const LstmSeqFwdArgs& a);
 int lstm_bwd_seq(cudaStream_t stream, const LstmSeqBwdArgs& a);
+int lstm_fwd_seq2(cudaStream_t stream, const LstmSeqFwdArgs& a);  // lstm_seq2.cu: TMA-store hand-over of the recurrent operand
+int lstm_bwd_seq2(cudaStream_t stream, const LstmSeqBwdArgs& a);
 
 // vgg_bwd.cu -------------------------------------------------------------------------------
 int conv3x3_wgrad(cudaStream_t s, const void* x, const void* dy, float* dw, int B, int hw, int cin, int cout,
