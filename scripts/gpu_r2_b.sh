@@ -1,15 +1,14 @@
 #!/bin/bash
 set -u
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_train_step_gpu.py tests/test_full_size_gpu.py tests/test_dp_gpu.py tests/test_main_gpu.py -m gpu -q -x > gpurun_out/pytest_lstm2.log 2>&1; echo "pytest rc=$?"; tail -5 gpurun_out/pytest_lstm2.log
 Q="--steps 10 --warmup 3 --no-e2e --no-cpu-baseline --no-extra-configs"
-for V in 2; do
+for V in 2 1; do
   VC_LSTM_SEQ=$V timeout 200 python bench.py --workload feats_normal_b256 $Q > gpurun_out/lstm_v${V}_n1280.json 2> gpurun_out/lstm_v${V}_n1280.err; echo "v$V n1280 rc=$?"
   VC_LSTM_SEQ=$V timeout 200 python bench.py --workload cfg3_feats_gmm_cv_b128 $Q > gpurun_out/lstm_v${V}_n640.json 2> gpurun_out/lstm_v${V}_n640.err; echo "v$V n640 rc=$?"
 done
 python - <<'PY'
 import json
-for f in ("lstm_v2_n1280","lstm_v2_n640"):
+for f in ("lstm_v2_n1280","lstm_v1_n1280","lstm_v2_n640","lstm_v1_n640"):
     try:
         d=json.loads(open("gpurun_out/%s.json"%f).read())
         fam=d["families"]

@@ -184,6 +184,12 @@ int Model::grad_ready_params(std::initializer_list<int> ids, cudaStream_t s) {
   int64_t r[16][2];
   int n = 0;
   for (int pi : ids) {
+    if (pi == -2 && n < 16) {  // the 64-float tail behind the clipped-Adam region (embedding-slice squared norms, Q4)
+      r[n][0] = n_adam;
+      r[n][1] = 64;
+      ++n;
+      continue;
+    }
     if (pi < 0) continue;
     const ParamInfo& p = params[pi];
     if (p.parent >= 0 || p.region == 1) continue;

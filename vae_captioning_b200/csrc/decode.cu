@@ -322,7 +322,7 @@ int Model::decode_begin(const float* feats_dev, const float* c_v_dev, int B, con
   DecodeWs* w = dws;
   const bool has_cv = cfg.use_c_v || cfg.prior != VC_PRIOR_NORMAL;
   if (has_cv && c_v_dev == nullptr) return set_error(VC_E_ARG, "this configuration needs cluster vectors (c_v)");
-  if (shadows_dirty) VC_TRY(refresh_shadows(s));
+  VC_TRY(refresh_decode_shadows(s));
   VC_TRY(cast_f32_bf16(s, feats_dev, w->feats_h, B, F, F, F));
   // Generation runs its two long contractions (imf_emb K = 4096, z_rnn K = S*Z = 15000) un-split: split-K meets in fp32
   // atomics whose order changes from run to run, and a 1e-7 wobble in the initial state is enough to flip a bf16

@@ -702,7 +702,11 @@ int colsum_bf16(cudaStream_t s, const void* x, long long rows, int cols, long lo
 // Global norm (sum of squares into *out) and fused clip + TF-form Adam (Q5):
 //   g' = g * clip / max(sqrt(normsq), clip);  m = b1 m + (1-b1) g';  v = b2 v + (1-b2) g'^2;
 //   p -= lr_t * m / (sqrt(v) + eps),  lr_t = lr sqrt(1-b2^t)/(1-b1^t) (computed by the host).
-__global__ void k_sumsq(const float* __restrict__ g, long long n, float* __restrict__ out) {
+// Deterministic: block partials land in `partial`, the block that finishes last adds them up in index order. (Partial sums
+// meeting in atomicAdd made the global norm differ in its last bits from run to run -- and between data-parallel replicas,
+// whose clip scale and therefore whose parameters then drifted apart by ulps.)
+__global__ void k_sumsq(const float* __restrict__ g, long long n, float* __restrict__ out, float* __restrict__ partial,
+                        unsigned int* __restrict__ counter) {
   float acc = 0.f;
   const long long n4 = n / 4;
   const float4* g4 = reinterpret_cast<const float4*>(g);
@@ -716,17 +720,46 @@ __global__ void k_sumsq(const float* __restrict__ g, long long n, float* __restr
   __shared__ float red[32];
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
   __syncthreads();
+  __shared__ bool last;
   if (threadIdx.x < 32) {
     float a = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
     a = warp_sum(a);
-    if (threadIdx.x == 0 && a != 0.f) atomicAdd(out, a);
+    if (threadIdx.x == 0) {
+      partial[blockIdx.x] = a;
+      __threadfence();
+      last = atomicInc(counter, gridDim.x - 1) == gridDim.x - 1;  // wraps to 0: ready for the next launch
+    }
+  }
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  float a = 0.f;
+  for (unsigned int i = threadIdx.x; i < gridDim.x; i += blockDim.x) a += __ldcg(partial + i);
+  a = warp_sum(a);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = a;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float t = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+    t = warp_sum(t);
+    if (threadIdx.x == 0) *out += t;  // the caller zeroes `out`; one writer
   }
 }
 int sumsq(cudaStream_t s, const float* g, long long n, float* out) {
   if (n <= 0) return VC_OK;
+  static float* partial = nullptr;  // one GPU per process (include/vaecap.h): scratch shared by every handle's launches
+  static unsigned int* counter = nullptr;
+  constexpr int kMaxBlocks = 8192;
+  if (partial == nullptr) {
+    VC_CUDA(cudaMalloc((void**)&partial, kMaxBlocks * sizeof(float)));
+    VC_CUDA(cudaMalloc((void**)&counter, sizeof(unsigned int)));
+    VC_CUDA(cudaMemset(counter, 0, sizeof(unsigned int)));
+  }
+  int grid = grid_for(n, 256, 8);
+  if (grid > kMaxBlocks) grid = kMaxBlocks;
   {
     ProfScope ps(s, "sumsq");
-    k_sumsq<<<grid_for(n, 256, 8), 256, 0, s>>>(g, n, out);
+    k_sumsq<<<grid, 256, 0, s>>>(g, n, out, partial, counter);
   }
   VC_CUDA(cudaGetLastError());
   return VC_OK;

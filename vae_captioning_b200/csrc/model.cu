@@ -153,7 +153,9 @@ int Model::init(const vc_config& c, int dev) {
   // ---- shadows
   const int N = maxN, T = maxT;
   VC_TRY(dalloc((uint16_t**)&imf_wt, (size_t)E * F));
+  VC_TRY(dalloc((uint16_t**)&imf_nat, (size_t)F * E));
   if (has_cv) VC_TRY(dalloc((uint16_t**)&cv_wt, (size_t)E * KP));
+  if (has_cv) VC_TRY(dalloc((uint16_t**)&cv_nat, (size_t)KP * E));
   auto setup_lstm = [&](LstmNet& L, const char* kname, const char* bname, int H, int pre) -> int {
     L.p_kernel = pidx(kname);
     L.p_bias = pidx(bname);
@@ -181,7 +183,6 @@ int Model::init(const vc_config& c, int dev) {
   VC_TRY(setup_lstm(dec, "decoder/net/multi_rnn_cell/cell_0/lstm_cell/kernel",
                     "decoder/net/multi_rnn_cell/cell_0/lstm_cell/bias", Hd, 1 + cvstep + (cfg.no_encoder ? 0 : 1)));
   if (!cfg.no_encoder) {
-    VC_TRY(dalloc((uint16_t**)&heads_wt, (size_t)heads_cols * He));
     VC_TRY(dalloc((uint16_t**)&heads_nat, (size_t)He * heads_cols));
     heads_bias = pp(p_heads_b);
     VC_TRY(dalloc((uint16_t**)&z_wt, (size_t)E * S * Z));
@@ -295,13 +296,16 @@ int Model::set_cluster_means(const float* src) {
 }
 
 // ------------------------------------------------------------------------------------------
+// bf16 operand shadows of the fp32 master weights, rebuilt after every optimiser step. The train / eval graph reads every
+// dense kernel in its NATURAL [in, out] layout (MN-major B operand of the tcgen05 GEMMs, K-major B of the dgrad GEMMs), so
+// the per-step refresh is plain casts plus the gate-interleaved LSTM kernels; the transposed copies the generation path
+// uses (decode.cu) are rebuilt lazily, the first time a decode call follows a weight change (refresh_decode_shadows).
 int Model::refresh_shadows(cudaStream_t s) {
   ProfTag ptag("refresh_shadows");
   const int E = cfg.embed_size, Z = cfg.latent_size, S = cfg.gen_z_samples, V = cfg.vocab_size, F = cfg.cnn_feature_size,
             K = cfg.num_clusters;
-  VC_TRY(transpose_cast(s, pp(pidx("imf_emb/kernel")), imf_wt, F, E, E, F, 0, 0));
-  if (imf_nat) VC_TRY(cast_f32_bf16(s, pp(pidx("imf_emb/kernel")), imf_nat, F, E, E, E));
-  if (cv_wt) VC_TRY(transpose_cast(s, pp(pidx("cv_emb/kernel")), cv_wt, K, E, E, KP, 0, 0));
+  VC_TRY(cast_f32_bf16(s, pp(pidx("imf_emb/kernel")), imf_nat, F, E, E, E));
+  if (cv_nat) VC_TRY(cast_f32_bf16(s, pp(pidx("cv_emb/kernel")), cv_nat, K, E, E, E));
   auto lstm = [&](LstmNet& L) -> int {
     VC_TRY(transpose_cast(s, pp(L.p_kernel), L.w_t_perm, L.E + L.H, 4 * L.H, 4 * L.H, L.E + L.H, L.H, 64));
     if (L.w_t_perm32) VC_TRY(transpose_cast(s, pp(L.p_kernel), L.w_t_perm32, L.E + L.H, 4 * L.H, 4 * L.H, L.E + L.H, L.H, 32));
@@ -311,19 +315,32 @@ int Model::refresh_shadows(cudaStream_t s) {
   if (!cfg.no_encoder) {
     VC_TRY(lstm(enc));
     const int He = cfg.encoder_hidden;
-    VC_TRY(transpose_cast(s, pp(p_heads_w), heads_wt, He, heads_cols, heads_cols, He, 0, 0));
     VC_TRY(cast_f32_bf16(s, pp(p_heads_w), heads_nat, He, heads_cols, heads_cols, heads_cols));
     const int pz = pidx("decoder/net/z_rnn/kernel");
-    VC_TRY(transpose_cast(s, pp(pz), z_wt, S * Z, E, E, (int64_t)S * Z, 0, 0));
     VC_TRY(cast_f32_bf16(s, pp(pz), z_nat, (int64_t)S * Z, E, E, E));
     VC_TRY(cast_f32_bf16(s, pp(pidx("encoder/enc_embeddings")), enc_emb_h, V, E, E, E));
   }
   VC_TRY(lstm(dec));
   const int po = pidx("decoder/rnn_logits/kernel");
-  VC_TRY(transpose_cast(s, pp(po), wo_t, cfg.decoder_hidden, V, V, cfg.decoder_hidden, 0, 0));
   VC_TRY(cast_f32_bf16(s, pp(po), wo_nat, cfg.decoder_hidden, V, V, VP));
   VC_TRY(cast_f32_bf16(s, pp(pidx("decoder/net/dec_embeddings")), dec_emb_h, V, E, E, E));
   shadows_dirty = false;
+  decode_shadows_dirty = true;
+  return VC_OK;
+}
+
+int Model::refresh_decode_shadows(cudaStream_t s) {
+  if (shadows_dirty) VC_TRY(refresh_shadows(s));
+  if (!decode_shadows_dirty) return VC_OK;
+  ProfTag ptag("refresh_shadows");
+  const int E = cfg.embed_size, Z = cfg.latent_size, S = cfg.gen_z_samples, V = cfg.vocab_size, F = cfg.cnn_feature_size,
+            K = cfg.num_clusters;
+  VC_TRY(transpose_cast(s, pp(pidx("imf_emb/kernel")), imf_wt, F, E, E, F, 0, 0));
+  if (cv_wt) VC_TRY(transpose_cast(s, pp(pidx("cv_emb/kernel")), cv_wt, K, E, E, KP, 0, 0));
+  if (!cfg.no_encoder)
+    VC_TRY(transpose_cast(s, pp(pidx("decoder/net/z_rnn/kernel")), z_wt, S * Z, E, E, (int64_t)S * Z, 0, 0));
+  VC_TRY(transpose_cast(s, pp(pidx("decoder/rnn_logits/kernel")), wo_t, cfg.decoder_hidden, V, V, cfg.decoder_hidden, 0, 0));
+  decode_shadows_dirty = false;
   return VC_OK;
 }
 
@@ -586,7 +603,7 @@ int Model::forward(const StepInputs& in, bool write_grad, cudaStream_t s) {
   VC_TRY(cast_f32_bf16(s, feats, feats_h, B, F, F, F));
   VC_CUDA(cudaMemsetAsync(imf_f, 0, (size_t)B * E * sizeof(float), s));
   {
-    Operand A{feats_h, B, F, F, false}, Bw{imf_wt, E, F, F, false};
+    Operand A{feats_h, B, F, F, false}, Bw{imf_nat, F, E, E, true};
     EpiStore e{};
     e.out = imf_f; e.ld = E; e.bias = pp(pidx("imf_emb/bias")); e.atomic = 1; e.alpha = 1.f;
     ProfTag ptag("imf_emb");
@@ -596,7 +613,7 @@ int Model::forward(const StepInputs& in, bool write_grad, cudaStream_t s) {
   if (has_cv) {  // main.py:103-114
     VC_TRY(cast_f32_bf16(s, in.c_v, cv_h, N, K, K, KP));
     if (cfg.use_c_v) {
-      Operand A{cv_h, N, K, KP, false}, Bw{cv_wt, E, K, KP, false};
+      Operand A{cv_h, N, K, KP, false}, Bw{cv_nat, K, E, E, true};
       EpiStore e{};
       e.out = cv_f; e.ld = E; e.bias = pp(pidx("cv_emb/bias")); e.alpha = 1.f;
       ProfTag ptag("cv_emb");
@@ -612,7 +629,7 @@ int Model::forward(const StepInputs& in, bool write_grad, cudaStream_t s) {
     VC_TRY(lstm_forward(enc, N, T, in.len, nullptr, nullptr, s));
     const uint16_t* hT = (uint16_t*)enc.Hs + (size_t)(enc.pre + T) * N * He;
     {
-      Operand A{hT, N, He, He, false}, Bw{heads_wt, heads_cols, He, He, false};
+      Operand A{hT, N, He, He, false}, Bw{heads_nat, He, heads_cols, heads_cols, true};
       EpiStore e{};
       e.out = heads_f; e.ld = heads_cols; e.bias = heads_bias; e.alpha = 1.f;
       ProfTag ptag("heads");
@@ -633,7 +650,7 @@ int Model::forward(const StepInputs& in, bool write_grad, cudaStream_t s) {
     VC_CUDA(cudaMemsetAsync(zdec_f, 0, (size_t)N * E * sizeof(float), s));
     {
       const int SZ = S * Z;
-      Operand A{z, N, SZ, SZ, false}, Bw{z_wt, E, SZ, SZ, false};
+      Operand A{z, N, SZ, SZ, false}, Bw{z_nat, SZ, E, E, true};
       EpiStore e{};
       e.out = zdec_f; e.ld = E; e.bias = pp(pidx("decoder/net/z_rnn/bias")); e.atomic = 1; e.alpha = 1.f;
       const int tiles = ((N + 127) / 128) * ((E + 127) / 128);
@@ -647,7 +664,7 @@ int Model::forward(const StepInputs& in, bool write_grad, cudaStream_t s) {
                       cfg.dec_keep_rate < 1.f ? in.rng.emb_keep_dev : nullptr, 1.f / cfg.dec_keep_rate, N, T, E, V));
   VC_TRY(lstm_forward(dec, N, T, in.len, Out, cfg.dec_lstm_drop < 1.f ? in.rng.out_keep_dev : nullptr, s));
   {
-    Operand A{Out, (long long)T * N, Hd, Hd, false}, Bw{wo_t, V, Hd, Hd, false};
+    Operand A{Out, (long long)T * N, Hd, Hd, false}, Bw{wo_nat, Hd, V, VP, true};
     ProfTag ptag("logits_fwd");
     VC_TRY(gemm_tma_rows(s, A, Bw, T * N, V, Hd, logits, VP, pp(pidx("decoder/rnn_logits/bias")), 0, 256));
   }
@@ -803,11 +820,10 @@ int Model::backward(const StepInputs& in, cudaStream_t s) {
   if (comm != nullptr) {
     // last bucket: encoder LSTM + table, the two small projections, and the 64-float tail whose first two entries are
     // the per-token embedding-slice squared norms of this rank (Q4: the norm is over every tower's slices)
-    if (!cfg.no_encoder) VC_TRY(grad_ready_params({enc.p_kernel, enc.p_bias, pidx("encoder/enc_embeddings")}, s));
+    // one NCCL group (one launch) for all of it; params are listed in buffer order so neighbours merge into one range
     VC_TRY(grad_ready_params({pidx("imf_emb/kernel"), pidx("imf_emb/bias"), cfg.use_c_v ? pidx("cv_emb/kernel") : -1,
-                              cfg.use_c_v ? pidx("cv_emb/bias") : -1}, s));
-    const int64_t tail[1][2] = {{n_adam, 64}};
-    VC_TRY(grad_ready(tail, 1, s));
+                              cfg.use_c_v ? pidx("cv_emb/bias") : -1, cfg.no_encoder ? -1 : enc.p_kernel,
+                              cfg.no_encoder ? -1 : enc.p_bias, cfg.no_encoder ? -1 : pidx("encoder/enc_embeddings"), -2}, s));
   }
   // squared norm of the dense (non-embedding) gradients -> tail[2] (apply); embedding slices are in tail[0..1] (Q4)
   return VC_OK;

@@ -77,13 +77,13 @@ class Model {
   float *Pf = nullptr, *Gf = nullptr, *Mf = nullptr, *Vf = nullptr;  // flat fp32: params, grads, Adam m, v
   float* g_tail = nullptr;  // 4 floats after the Adam region of G: [|enc slices|^2, |dec slices|^2, |dense|^2, -]
   int64_t adam_t = 0;       // TF global_step of the optimiser (1-based after the first update)
-  bool shadows_dirty = true;
+  bool shadows_dirty = true, decode_shadows_dirty = true;
   bool have_forward = false, logits_intact = false;
   int lastN = 0, lastT = 0;
   float last_ann = 1.f;
 
   // --- shadows (bf16 unless noted)
-  void *imf_wt = nullptr, *cv_wt = nullptr, *heads_wt = nullptr, *heads_nat = nullptr, *z_wt = nullptr, *z_nat = nullptr,
+  void *imf_wt = nullptr, *cv_wt = nullptr, *cv_nat = nullptr, *heads_nat = nullptr, *z_wt = nullptr, *z_nat = nullptr,
        *wo_t = nullptr, *wo_nat = nullptr, *enc_emb_h = nullptr, *dec_emb_h = nullptr;
   // The posterior heads (encoder.py:59-107) are packed: kernel block [He, heads_cols] and bias block [heads_cols],
   // head k's mean at columns [2k*ZP, 2k*ZP+Z), its log-std at [(2k+1)*ZP, ...). The TF variables
@@ -187,6 +187,7 @@ class Model {
   int set_cluster_means(const float* src_host);
 
   int refresh_shadows(cudaStream_t s);
+  int refresh_decode_shadows(cudaStream_t s);
   int forward(const StepInputs& in, bool write_grad, cudaStream_t s);
   int backward(const StepInputs& in, cudaStream_t s);
   int apply(float grad_scale, cudaStream_t s);

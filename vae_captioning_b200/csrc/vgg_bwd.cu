@@ -214,7 +214,6 @@ int Model::vgg_bwd_init() {
   const size_t big = (size_t)B * 224 * 224 * 64;
   VC_TRY(dalloc((uint16_t**)&vgg_bwd_a, big));
   VC_TRY(dalloc((uint16_t**)&vgg_bwd_b, big));
-  VC_TRY(dalloc((uint16_t**)&imf_nat, (size_t)cfg.cnn_feature_size * cfg.embed_size));
   VC_TRY(dalloc((uint16_t**)&dfc2_pre, (size_t)B * 4096));
   VC_TRY(dalloc((uint16_t**)&dfc1_pre, (size_t)B * 4096));
   VC_TRY(dalloc(&dfeats_f, (size_t)B * cfg.cnn_feature_size));
