@@ -69,6 +69,90 @@ int transpose_cast(cudaStream_t s, const float* src, void* dst, int R, int C, lo
   return VC_OK;
 }
 
+// Every bf16 operand shadow of one optimiser step in ONE launch (the per-tensor casts / transposes above were 13 launches
+// of 2-15 us each per step). Job kinds: 0 = dst[r, c] = bf16(src[r, c]) (row pitches may differ), vectorised by 4 when
+// the row length and both pitches allow; 1 = the gate-interleaving transpose of k_transpose_cast. Blocks are dealt to
+// jobs by a prefix table.
+__global__ void __launch_bounds__(256) k_refresh_multi(const RefreshJobs jobs) {
+  __shared__ float tile[32][33];
+  int j = 0;
+  while (j + 1 < jobs.n && (int)blockIdx.x >= jobs.j[j + 1].blk0) ++j;
+  const RefreshJob& J = jobs.j[j];
+  const unsigned int b = blockIdx.x - J.blk0;
+  const float* __restrict__ src = J.src;
+  __nv_bfloat16* __restrict__ dst = J.dst;
+  if (J.kind == 0) {
+    const unsigned int total = (unsigned int)J.rows * (unsigned int)J.cols;
+    if (J.vec4) {
+      const unsigned int c4n = (unsigned int)J.cols >> 2;
+      const unsigned int i0 = (b * 256u + threadIdx.x) * 2u;  // two float4 per thread
+#pragma unroll
+      for (unsigned int k = 0; k < 2; ++k) {
+        const unsigned int i = i0 + k;
+        if (i * 4u >= total) break;
+        const unsigned int r = i / c4n, c = (i - r * c4n) * 4u;
+        const float4 v = *reinterpret_cast<const float4*>(src + (size_t)r * J.ld_src + c);
+        uint2 o;
+        o.x = pack_bf16(v.x, v.y);
+        o.y = pack_bf16(v.z, v.w);
+        *reinterpret_cast<uint2*>(dst + (size_t)r * J.ld_dst + c) = o;
+      }
+    } else {
+      const unsigned int i0 = b * 2048u + threadIdx.x;
+#pragma unroll
+      for (unsigned int k = 0; k < 8; ++k) {
+        const unsigned int i = i0 + k * 256u;
+        if (i >= total) break;
+        const unsigned int r = i / (unsigned int)J.cols, c = i - r * (unsigned int)J.cols;
+        dst[(size_t)r * J.ld_dst + c] = __float2bfloat16(src[(size_t)r * J.ld_src + c]);
+      }
+    }
+    return;
+  }
+  const int tiles_c = (J.cols + 31) / 32;
+  const int c0 = (int)(b % tiles_c) * 32, r0 = (int)(b / tiles_c) * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int i = ty; i < 32; i += 8) {
+    const int r = r0 + i, c = c0 + tx;
+    tile[i][tx] = (r < J.rows && c < J.cols) ? src[(size_t)r * J.ld_src + c] : 0.f;
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int c = c0 + i, r = r0 + tx;
+    if (c < J.cols && r < J.rows) {
+      int cd = c;
+      if (J.gate_h > 0) {
+        const int g = c / J.gate_h, u = c - g * J.gate_h;
+        cd = (u / J.upt) * (4 * J.upt) + g * J.upt + (u % J.upt);
+      }
+      dst[(size_t)cd * J.ld_dst + r] = __float2bfloat16(tile[tx][i]);
+    }
+  }
+}
+int refresh_multi(cudaStream_t s, RefreshJobs& jobs) {
+  if (jobs.n <= 0) return VC_OK;
+  int blocks = 0;
+  for (int i = 0; i < jobs.n; ++i) {
+    RefreshJob& J = jobs.j[i];
+    J.blk0 = blocks;
+    if (J.kind == 0) {
+      J.vec4 = (J.cols % 4 == 0 && J.ld_src % 4 == 0 && J.ld_dst % 4 == 0 && (reinterpret_cast<uintptr_t>(J.src) & 15) == 0 &&
+                (reinterpret_cast<uintptr_t>(J.dst) & 7) == 0) ? 1 : 0;
+      const long long total = (long long)J.rows * J.cols;
+      if (total >= (1LL << 31)) return set_error(VC_E_SHAPE, "refresh_multi: tensor too large");
+      blocks += (int)((total + 2047) / 2048);
+    } else {
+      blocks += ((J.cols + 31) / 32) * ((J.rows + 31) / 32);
+    }
+  }
+  {
+    ProfScope ps(s, "refresh_shadows");
+    k_refresh_multi<<<blocks, 256, 0, s>>>(jobs);
+  }
+  VC_CUDA(cudaGetLastError());
+  return VC_OK;
+}
+
 // out_bf16[(b*C + c), :] = bf16(src[b, :])  for c in [0, C): feature tiling (main.py:84-89) applied
 // after the projection (Q7); written to up to two destinations (encoder and decoder X slot 0).
 __global__ void k_tile_cast(const float* __restrict__ src, __nv_bfloat16* __restrict__ d0, __nv_bfloat16* __restrict__ d1,

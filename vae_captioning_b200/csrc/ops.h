@@ -106,6 +106,26 @@ int cast_f32_bf16(cudaStream_t s, const float* src, void* dst, long long rows, i
 int bf16_to_f32(cudaStream_t s, const void* src, float* dst, long long rows, int cols, long long ld_src, long long ld_dst);
 int transpose_cast(cudaStream_t s, const float* src, void* dst, int R, int C, long long ld_src, long long ld_dst,
                    int gate_h, int upt);
+struct RefreshJob {
+  const float* src;
+  __nv_bfloat16* dst;
+  int rows, cols;       // of src
+  int ld_src, ld_dst;
+  int kind;             // 0: cast, 1: transpose (+ LSTM gate interleave when gate_h > 0)
+  int gate_h, upt;
+  int vec4, blk0;       // filled by refresh_multi
+};
+struct RefreshJobs {
+  RefreshJob j[16];
+  int n = 0;
+  void cast(const float* src, void* dst, int rows, int cols, int ld_src, int ld_dst) {
+    j[n++] = RefreshJob{src, (__nv_bfloat16*)dst, rows, cols, ld_src, ld_dst, 0, 0, 0, 0, 0};
+  }
+  void transpose(const float* src, void* dst, int rows, int cols, int ld_src, int ld_dst, int gate_h, int upt) {
+    j[n++] = RefreshJob{src, (__nv_bfloat16*)dst, rows, cols, ld_src, ld_dst, 1, gate_h, upt, 0, 0};
+  }
+};
+int refresh_multi(cudaStream_t s, RefreshJobs& jobs);
 int tile_cast(cudaStream_t s, const float* src, void* d0, void* d1, int B, int C, int E);
 int tile_reduce(cudaStream_t s, const float* a, const float* b2, float* dst_f, void* dst_h, int B, int C, int E);
 int embed_gather(cudaStream_t s, const void* table, const int* tok, void* X, const float* keep_mask, float inv_keep,
