@@ -47,6 +47,12 @@ size_t g_used = 0;
 thread_local const char* t_tag = nullptr;
 }  // namespace
 
+static thread_local int t_sm_cap = 0;
+int sm_budget() { return t_sm_cap > 0 && t_sm_cap < num_sms() ? t_sm_cap : num_sms(); }
+GridCap::GridCap(int sms) : prev(t_sm_cap) { t_sm_cap = sms; }
+GridCap::~GridCap() { t_sm_cap = prev; }
+bool prof_is_on() { return g_prof_on; }
+
 unsigned long long launch_count() { return g_launches.load(); }
 
 void prof_enable(bool on) {

@@ -30,6 +30,16 @@ int set_error(int code, const char* fmt, ...);
   } while (0)
 
 int num_sms();
+// SMs a persistent GEMM launched inside a GridCap scope may occupy (default: all of them). The backward pass runs the
+// weight-gradient GEMMs nothing downstream waits for on a side stream next to the whole-sequence BPTT kernels, which hold
+// (N/128) x (H/units) SMs for their whole duration: a 148-CTA grid would queue behind them, a capped one fits beside them.
+int sm_budget();
+struct GridCap {
+  int prev;
+  explicit GridCap(int sms);
+  ~GridCap();
+};
+bool prof_is_on();
 
 // ---- launch accounting + optional per-kernel-family CUDA-event timing (bench.py's roofline leg).
 // Every kernel launch site opens a ProfScope: it counts the launch and, while profiling is enabled,
@@ -163,7 +173,7 @@ int launch_gemm(const GemmPlan& p, const Epi& epi, cudaStream_t stream) {
   }
   const int total = p.core.m_tiles * p.core.n_tiles * p.core.splits;
   if (total <= 0) return VC_OK;
-  const int grid = total < num_sms() ? total : num_sms();
+  const int grid = total < sm_budget() ? total : sm_budget();
   GemmCore core = p.core;
   core.stages = gemm_pick_stages(core.bn, Epi::kSmemBytes);
   if (core.stages < 2) return set_error(VC_E_ARG, "launch_gemm: tile too large for shared memory (bn=%d)", core.bn);

@@ -17,6 +17,9 @@ Model::~Model() {
     if (q.consumed) cudaEventDestroy(q.consumed);
   }
   if (host_scal) cudaFreeHost(host_scal);
+  if (side) cudaStreamDestroy(side);
+  if (ev_fork) cudaEventDestroy(ev_fork);
+  if (ev_join) cudaEventDestroy(ev_join);
 }
 
 int Model::add_param(const std::string& name, std::vector<int64_t> shape, int region, bool hidden) {
@@ -234,6 +237,13 @@ int Model::init(const vc_config& c, int dev) {
   VC_TRY(dalloc(&st_in, (size_t)N * T));
   VC_TRY(dalloc(&st_len, (size_t)N));
   VC_CUDA(cudaMallocHost((void**)&host_scal, 64 * sizeof(float)));
+  VC_CUDA(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
+  VC_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+  VC_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+  {  // SMs the whole-sequence recurrences leave idle at the handle's batch size (minus a few for NCCL's channels)
+    const int lstm_ctas = ((maxN + 127) / 128) * (cfg.decoder_hidden / lstm_seq_units(maxN, cfg.decoder_hidden));
+    side_sm_cap = std::max(24, num_sms() - lstm_ctas - 12);
+  }
   if (cfg.with_cnn || cfg.fine_tune) VC_TRY(vgg_init());
   shadows_dirty = true;
   return VC_OK;
@@ -489,6 +499,24 @@ int Model::lstm_forward(LstmNet& L, int N, int T, const int32_t* len, void* out,
   return VC_OK;
 }
 
+// Side stream of the backward pass (VC_BWD_OVERLAP=0 turns it off; per-kernel profiling turns it off so that every
+// kernel is timed running alone). side_begin makes `side` wait for everything enqueued on `s` so far and returns
+// whether work should go there; side_join makes `s` wait for everything enqueued on `side`.
+bool Model::side_begin(cudaStream_t s) {
+  static const bool enabled = [] { const char* e = getenv("VC_BWD_OVERLAP"); return !(e && e[0] == '0'); }();
+  if (!enabled || side == nullptr || prof_is_on()) return false;
+  if (cudaEventRecord(ev_fork, s) != cudaSuccess || cudaStreamWaitEvent(side, ev_fork, 0) != cudaSuccess) return false;
+  side_used = true;
+  return true;
+}
+int Model::side_join(cudaStream_t s) {
+  if (!side_used) return VC_OK;
+  VC_CUDA(cudaEventRecord(ev_join, side));
+  VC_CUDA(cudaStreamWaitEvent(s, ev_join, 0));
+  side_used = false;
+  return VC_OK;
+}
+
 int Model::lstm_backward(LstmNet& L, int N, int T, const int32_t* len, const float* d_out, const float* out_keep,
                          cudaStream_t s) {
   const int steps = L.pre + T;
@@ -525,7 +553,13 @@ int Model::lstm_backward(LstmNet& L, int N, int T, const int32_t* len, const flo
     a.pre = L.pre; a.T = T; a.steps = steps; a.N = N; a.E = L.E; a.H = L.H;
     VC_TRY(lstm_bwd_seq(s, a));
   }
-  // weight gradient: dW[E+H, 4H] = [X ; H_prev]^T x dG over all steps (one GEMM, split-K, fp32 atomics)
+  // weight gradient: dW[E+H, 4H] = [X ; H_prev]^T x dG over all steps (one GEMM, split-K, fp32 atomics). Nothing in the
+  // backward pass waits for it (nor for the bias gradient): with the side stream on, both run there, beside whatever
+  // the main stream does next -- for the decoder that is the encoder's BPTT, which leaves 68 of 148 SMs idle.
+  cudaStream_t main_s = s;
+  const bool on_side = side_begin(s);
+  if (on_side) s = side;
+  GridCap cap(on_side ? side_sm_cap : 0);
   const long long rows = (long long)steps * N;
   Operand AX{L.X, rows, L.E, L.E, true};
   Operand AH{L.Hs, rows, L.H, L.H, true};
@@ -549,6 +583,9 @@ int Model::lstm_backward(LstmNet& L, int N, int T, const int32_t* len, const flo
     }
   }
   VC_TRY(colsum_bf16(s, L.dG, rows, 4 * L.H, 4 * L.H, gp(L.p_bias)));
+  VC_TRY(grad_ready_params({L.p_kernel, L.p_bias}, s));  // data parallel: this bucket leaves from the stream that made it
+  s = main_s;
+  GridCap uncap(0);
   // input gradient: dX[steps*N, E] = dG x W_x^T  (B = rows 0..E of the natural shadow)
   Operand AG{L.dG, rows, 4LL * L.H, 4LL * L.H, false};
   Operand BW{L.w_nat, L.E, 4LL * L.H, 4LL * L.H, false};
@@ -693,6 +730,11 @@ int Model::backward(const StepInputs& in, cudaStream_t s) {
       ProfTag ptag("logits_dgrad");
       VC_TRY(gemm_store(s, A, nullptr, 0, Bw, (int)rows, Hd, V, e, Hd % 256 == 0 ? 256 : 64, 1));
     }
+    // dW_o and db_o: on the side stream when it is on (beside the decoder's BPTT)
+    cudaStream_t main_s = s;
+    const bool on_side = side_begin(s);
+    if (on_side) s = side;
+    GridCap cap(on_side ? side_sm_cap : 0);
     Operand A2{Out, rows, Hd, Hd, true}, B2{logits, rows, V, VP, true};
     EpiStore e2{};
     e2.out = gp(pidx("decoder/rnn_logits/kernel")); e2.ld = V; e2.alpha = 1.f;
@@ -715,10 +757,11 @@ int Model::backward(const StepInputs& in, cudaStream_t s) {
       VC_TRY(gemm_store(s, A2, nullptr, 0, B2, Hd, V, (int)rows, e2, 256, splits));
     }
     VC_TRY(colsum_bf16(s, logits, rows, V, VP, gp(pidx("decoder/rnn_logits/bias"))));
+    // data parallel: each group of gradients is summed over the ranks as soon as its last producer is enqueued
+    // (comm.cu); the vocabulary projection's 23 MB travel under the decoder's BPTT
+    VC_TRY(grad_ready_params({pidx("decoder/rnn_logits/kernel"), pidx("decoder/rnn_logits/bias")}, s));
+    s = main_s;
   }
-  // data parallel: each group of gradients is summed over the ranks as soon as its last producer is enqueued
-  // (comm.cu); the vocabulary projection's 23 MB travel under the decoder's BPTT
-  VC_TRY(grad_ready_params({pidx("decoder/rnn_logits/kernel"), pidx("decoder/rnn_logits/bias")}, s));
   // decoder BPTT
   VC_CUDA(cudaMemsetAsync(dec.dh_carry, 0, (size_t)N * Hd * sizeof(float), s));
   VC_CUDA(cudaMemsetAsync(dec.dc_carry, 0, (size_t)N * Hd * sizeof(float), s));
@@ -726,7 +769,7 @@ int Model::backward(const StepInputs& in, cudaStream_t s) {
   VC_TRY(embed_scatter(s, dec.dX + (size_t)dec.pre * N * E, in.cap_in, gp(pidx("decoder/net/dec_embeddings")),
                        cfg.dec_keep_rate < 1.f ? in.rng.emb_keep_dev : nullptr, 1.f / cfg.dec_keep_rate, g_tail + 1, N, T,
                        E, V));
-  VC_TRY(grad_ready_params({dec.p_kernel, dec.p_bias, pidx("decoder/net/dec_embeddings")}, s));
+  VC_TRY(grad_ready_params({pidx("decoder/net/dec_embeddings")}, s));
   if (!cfg.no_encoder) {
     const int He = cfg.encoder_hidden;
     const int SZ = S * Z;
@@ -820,9 +863,9 @@ int Model::backward(const StepInputs& in, cudaStream_t s) {
     // the per-token embedding-slice squared norms of this rank (Q4: the norm is over every tower's slices)
     // one NCCL group (one launch) for all of it; params are listed in buffer order so neighbours merge into one range
     VC_TRY(grad_ready_params({pidx("imf_emb/kernel"), pidx("imf_emb/bias"), cfg.use_c_v ? pidx("cv_emb/kernel") : -1,
-                              cfg.use_c_v ? pidx("cv_emb/bias") : -1, cfg.no_encoder ? -1 : enc.p_kernel,
-                              cfg.no_encoder ? -1 : enc.p_bias, cfg.no_encoder ? -1 : pidx("encoder/enc_embeddings"), -2}, s));
+                              cfg.use_c_v ? pidx("cv_emb/bias") : -1, cfg.no_encoder ? -1 : pidx("encoder/enc_embeddings"), -2}, s));
   }
+  VC_TRY(side_join(s));  // the optimiser (or the caller's own all-reduce) follows on `s`
   // squared norm of the dense (non-embedding) gradients -> tail[2] (apply); embedding slices are in tail[0..1] (Q4)
   return VC_OK;
 }

@@ -161,6 +161,14 @@ class Model {
   int decode_step(const int32_t* tok_host, int M, float* probs_host, cudaStream_t s);
   int decode_state(float* c_host, float* h_host, const float* c_in, const float* h_in, cudaStream_t s);
 
+  // --- side stream of the backward pass: weight / bias gradients nothing downstream waits for run beside the BPTT kernels
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  int side_sm_cap = 0;
+  bool side_used = false;
+  bool side_begin(cudaStream_t s);
+  int side_join(cudaStream_t s);
+
   // --- data-parallel gradient all-reduce (comm.cu); null = single device
   Comm* comm = nullptr;
   int comm_init(const void* id128, int rank, int world);
