@@ -511,7 +511,8 @@ def run_train(args, name, rank, world, local_rank, steps, warmup, full):
         eng.comm_set_mode(1)
         allreduce = {"bytes": comm["bytes"], "buckets": comm["buckets"], "span_ms": comm["span_ms"],
                      "exposed_ms": ms / steps - ms_m0, "exposed_ms_unbucketed": ms_m2 - ms_m0,
-                     "ms_per_step_no_allreduce": ms_m0, "ms_per_step_unbucketed": ms_m2, "transport": "fp32",
+                     "ms_per_step_no_allreduce": ms_m0, "ms_per_step_unbucketed": ms_m2,
+                     "transport": "bf16 (VC_GRAD_BF16=1)" if os.environ.get("VC_GRAD_BF16") == "1" else "fp32",
                      "note": "span = first bucket start to last bucket end on the communication stream of the last timed "
                              "step; exposed = step time minus the same step with the reduction switched off"}
 

@@ -129,7 +129,10 @@ def main():
                     worst_sim = max(worst_sim, d)
                 entry["grad_vs_alias_sum_max_rel"] = worst_sim
                 # split-K partial sums meet in fp32 atomics, so two runs of the same shard differ in the last bits
-                good = (entry["crc_equal"] and worst <= 4e-2 and worst_sim <= 2e-3 and
+                # bf16 transport (VC_GRAD_BF16=1) rounds every gradient to 8 mantissa bits on the wire: 1e-2 of max-abs there
+                sim_tol = 1e-2 if os.environ.get("VC_GRAD_BF16") == "1" else 2e-3
+                entry["transport"] = "bf16" if os.environ.get("VC_GRAD_BF16") == "1" else "fp32"
+                good = (entry["crc_equal"] and worst <= 4e-2 and worst_sim <= sim_tol and
                         abs(out["global_norm"] - norm) <= 3e-2 * norm)
                 entry["ok"] = bool(good)
                 ok = ok and good

@@ -33,7 +33,27 @@ struct Nccl {
   const char* (*GetErrorString)(ncclResult) = nullptr;
   std::string err;
 };
-constexpr int kNcclFloat32 = 7, kNcclSum = 0;  // nccl.h: ncclFloat32 = 7, ncclSum = 0 (stable since NCCL 2.0)
+constexpr int kNcclFloat32 = 7, kNcclBfloat16 = 9, kNcclSum = 0;  // nccl.h enum values (stable since NCCL 2.10)
+
+// bf16 transport (VC_GRAD_BF16=1): fp32 gradients are rounded to bf16 for the wire and widened back afterwards, both on
+// the communication stream. Vectorised by 8; ranges are multiples of 64 floats.
+__global__ void k_grad_pack(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long n8) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+    const float4 a = reinterpret_cast<const float4*>(src)[2 * i], b = reinterpret_cast<const float4*>(src)[2 * i + 1];
+    uint4 o;
+    o.x = pack_bf16(a.x, a.y); o.y = pack_bf16(a.z, a.w); o.z = pack_bf16(b.x, b.y); o.w = pack_bf16(b.z, b.w);
+    reinterpret_cast<uint4*>(dst)[i] = o;
+  }
+}
+__global__ void k_grad_unpack(const __nv_bfloat16* __restrict__ src, float* __restrict__ dst, long long n8) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+    const uint4 v = reinterpret_cast<const uint4*>(src)[i];
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+    const float2 p0 = __bfloat1622float2(h[0]), p1 = __bfloat1622float2(h[1]), p2 = __bfloat1622float2(h[2]), p3 = __bfloat1622float2(h[3]);
+    reinterpret_cast<float4*>(dst)[2 * i] = make_float4(p0.x, p0.y, p1.x, p1.y);
+    reinterpret_cast<float4*>(dst)[2 * i + 1] = make_float4(p2.x, p2.y, p3.x, p3.y);
+  }
+}
 
 const Nccl* nccl() {
   static Nccl n;
@@ -82,6 +102,7 @@ struct Comm {
   cudaEvent_t t0 = nullptr, t1 = nullptr;  // timing of the first / last collective of a step (vc_comm_stats)
   int next_event = 0;
   bool pending = false, timed = false;
+  __nv_bfloat16* wire = nullptr;  // bf16 transport buffer (same element offsets as the gradient buffer); null = fp32 transport
   int mode = 1;  // 0: no reduction (measurement only), 1: bucketed + overlapped, 2: one all-reduce behind the backward pass
   long long bytes_step = 0, calls_step = 0;
 };
@@ -118,6 +139,9 @@ int Model::comm_init(const void* id128, int rank, int world) {
   VC_CUDA(cudaEventCreateWithFlags(&c->done, cudaEventDisableTiming));
   VC_CUDA(cudaEventCreate(&c->t0));
   VC_CUDA(cudaEventCreate(&c->t1));
+  if (const char* e = getenv("VC_GRAD_BF16")) {
+    if (e[0] == '1') VC_CUDA(cudaMalloc((void**)&c->wire, (size_t)(cfg.fine_tune ? n_total : n_adam + 64) * sizeof(__nv_bfloat16)));
+  }
   comm = c;
   return VC_OK;
 }
@@ -134,11 +158,13 @@ void Model::comm_release() {
   if (comm->t0) cudaEventDestroy(comm->t0);
   if (comm->t1) cudaEventDestroy(comm->t1);
   if (comm->stream) cudaStreamDestroy(comm->stream);
+  if (comm->wire) cudaFree(comm->wire);
   delete comm;
   comm = nullptr;
 }
 
 int Model::comm_world() const { return comm ? comm->world : 1; }
+bool Model::comm_bf16() const { return comm != nullptr && comm->wire != nullptr; }
 
 // Gradients in [off, off + count) of the flat buffer (several ranges per call = one bucket) are final on stream `s`:
 // sum them over the ranks on the communication stream. No-op without a communicator or with world == 1.
@@ -161,18 +187,32 @@ int Model::comm_reduce(const int64_t (*ranges)[2], int n_ranges, cudaStream_t s)
     VC_CUDA(cudaEventRecord(c.t0, c.stream));
     c.timed = true;
   }
+  // the 64-float tail (squared norms, O(1e5) under the AG prior) always travels in fp32
+  auto wired = [&](int i) { return c.wire != nullptr && ranges[i][1] > 64; };
+  for (int i = 0; i < n_ranges; ++i)
+    if (wired(i)) {
+      const long long n8 = ranges[i][1] / 8;
+      k_grad_pack<<<(int)std::min<long long>((n8 + 255) / 256, num_sms() * 4), 256, 0, c.stream>>>(Gf + ranges[i][0], c.wire + ranges[i][0], n8);
+    }
   if (n_ranges > 1) VC_NCCL(n, n->GroupStart());
   for (int i = 0; i < n_ranges; ++i) {
     const int64_t off = ranges[i][0], cnt = ranges[i][1];
     if (cnt <= 0) continue;
-    ncclResult r = n->AllReduce(Gf + off, Gf + off, (size_t)cnt, kNcclFloat32, kNcclSum, c.comm, c.stream);
+    ncclResult r = wired(i) ? n->AllReduce(c.wire + off, c.wire + off, (size_t)cnt, kNcclBfloat16, kNcclSum, c.comm, c.stream)
+                            : n->AllReduce(Gf + off, Gf + off, (size_t)cnt, kNcclFloat32, kNcclSum, c.comm, c.stream);
     if (r != 0) {
       if (n_ranges > 1) n->GroupEnd();
       return set_error(VC_E_NCCL, "ncclAllReduce(%lld floats) failed: %s", (long long)cnt, n->GetErrorString(r));
     }
-    c.bytes_step += cnt * 4;
+    c.bytes_step += cnt * (wired(i) ? 2 : 4);
   }
   if (n_ranges > 1) VC_NCCL(n, n->GroupEnd());
+  for (int i = 0; i < n_ranges; ++i)
+    if (wired(i)) {
+      const long long n8 = ranges[i][1] / 8;
+      k_grad_unpack<<<(int)std::min<long long>((n8 + 255) / 256, num_sms() * 4), 256, 0, c.stream>>>(c.wire + ranges[i][0], Gf + ranges[i][0], n8);
+    }
+  VC_CUDA(cudaGetLastError());
   c.calls_step += 1;
   c.pending = true;
   return VC_OK;

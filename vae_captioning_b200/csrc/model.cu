@@ -243,6 +243,7 @@ int Model::init(const vc_config& c, int dev) {
   {  // SMs the whole-sequence recurrences leave idle at the handle's batch size (minus a few for NCCL's channels)
     const int lstm_ctas = ((maxN + 127) / 128) * (cfg.decoder_hidden / lstm_seq_units(maxN, cfg.decoder_hidden));
     side_sm_cap = std::max(24, num_sms() - lstm_ctas - 12);
+    if (const char* e = getenv("VC_SIDE_SMS")) side_sm_cap = std::max(8, atoi(e));
   }
   if (cfg.with_cnn || cfg.fine_tune) VC_TRY(vgg_init());
   shadows_dirty = true;
@@ -556,8 +557,10 @@ int Model::lstm_backward(LstmNet& L, int N, int T, const int32_t* len, const flo
   // weight gradient: dW[E+H, 4H] = [X ; H_prev]^T x dG over all steps (one GEMM, split-K, fp32 atomics). Nothing in the
   // backward pass waits for it (nor for the bias gradient): with the side stream on, both run there, beside whatever
   // the main stream does next -- for the decoder that is the encoder's BPTT, which leaves 68 of 148 SMs idle.
+  // Data parallel: by now the communication stream is moving the vocabulary / decoder / head buckets and NCCL needs the
+  // idle SMs more than this GEMM does (8 x B200, cfg 3: 2.80 ms per step with it on the side stream, 2.77 without).
   cudaStream_t main_s = s;
-  const bool on_side = side_begin(s);
+  const bool on_side = comm_world() == 1 && side_begin(s);
   if (on_side) s = side;
   GridCap cap(on_side ? side_sm_cap : 0);
   const long long rows = (long long)steps * N;

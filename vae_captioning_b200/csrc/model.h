@@ -174,6 +174,7 @@ class Model {
   int comm_init(const void* id128, int rank, int world);
   void comm_release();
   int comm_world() const;
+  bool comm_bf16() const;
   int grad_ready(const int64_t (*ranges)[2], int n_ranges, cudaStream_t s);
   int grad_ready_params(std::initializer_list<int> ids, cudaStream_t s);
   int comm_reduce(const int64_t (*ranges)[2], int n_ranges, cudaStream_t s);
