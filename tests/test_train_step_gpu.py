@@ -194,6 +194,25 @@ def test_unknown_optimizer_is_rejected():
         engine_for(cfg, params, 2, 5)
 
 
+def test_decoder_dropout_flags_draw_philox_masks():
+    """--dec_drop / --dec_lstm_drop without explicit masks (the CLI path): keep masks come from Philox(seed, step)
+    on the device. Same seed and step -> same step; another seed -> another draw; the loss stays close to the oracle's
+    with ITS explicit masks (same distribution, different draw) and the gradient check of the explicit-mask case above
+    covers the arithmetic."""
+    cfg, params, batch = make_case(SMALL, 6, 7, seed=31, ragged=True, dec_keep_rate=0.7, dec_lstm_drop=0.8)
+    outs = []
+    for seed in (5, 5, 6):
+        eng = engine_for(cfg, params, 6, 7)
+        outs.append(eng.train_step(anneal=0, rng={"seed": seed, "eps": rng_for(batch)["eps"]}, **feed_of(batch)))
+        eng.close()
+    assert abs(outs[0]["rec_loss"] - outs[1]["rec_loss"]) <= 1e-5 * abs(outs[0]["rec_loss"])
+    assert abs(outs[0]["rec_loss"] - outs[2]["rec_loss"]) > 1e-6 * abs(outs[0]["rec_loss"])
+    with torch.no_grad():
+        ref = O.forward(params, cfg, batch)
+    assert abs(outs[0]["rec_loss"] - float(ref["rec_loss"])) <= 0.05 * abs(float(ref["rec_loss"]))
+    assert np.isfinite(outs[0]["global_norm"]) and outs[0]["global_norm"] > 0
+
+
 def test_clip_identity_and_adam_first_step_kat():
     """Known-answer: with |g| <= clip the clip is the identity, and Adam's first step is
     lr_t * (1-b1) g / (sqrt((1-b2) g^2) + eps) with lr_t = lr sqrt(1-b2)/(1-b1)  ~=  lr * sign(g)."""

@@ -69,6 +69,30 @@ int transpose_cast(cudaStream_t s, const float* src, void* dst, int R, int C, lo
   return VC_OK;
 }
 
+// tf.nn.dropout / DropoutWrapper keep masks (decoder.py:85-87, rnn_model.py:45-46) drawn on the device when the caller
+// gives none: mask[i] = 1 if Philox4x32-10(seed ^ salt, subsequence = i / 4, offset = step) uniform < keep_prob else 0.
+__global__ void k_keep_mask(float* __restrict__ mask, long long n, float keep_prob, unsigned long long seed,
+                            unsigned long long offset) {
+  const long long n4 = (n + 3) / 4;
+  for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < n4; q += (long long)gridDim.x * blockDim.x) {
+    curandStatePhilox4_32_10_t st;
+    curand_init(seed, (unsigned long long)q, offset, &st);
+    const float4 u = curand_uniform4(&st);
+    const float v[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (4 * q + j < n) mask[4 * q + j] = v[j] <= keep_prob ? 1.f : 0.f;
+  }
+}
+int keep_mask(cudaStream_t s, float* mask, long long n, float keep_prob, unsigned long long seed, unsigned long long offset) {
+  {
+    ProfScope ps(s, "keep_mask");
+    k_keep_mask<<<grid_for((n + 3) / 4, 256, 2), 256, 0, s>>>(mask, n, keep_prob, seed, offset);
+  }
+  VC_CUDA(cudaGetLastError());
+  return VC_OK;
+}
+
 // Every bf16 operand shadow of one optimiser step in ONE launch (the per-tensor casts / transposes above were 13 launches
 // of 2-15 us each per step). Job kinds: 0 = dst[r, c] = bf16(src[r, c]) (row pitches may differ), vectorised by 4 when
 // the row length and both pitches allow; 1 = the gate-interleaving transpose of k_transpose_cast. Blocks are dealt to

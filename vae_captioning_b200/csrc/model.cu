@@ -611,17 +611,27 @@ static float annealing_coeff(const vc_config& c, int64_t gs) {  // main.py:162-1
 
 // ------------------------------------------------------------------------------------------
 // scal layout: 0 ce_sum, 1 mask_sum, 2 mask count (pre-pass), 3 kl_sum, 7 global norm, 8 sum(w^2) over cnn/ (fine_tune)
-int Model::forward(const StepInputs& in, bool write_grad, cudaStream_t s) {
+int Model::forward(StepInputs& in, bool write_grad, cudaStream_t s) {
   const int B = in.B, T = in.T, C = cfg.num_captions, N = B * C;
   const int E = cfg.embed_size, Hd = cfg.decoder_hidden, Z = cfg.latent_size, S = cfg.gen_z_samples, V = cfg.vocab_size,
             F = cfg.cnn_feature_size, K = cfg.num_clusters;
   if (B < 1 || B > cfg.max_batch || T < 1 || T > maxT) return set_error(VC_E_SHAPE, "batch/len out of range");
   const bool has_cv = cfg.use_c_v || cfg.prior != VC_PRIOR_NORMAL;
   if (has_cv && in.c_v == nullptr) return set_error(VC_E_ARG, "this configuration needs cluster vectors (c_v)");
-  if (cfg.dec_keep_rate < 1.f && in.rng.emb_keep_dev == nullptr)
-    return set_error(VC_E_ARG, "dec_keep_rate < 1 needs rng.emb_keep_dev (Philox dropout masks are not implemented)");
-  if (cfg.dec_lstm_drop < 1.f && in.rng.out_keep_dev == nullptr)
-    return set_error(VC_E_ARG, "dec_lstm_drop < 1 needs rng.out_keep_dev (Philox dropout masks are not implemented)");
+  // --dec_drop / --dec_lstm_drop without explicit masks: Philox(seed, global_step) keep masks drawn on the device
+  // (tf.nn.dropout draws fresh uniforms every sess.run); the backward pass of the same step reads the same buffers
+  if (cfg.dec_keep_rate < 1.f && in.rng.emb_keep_dev == nullptr) {
+    if (emb_keep_buf == nullptr) VC_TRY(dalloc(&emb_keep_buf, (size_t)maxN * maxT * E, false));
+    VC_TRY(keep_mask(s, emb_keep_buf, (long long)N * T * E, cfg.dec_keep_rate, in.rng.seed ^ 0x243F6A8885A308D3ull,
+                     (unsigned long long)in.global_step));
+    in.rng.emb_keep_dev = emb_keep_buf;
+  }
+  if (cfg.dec_lstm_drop < 1.f && in.rng.out_keep_dev == nullptr) {
+    if (out_keep_buf == nullptr) VC_TRY(dalloc(&out_keep_buf, (size_t)maxN * maxT * Hd, false));
+    VC_TRY(keep_mask(s, out_keep_buf, (long long)N * T * Hd, cfg.dec_lstm_drop, in.rng.seed ^ 0x13198A2E03707344ull,
+                     (unsigned long long)in.global_step));
+    in.rng.out_keep_dev = out_keep_buf;
+  }
   if (shadows_dirty) VC_TRY(refresh_shadows(s));
   VC_CUDA(cudaMemsetAsync(scal, 0, 64 * sizeof(float), s));
 

@@ -107,6 +107,7 @@ class Model {
   float *st_feats = nullptr, *st_cv = nullptr;
   int32_t *st_lbl = nullptr, *st_in = nullptr, *st_len = nullptr;
   float* host_scal = nullptr;  // pinned
+  float *emb_keep_buf = nullptr, *out_keep_buf = nullptr;  // Philox keep masks of the decoder dropouts (allocated on first use)
   // Double-buffered feed (vc_stage_batch / vc_train_step_staged): the next step's host buffers are copied into one slot
   // on a copy stream while the current step computes from the other. Slots are allocated on first use.
   struct StageSlot {
@@ -197,7 +198,7 @@ class Model {
 
   int refresh_shadows(cudaStream_t s);
   int refresh_decode_shadows(cudaStream_t s);
-  int forward(const StepInputs& in, bool write_grad, cudaStream_t s);
+  int forward(StepInputs& in, bool write_grad, cudaStream_t s);  // may fill in.rng's dropout masks (Philox) for backward()
   int backward(const StepInputs& in, cudaStream_t s);
   int apply(float grad_scale, cudaStream_t s);
   int fetch(vc_step_out* out, cudaStream_t s);

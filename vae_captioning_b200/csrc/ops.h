@@ -126,6 +126,7 @@ struct RefreshJobs {
   }
 };
 int refresh_multi(cudaStream_t s, RefreshJobs& jobs);
+int keep_mask(cudaStream_t s, float* mask, long long n, float keep_prob, unsigned long long seed, unsigned long long offset);
 int tile_cast(cudaStream_t s, const float* src, void* d0, void* d1, int B, int C, int E);
 int tile_reduce(cudaStream_t s, const float* a, const float* b2, float* dst_f, void* dst_h, int B, int C, int E);
 int embed_gather(cudaStream_t s, const void* table, const int* tok, void* X, const float* keep_mask, float inv_keep,
