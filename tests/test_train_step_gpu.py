@@ -213,6 +213,21 @@ def test_decoder_dropout_flags_draw_philox_masks():
     assert np.isfinite(outs[0]["global_norm"]) and outs[0]["global_norm"] > 0
 
 
+def test_vocabulary_wider_than_the_register_resident_ce_kernel():
+    """V = 13001 > 12288 takes the looped cross-entropy kernel: loss, logits and the vocabulary gradients as
+    in the small cases."""
+    sizes = dict(TINY)
+    sizes["vocab_size"] = 13001
+    cfg, eng, grads, gnorm = grads_case(sizes, 2, 4, True)
+    for name in ("decoder/rnn_logits/kernel", "decoder/rnn_logits/bias", "decoder/net/dec_embeddings", "imf_emb/kernel"):
+        ref = grads[name].numpy()
+        got = eng.get_gradient(name)
+        assert np.max(np.abs(got - ref)) <= 4e-2 * max(np.max(np.abs(ref)), 1e-12), name
+    out = eng.apply_gradients(1.0)
+    assert abs(out["global_norm"] - gnorm) <= 2e-2 * gnorm
+    eng.close()
+
+
 def test_clip_identity_and_adam_first_step_kat():
     """Known-answer: with |g| <= clip the clip is the identity, and Adam's first step is
     lr_t * (1-b1) g / (sqrt((1-b2) g^2) + eps) with lr_t = lr sqrt(1-b2)/(1-b1)  ~=  lr * sign(g)."""

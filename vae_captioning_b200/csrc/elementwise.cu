@@ -742,14 +742,75 @@ k_ce(__nv_bfloat16* __restrict__ logits, long long ld, const int* __restrict__ l
     }
   }
 }
+// Vocabularies wider than the register-resident form above holds (V > 12288): same result, the row is read from
+// global memory three times (max, sum of exponentials, gradient) instead of living in registers.
+__global__ void __launch_bounds__(kCeThreads)
+k_ce_wide(__nv_bfloat16* __restrict__ logits, long long ld, const int* __restrict__ lbl, int N, int T, int V,
+          float* __restrict__ sums, float* __restrict__ ce_rows, const float* __restrict__ count, float loss_scale,
+          int write_grad) {
+  const int row = blockIdx.x;
+  const int t = row / N, n = row - t * N;
+  const int label = lbl[(long long)n * T + t];
+  __nv_bfloat16* p = logits + (long long)row * ld;
+  __shared__ float red[kCeThreads / 32];
+  __shared__ float bcast;
+  float mx = -INFINITY;
+  for (int c = threadIdx.x; c < V; c += kCeThreads) mx = fmaxf(mx, __bfloat162float(p[c]));
+  mx = warp_max(mx);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float m2 = threadIdx.x < kCeThreads / 32 ? red[threadIdx.x] : -INFINITY;
+    m2 = warp_max(m2);
+    if (threadIdx.x == 0) bcast = m2;
+  }
+  __syncthreads();
+  mx = bcast;
+  float sum = 0.f;
+  for (int c = threadIdx.x; c < V; c += kCeThreads) sum += __expf(__bfloat162float(p[c]) - mx);
+  __syncthreads();
+  sum = warp_sum(sum);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sum;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float s2 = threadIdx.x < kCeThreads / 32 ? red[threadIdx.x] : 0.f;
+    s2 = warp_sum(s2);
+    if (threadIdx.x == 0) bcast = s2;
+  }
+  __syncthreads();
+  sum = bcast;
+  const float mask = label != 0 ? 1.f : 0.f;
+  if (threadIdx.x == 0) {
+    const int lc = label < 0 ? 0 : (label >= V ? V - 1 : label);
+    const float ce = logf(sum) + mx - __bfloat162float(p[lc]);
+    if (ce_rows) ce_rows[(long long)n * T + t] = ce;
+    if (mask != 0.f) {
+      atomicAdd(&sums[0], ce);
+      atomicAdd(&sums[1], 1.f);
+    }
+  }
+  if (write_grad) {
+    __syncthreads();
+    const float gm = mask * loss_scale / fmaxf(count[0], 1.f);
+    const float g = gm / sum;
+    for (int c = threadIdx.x; c < (int)ld; c += kCeThreads) {
+      float a = 0.f;
+      if (c < V) a = __expf(__bfloat162float(p[c]) - mx) * g - (c == label ? gm : 0.f);
+      p[c] = __float2bfloat16(a);
+    }
+  }
+}
+
 int ce_rows(cudaStream_t s, void* logits, long long ld, const int* lbl, int N, int T, int V, float* sums, float* ce_out,
             const float* count, float loss_scale, int write_grad) {
-  if (V > kCeThreads * kCeVecs * 8) return set_error(VC_E_SHAPE, "vocab_size %d exceeds CE kernel limit", V);
   if (ld % 8 != 0 || (reinterpret_cast<uintptr_t>(logits) & 15) != 0)
     return set_error(VC_E_SHAPE, "logits rows must be 16-byte aligned (pitch multiple of 8)");
   {
     ProfScope ps(s, "ce");
-    k_ce<<<N * T, kCeThreads, 0, s>>>((__nv_bfloat16*)logits, ld, lbl, N, T, V, sums, ce_out, count, loss_scale, write_grad);
+    if (V > kCeThreads * kCeVecs * 8)
+      k_ce_wide<<<N * T, kCeThreads, 0, s>>>((__nv_bfloat16*)logits, ld, lbl, N, T, V, sums, ce_out, count, loss_scale, write_grad);
+    else
+      k_ce<<<N * T, kCeThreads, 0, s>>>((__nv_bfloat16*)logits, ld, lbl, N, T, V, sums, ce_out, count, loss_scale, write_grad);
   }
   VC_CUDA(cudaGetLastError());
   return VC_OK;
