@@ -294,6 +294,36 @@ def run_decode(args, w, name, rank, world, local_rank):
     launches = int(lib.vc_launch_count() - l0)
     clocks = sampler.stop() if sampler else None
     value = world * B * args.steps / (ms / 1e3)
+    # roofline of the dominant kernel family: the per-token vocabulary projection [M, 512] x [512, V] -> fp32 logits. Its
+    # algorithmic bytes per launch: W_o once (bf16) + the logits rows it must hand to the top-k (fp32) + the h rows (bf16);
+    # M = B rows for greedy, up to B * beam for the beam steps (summed over the launches of one profiled step)
+    roofline, families = None, {}
+    if rank == 0 and not args.no_profile:
+        torch.cuda.synchronize()
+        lib.vc_profile_enable(1)
+        step()
+        names = ctypes.create_string_buffer(8192)
+        msb = (ctypes.c_float * 256)()
+        cnt = (ctypes.c_int * 256)()
+        n = lib.vc_profile_collect(names, 8192, msb, cnt, 256)
+        lib.vc_profile_enable(0)
+        for i, fn in enumerate(names.value.decode().split(",") if n else []):
+            families[fn] = {"ms_per_step": msb[i], "launches_per_step": cnt[i]}
+        if "logits_decode" in families:
+            f = families["logits_decode"]
+            H = p.decoder_hidden
+            n_g, n_b = 30, 30  # launches: greedy gen_max_len steps with M = B, beam steps with M = B * beam (first beam step M = B)
+            rows = n_g * B + B + (n_b - 1) * B * 5
+            nbytes = f["launches_per_step"] * V * H * 2.0 + rows * (V * 4.0 + H * 2.0)
+            peak = 6454.6
+            try:
+                peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs", peak)
+            except Exception:
+                pass
+            ach = nbytes / (f["ms_per_step"] / 1e3) / 1e9
+            roofline = {"kernel": "logits_decode", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
+                        "frac": ach / peak, "traffic": None, "share_of_step": f["ms_per_step"] / sum(x["ms_per_step"] for x in families.values()),
+                        "note": "algorithmic bytes = W_o (bf16) per launch + fp32 logits rows written for the top-k + bf16 state rows read"}
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         ra = argparse.Namespace(**vars(args))
@@ -311,7 +341,8 @@ def run_decode(args, w, name, rank, world, local_rank):
                            "parallelism": "replicas%d" % world},
                 "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 2 * int(host.numel()) * 4,
                         "d2h_bytes_per_step": B * 30 * 4 + B * 5 * 30 * 4 + B * 5 * 8 + B * 8},
-                "gpu_launches": launches, "clocks": clocks, "roofline": None, "cpu_baseline": cpu_baseline}
+                "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
+                "families": families}
         emit(line)
     if world > 1:
         dist.destroy_process_group()

@@ -51,6 +51,8 @@ struct GemmCore {
   // (OOB zero fill = SAME padding); B is the same un-shifted patch of the output gradient.
   int pw, ph, pn, tw, th, tiles_w, tiles_h, cpk;  // cpk = Cin / 64 chunks per filter tap
   int n_img;                                      // A_WGRAD3x3: image count (an image index >= n_img zero-fills)
+  int tap_rows;  // A_CONV3x3 over a window map (conv1_1): k-block kb is filter ROW kb; the three taps of the row and their
+                 // channels are one contiguous run of the zero-padded input, so the box moves by (0, kb) instead of (s-1, r-1)
 };
 
 struct PatchOrigin {
@@ -204,7 +206,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           } else {
             const int tap = kb / g.cpk;
             const int c0 = (kb - tap * g.cpk) * kBK;
-            const int fr = tap / 3, fs = tap - fr * 3;
+            const int fr = g.tap_rows ? tap + 1 : tap / 3, fs = g.tap_rows ? 1 : tap - (tap / 3) * 3;
 #pragma unroll
             for (int q = 0; q < 4; ++q)
               tma_load_4d(sa + q * 4096, &tmA, &full[stage], c0, po[q].w + fs - 1, po[q].h + fr - 1, po[q].n);

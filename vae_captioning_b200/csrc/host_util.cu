@@ -391,6 +391,41 @@ int plan_conv(GemmPlan* p, const void* in, const void* wt, const ConvGeom& cg, i
   return VC_OK;
 }
 
+int plan_conv1_window(GemmPlan* p, const void* padded, const void* wt, int W, int H, int Nimg, int Cout) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return set_error(VC_E_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  ConvGeom cg;
+  VC_TRY(conv_geometry(&cg, W, H, Nimg, 64, Cout));
+  memset(p, 0, sizeof(*p));
+  GemmCore& g = p->core;
+  const int tn = 4 / (cg.tw * cg.th);
+  g.pw = cg.pw; g.ph = cg.ph; g.pn = cg.pn; g.tw = cg.tw; g.th = cg.th;
+  g.tiles_w = (W + cg.pw * cg.tw - 1) / (cg.pw * cg.tw);
+  g.tiles_h = (H + cg.ph * cg.th - 1) / (cg.ph * cg.th);
+  g.m_tiles = g.tiles_w * g.tiles_h * ((Nimg + cg.pn * tn - 1) / (cg.pn * tn));
+  g.n_tiles = 1;
+  g.cpk = 1;
+  g.k_blocks = 3;
+  g.splits = 1;
+  g.bn = Cout;
+  g.stages = gemm_pick_stages(Cout, 0);
+  g.a_mode = A_CONV3x3;
+  g.b_mn = 0;
+  g.a_switch = -1;
+  g.tap_rows = 1;
+  cuuint64_t dims[4] = {64, (cuuint64_t)W, (cuuint64_t)H + 2, (cuuint64_t)Nimg};
+  cuuint64_t strides[3] = {16, (cuuint64_t)(W + 2) * 16, (cuuint64_t)(H + 2) * (W + 2) * 16};
+  cuuint32_t box[4] = {64, (cuuint32_t)cg.pw, (cuuint32_t)cg.ph, (cuuint32_t)cg.pn};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(&p->tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(padded), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(VC_E_CUDA, "cuTensorMapEncodeTiled(conv1 window map W=%d H=%d N=%d) -> %d", W, H, Nimg, (int)r);
+  p->tmA2 = p->tmA;
+  VC_TRY(make_tmap_2d(&p->tmB, wt, 192, Cout, 192, 64, Cout));
+  return VC_OK;
+}
+
 int plan_conv_wgrad(GemmPlan* p, const void* in, const void* dy, int W, int H, int Nimg, int Cin, int Cout, int bn,
                     int splits) {
   if (Cin % 64 != 0 || Cout % 64 != 0) return set_error(VC_E_SHAPE, "plan_conv_wgrad: Cin=%d Cout=%d must be multiples of 64", Cin, Cout);

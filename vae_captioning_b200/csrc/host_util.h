@@ -103,6 +103,13 @@ int plan_gemm(GemmPlan* p, const Operand& A, const Operand* A2, long long a2_at,
 // D = conv3x3_same(in NHWC bf16 [Nimg,H,W,Cin], Wt bf16 [Cout, 9*Cin] (tap-major, then cin)); Cin % 64 == 0.
 int plan_conv(GemmPlan* p, const void* in, const void* wt, const ConvGeom& g, int bn);
 
+// conv1_1 (Cin = 3) without an im2col matrix: `padded` is the mean-subtracted image as bf16 [Nimg, H+2, W+2, 8] (3 channels
+// + 5 zeros per pixel, a zero border of one pixel). The 3 taps x 3 channels of one filter row are then 24 consecutive
+// elements starting at pixel (x, y + r) of the padded image, so ONE overlapping-stride tensor map {64, W, H+2, Nimg} with a
+// pixel stride of 16 bytes delivers a [128 pixels x 64] k-block per filter row (elements 24..63 run into the neighbouring
+// pixels and meet zero weights). wt: bf16 [Cout, 192], k = r*64 + s*8 + c.
+int plan_conv1_window(GemmPlan* p, const void* padded, const void* wt, int W, int H, int Nimg, int Cout);
+
 // Filter gradient of the same convolution: dW[9*Cin, Cout] (HWIO row-major) += patches(in)^T x dY, contraction over
 // the Nimg*H*W pixels in 64-pixel patches, split-K over `splits` CTAs per output tile (fp32 atomic epilogue).
 // in: NHWC bf16 [Nimg,H,W,Cin]; dy: NHWC bf16 [Nimg,H,W,Cout]; Cin, Cout multiples of 64; bn divides Cout.
