@@ -128,8 +128,7 @@ class Model {
   // --- VGG16 (vgg.cu)
   std::vector<VggLayer> vgg;
   void* vgg_padded = nullptr;  // bf16 [B, 226, 226, 8]: mean-subtracted, zero-bordered input of the window form of conv1_1
-  bool conv1_window = false, conv1_direct = true;
-  void* conv1_w32 = nullptr;   // bf16 [64, 32]: conv1_1 filter for the direct form (k_conv1_direct)
+  bool conv1_window = false;  // VC_CONV1=window
   void *vgg_im2col = nullptr, *fc1_w = nullptr, *fc2_w = nullptr, *fc1_h = nullptr;
   float *fc_acc = nullptr, *fc2_f = nullptr, *st_images = nullptr, *conv1_bias2 = nullptr;
   bool vgg_shadows_dirty = true, vgg_keep = false, vgg_have_unpooled = false;

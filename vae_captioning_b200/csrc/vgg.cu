@@ -92,125 +92,6 @@ __global__ void k_conv1_window_shadow(const float* __restrict__ w, __nv_bfloat16
   }
 }
 
-// ------------------------------------------------------------------------------------------
-// conv1_1 straight from the pixels (VC_CONV1=direct, the default). The layer is 0.17 GFLOP per image against 6.4 MB of
-// output: HBM-bound by a factor of ~6 even at a fifth of the tensor peak, and its contraction (K = 27) is too short for
-// the TMA-fed tcgen05 pipeline to pay -- the A operand would be 128-byte rows of which 54 bytes are data (the im2col
-// form writes and re-reads 0.8 GB for it; the overlapping-stride TMA window form, VC_CONV1=window, is bound by the TMA's
-// row-request rate: 1.27 ms). Here a CTA stages the (4+2) x (32+2) pixel patch it needs (mean subtracted, bf16, zero
-// border = SAME padding) in shared memory, every warp builds the A fragments of its 16 pixels x 32 (27 + 5 zero) taps
-// directly in registers, runs 16 warp-level m16n8k16 MMAs against register-resident filter fragments, adds bias + ReLU,
-// and writes its 16 pixels x 64 channels (2 KB, contiguous in NHWC) with whole-line stores. Reads 0.04 GB (uint8) or
-// 0.15 GB (fp32) and writes 1.64 GB per 256 images, nothing else.
-__device__ __forceinline__ void mma_m16n8k16_bf16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
-
-constexpr int kC1Rows = 4, kC1Cols = 32;                 // output pixels per CTA tile: 4 rows x 32 columns = 8 warp tiles
-constexpr int kC1Pitch = (kC1Cols + 2) * 3 + 2;          // bf16 elements per staged patch row (102 + 2 pad)
-
-template <class TIn>
-__global__ void __launch_bounds__(256) k_conv1_direct(const TIn* __restrict__ img, const __nv_bfloat16* __restrict__ w32,
-                                                       const float* __restrict__ bias, __nv_bfloat16* __restrict__ out,
-                                                       int B, int H, int W) {
-  __shared__ __align__(16) __nv_bfloat16 patch[kC1Rows + 2][kC1Pitch];
-  __shared__ __align__(16) uint8_t stage[8][2048];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int g = lane >> 2, q = lane & 3;
-  // filter fragments: B[k][n] = w32[n * 32 + k], k = r*9 + s*3 + c (HWIO order), columns 27..31 zero
-  uint32_t bf[2][8][2];
-#pragma unroll
-  for (int ks = 0; ks < 2; ++ks)
-#pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
-      const __nv_bfloat16* p = w32 + (nt * 8 + g) * 32 + ks * 16 + q * 2;
-      bf[ks][nt][0] = *reinterpret_cast<const uint32_t*>(p);
-      bf[ks][nt][1] = *reinterpret_cast<const uint32_t*>(p + 8);
-    }
-  float bv[8][2];
-#pragma unroll
-  for (int nt = 0; nt < 8; ++nt) {
-    bv[nt][0] = bias[nt * 8 + q * 2];
-    bv[nt][1] = bias[nt * 8 + q * 2 + 1];
-  }
-  // this thread's 8 taps: k = ks*16 + {0, 8} + q*2 + {0, 1} -> patch offset (row r, element s*3 + c = k - 9 r) or none (k >= 27)
-  int koff[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int k = (i >> 2) * 16 + ((i >> 1) & 1) * 8 + q * 2 + (i & 1);
-    koff[i] = k < 27 ? (k / 9) * kC1Pitch + (k % 9) : -1;
-  }
-  const int tiles_x = W / kC1Cols, tiles_y = H / kC1Rows;
-  const long long total = (long long)B * tiles_y * tiles_x;
-  const float mean[3] = {123.68f, 116.779f, 103.939f};  // image_embeddings.py:30-34
-  const int wy = warp >> 1, wx = (warp & 1) * 16;        // this warp's row inside the tile and first column
-  for (long long tile = blockIdx.x; tile < total; tile += gridDim.x) {
-    const int tx = (int)(tile % tiles_x);
-    const long long r0 = tile / tiles_x;
-    const int ty = (int)(r0 % tiles_y);
-    const long long b = r0 / tiles_y;
-    const int x0 = tx * kC1Cols, y0 = ty * kC1Rows;
-    __syncthreads();  // the previous tile's patch has been consumed
-    for (int i = threadIdx.x; i < (kC1Rows + 2) * (kC1Cols + 2) * 3; i += 256) {
-      const int c = i % 3, px = (i / 3) % (kC1Cols + 2), py = i / (3 * (kC1Cols + 2));
-      const int yy = y0 + py - 1, xx = x0 + px - 1;
-      float v = 0.f;
-      if (yy >= 0 && yy < H && xx >= 0 && xx < W) v = static_cast<float>(img[((b * H + yy) * W + xx) * 3 + c]) - mean[c];
-      patch[py][px * 3 + c] = __float2bfloat16(v);
-    }
-    __syncthreads();
-    // A fragments: rows = pixels (wx + g) and (wx + g + 8) of tile row wy
-    const __nv_bfloat16* base0 = &patch[wy][(wx + g) * 3];
-    const __nv_bfloat16* base1 = base0 + 8 * 3;
-    uint32_t a[2][4];
-#pragma unroll
-    for (int ks = 0; ks < 2; ++ks) {
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {  // h: k + 0 / k + 8
-        const int i0 = ks * 4 + h * 2;
-        const uint16_t z = 0;
-        const uint16_t p00 = koff[i0] >= 0 ? *reinterpret_cast<const uint16_t*>(base0 + koff[i0]) : z;
-        const uint16_t p01 = koff[i0 + 1] >= 0 ? *reinterpret_cast<const uint16_t*>(base0 + koff[i0 + 1]) : z;
-        const uint16_t p10 = koff[i0] >= 0 ? *reinterpret_cast<const uint16_t*>(base1 + koff[i0]) : z;
-        const uint16_t p11 = koff[i0 + 1] >= 0 ? *reinterpret_cast<const uint16_t*>(base1 + koff[i0 + 1]) : z;
-        a[ks][h * 2 + 0] = (uint32_t)p00 | ((uint32_t)p01 << 16);  // (row g,     k .. k+1)
-        a[ks][h * 2 + 1] = (uint32_t)p10 | ((uint32_t)p11 << 16);  // (row g + 8, k .. k+1)
-      }
-    }
-    uint8_t* st = stage[warp];
-#pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
-      float d[4] = {0.f, 0.f, 0.f, 0.f};
-      mma_m16n8k16_bf16(d, a[0], bf[0][nt][0], bf[0][nt][1]);
-      mma_m16n8k16_bf16(d, a[1], bf[1][nt][0], bf[1][nt][1]);
-      // bias + ReLU; rows g and g + 8, channels nt*8 + q*2 .. +1; 16-byte chunk nt of a 128-byte row, XOR-swizzled by row
-      const uint32_t lo = pack_bf16(fmaxf(d[0] + bv[nt][0], 0.f), fmaxf(d[1] + bv[nt][1], 0.f));
-      const uint32_t hi = pack_bf16(fmaxf(d[2] + bv[nt][0], 0.f), fmaxf(d[3] + bv[nt][1], 0.f));
-      *reinterpret_cast<uint32_t*>(st + g * 128 + ((nt ^ (g & 7)) << 4) + q * 4) = lo;
-      *reinterpret_cast<uint32_t*>(st + (g + 8) * 128 + ((nt ^ ((g + 8) & 7)) << 4) + q * 4) = hi;
-    }
-    __syncwarp();
-    __nv_bfloat16* dst = out + (((b * H + y0 + wy) * W + x0 + wx) * 64);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int e = i * 32 + lane;  // 16-byte chunk index in the warp's 2 KB: row e / 8, chunk e % 8
-      const int r = e >> 3, c = e & 7;
-      *reinterpret_cast<uint4*>(dst + r * 64 + c * 8) = *reinterpret_cast<const uint4*>(st + r * 128 + ((c ^ (r & 7)) << 4));
-    }
-    __syncwarp();
-  }
-}
-// w32 bf16 [64, 32]: w32[co * 32 + k] = W[k][co] for k < 27 (HWIO rows r*9 + s*3 + c), zero for k = 27..31
-__global__ void k_conv1_direct_shadow(const float* __restrict__ w, __nv_bfloat16* __restrict__ w32) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < 64 * 32) {
-    const int co = i / 32, k = i % 32;
-    w32[i] = __float2bfloat16(k < 27 ? w[k * 64 + co] : 0.f);
-  }
-}
-
 // 2x2 stride-2 max-pool over NHWC bf16 (standalone form, used when un-pooled activations are kept).
 __global__ void k_maxpool2(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, int B, int H, int W,
                            int C) {
@@ -295,12 +176,10 @@ int Model::vgg_init() {
     if (L.pool) VC_TRY(dalloc((uint16_t**)&L.pooled, (size_t)B * (L.hw / 2) * (L.hw / 2) * L.cout));
   }
   VC_TRY(dalloc((uint16_t**)&vgg_im2col, (size_t)B * 224 * 224 * 32));
-  {  // conv1_1 form: direct (default) | window (overlapping-stride TMA map) | im2col (round 1)
+  {  // conv1_1 form: im2col + two-pixel-row GEMM (default) | window (overlapping-stride TMA map, VC_CONV1=window)
     const char* e = getenv("VC_CONV1");
     conv1_window = e && strcmp(e, "window") == 0;
-    conv1_direct = !(e && (strcmp(e, "window") == 0 || strcmp(e, "im2col") == 0));
   }
-  VC_TRY(dalloc((uint16_t**)&conv1_w32, 64 * 32));
   if (conv1_window) VC_TRY(dalloc((uint16_t**)&vgg_padded, (size_t)B * 226 * 226 * 8 + 256));  // + slack: the last window overruns
   VC_TRY(dalloc((uint16_t**)&fc1_w, (size_t)25088 * 4096));
   VC_TRY(dalloc((uint16_t**)&fc2_w, (size_t)4096 * 4096));
@@ -318,7 +197,6 @@ int Model::vgg_refresh_shadows(cudaStream_t s) {
   ProfTag ptag("refresh_shadows");
   {
     ProfScope ps(s, "refresh_shadows");
-    k_conv1_direct_shadow<<<8, 256, 0, s>>>(pp(vgg[0].p_w), (__nv_bfloat16*)conv1_w32);
     if (conv1_window)
       k_conv1_window_shadow<<<48, 256, 0, s>>>(pp(vgg[0].p_w), (__nv_bfloat16*)vgg[0].wt);
     else
@@ -408,7 +286,7 @@ int Model::vgg_forward(const float* images, float* fc2_out, int B, bool keep_unp
     else
       k_pad_rgb8<float><<<ew_grid(n, 256), 256, 0, s>>>(images, (uint4*)vgg_padded, B, 224, 224);
   }
-  if (!(conv1_window || conv1_direct) || cfg.fine_tune) {  // the im2col matrix: conv1_1's A operand in the older form, and the filter-gradient operand
+  if (!conv1_window || cfg.fine_tune) {  // the im2col matrix: conv1_1's A operand in the older form, and the filter-gradient operand
     ProfScope ps(s, "im2col_rgb");
     const long long n = (long long)B * 224 * 224;
     if (images_u8)  // uint8 pixels as the HDF5 image store keeps them (utils/batch_gen.py:278-294): a quarter of the bytes
@@ -420,19 +298,6 @@ int Model::vgg_forward(const float* images, float* fc2_out, int B, bool keep_unp
   const void* x = vgg_im2col;
   for (int l = 0; l < 13; ++l) {
     VggLayer& L = vgg[l];
-    if (l == 0 && conv1_direct) {
-      ProfScope ps(s, "conv1_1");
-      const int grid = num_sms() * 6;
-      if (images_u8)
-        k_conv1_direct<uint8_t><<<grid, 256, 0, s>>>(reinterpret_cast<const uint8_t*>(images), (const __nv_bfloat16*)conv1_w32,
-                                                      pp(L.p_b), (__nv_bfloat16*)L.out, B, 224, 224);
-      else
-        k_conv1_direct<float><<<grid, 256, 0, s>>>(images, (const __nv_bfloat16*)conv1_w32, pp(L.p_b), (__nv_bfloat16*)L.out, B,
-                                                    224, 224);
-      VC_CUDA(cudaGetLastError());
-      x = L.out;
-      continue;
-    }
     VC_TRY(vgg_conv_layer(l, x, B, !keep_unpooled, s));
     if (L.pool) {
       if (keep_unpooled) {
