@@ -650,8 +650,8 @@ constexpr int kCeVecs = 6;  // 8-element vectors per thread: V <= 256 * 6 * 8 = 
 __global__ void __launch_bounds__(kCeThreads)
 k_ce(__nv_bfloat16* __restrict__ logits, long long ld, const int* __restrict__ lbl, int N, int T, int V,
      float* __restrict__ sums, float* __restrict__ ce_rows, const float* __restrict__ count, float loss_scale,
-     int write_grad) {
-  const int row = blockIdx.x;
+     int write_grad, int row0) {
+  const int row = blockIdx.x + row0;
   const int t = row / N, n = row - t * N;
   const int label = lbl[(long long)n * T + t];
   uint4* p = reinterpret_cast<uint4*>(logits + (long long)row * ld);
@@ -747,8 +747,8 @@ k_ce(__nv_bfloat16* __restrict__ logits, long long ld, const int* __restrict__ l
 __global__ void __launch_bounds__(kCeThreads)
 k_ce_wide(__nv_bfloat16* __restrict__ logits, long long ld, const int* __restrict__ lbl, int N, int T, int V,
           float* __restrict__ sums, float* __restrict__ ce_rows, const float* __restrict__ count, float loss_scale,
-          int write_grad) {
-  const int row = blockIdx.x;
+          int write_grad, int row0) {
+  const int row = blockIdx.x + row0;
   const int t = row / N, n = row - t * N;
   const int label = lbl[(long long)n * T + t];
   __nv_bfloat16* p = logits + (long long)row * ld;
@@ -802,15 +802,16 @@ k_ce_wide(__nv_bfloat16* __restrict__ logits, long long ld, const int* __restric
 }
 
 int ce_rows(cudaStream_t s, void* logits, long long ld, const int* lbl, int N, int T, int V, float* sums, float* ce_out,
-            const float* count, float loss_scale, int write_grad) {
+            const float* count, float loss_scale, int write_grad, int row0, int n_rows) {
+  if (n_rows < 0) n_rows = N * T - row0;
   if (ld % 8 != 0 || (reinterpret_cast<uintptr_t>(logits) & 15) != 0)
     return set_error(VC_E_SHAPE, "logits rows must be 16-byte aligned (pitch multiple of 8)");
   {
     ProfScope ps(s, "ce");
     if (V > kCeThreads * kCeVecs * 8)
-      k_ce_wide<<<N * T, kCeThreads, 0, s>>>((__nv_bfloat16*)logits, ld, lbl, N, T, V, sums, ce_out, count, loss_scale, write_grad);
+      k_ce_wide<<<n_rows, kCeThreads, 0, s>>>((__nv_bfloat16*)logits, ld, lbl, N, T, V, sums, ce_out, count, loss_scale, write_grad, row0);
     else
-      k_ce<<<N * T, kCeThreads, 0, s>>>((__nv_bfloat16*)logits, ld, lbl, N, T, V, sums, ce_out, count, loss_scale, write_grad);
+      k_ce<<<n_rows, kCeThreads, 0, s>>>((__nv_bfloat16*)logits, ld, lbl, N, T, V, sums, ce_out, count, loss_scale, write_grad, row0);
   }
   VC_CUDA(cudaGetLastError());
   return VC_OK;

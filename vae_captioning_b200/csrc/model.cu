@@ -711,15 +711,55 @@ int Model::forward(StepInputs& in, bool write_grad, cudaStream_t s) {
   VC_TRY(embed_gather(s, dec_emb_h, in.cap_in, (uint16_t*)dec.X + (size_t)dec.pre * N * E,
                       cfg.dec_keep_rate < 1.f ? in.rng.emb_keep_dev : nullptr, 1.f / cfg.dec_keep_rate, N, T, E, V));
   VC_TRY(lstm_forward(dec, N, T, in.len, Out, cfg.dec_lstm_drop < 1.f ? in.rng.out_keep_dev : nullptr, s));
-  {
-    Operand A{Out, (long long)T * N, Hd, Hd, false}, Bw{wo_t, V, Hd, Hd, false};
-    ProfTag ptag("logits_fwd");
-    VC_TRY(gemm_tma_rows(s, A, Bw, T * N, V, Hd, logits, VP, pp(pidx("decoder/rnn_logits/bias")), 0, 256));
-  }
   // masked cross-entropy (main.py:152-158); AG differentiates the sum of an [N] lower bound (Q2)
   VC_TRY(count_mask(s, in.cap_lbl, (long long)N * T, scal + 2));
   const float loss_scale = cfg.prior == VC_PRIOR_AG ? (float)N : 1.f;
-  VC_TRY(ce_rows(s, logits, VP, in.cap_lbl, N, T, V, scal, ce_row, scal + 2, loss_scale, write_grad ? 1 : 0));
+  const long long rows_all = (long long)T * N;
+  // VC_VOCAB_CHUNK=<rows> turns the row-chunked form on (off by default: measured slower, see below and DESIGN section 8)
+  static const int chunk_env = [] { const char* e = getenv("VC_VOCAB_CHUNK"); return e ? atoi(e) : 0; }();
+  vocab_bwd_done = false;
+  if (write_grad && chunk_env > 0 && rows_all > 2 * chunk_env) {
+    // Training step: the [T*N, V] logits matrix (580 MB at N = 1280) is produced, turned into dlogits, column-summed
+    // and contracted with W_o^T one row chunk at a time, so that a chunk (2048 rows = 46 MB) is still in the 126 MB L2
+    // when the next kernel reads it: logits_fwd(chunk) -> CE(chunk) -> bias column sum(chunk) -> dgrad(chunk). Of the six
+    // passes the matrix used to make over HBM (fwd write, CE read + write, dgrad read, bias read, wgrad read) the
+    // write-back of dlogits and the weight-gradient read remain. The gradient buffers this touches are zeroed here
+    // instead of at the top of backward(). MEASURED (B200, caption model alone, ms per step, N = 1280 / N = 640): un-chunked
+    // 3.03 / 2.41; 4096-row chunks 3.26 / 2.47; 2048 rows 3.44 / 2.56; 1024 rows 3.86 / 2.77 -- the per-chunk GEMMs lose
+    // more to wave quantisation, split-K atomics of the input gradient and 4 launches per chunk than the L2 hits return.
+    const int rows_c = (chunk_env + kBM - 1) / kBM * kBM;
+    VC_CUDA(cudaMemsetAsync(Gf, 0, (size_t)(n_adam + 64) * sizeof(float), s));
+    VC_CUDA(cudaMemsetAsync(dOut, 0, (size_t)rows_all * Hd * sizeof(float), s));
+    const float* b_o = pp(pidx("decoder/rnn_logits/bias"));
+    float* db_o = gp(pidx("decoder/rnn_logits/bias"));
+    for (long long r0 = 0; r0 < rows_all; r0 += rows_c) {
+      const int rc = (int)std::min<long long>(rows_c, rows_all - r0);
+      uint16_t* lg = (uint16_t*)logits + r0 * VP;
+      {
+        Operand A{(uint16_t*)Out + r0 * Hd, rc, Hd, Hd, false}, Bw{wo_t, V, Hd, Hd, false};
+        ProfTag ptag("logits_fwd");
+        VC_TRY(gemm_tma_rows(s, A, Bw, rc, V, Hd, lg, VP, b_o, 0, 256));
+      }
+      VC_TRY(ce_rows(s, logits, VP, in.cap_lbl, N, T, V, scal, ce_row, scal + 2, loss_scale, 1, (int)r0, rc));
+      VC_TRY(colsum_bf16(s, lg, rc, V, VP, db_o));
+      {
+        Operand A{lg, rc, V, VP, false}, Bw{wo_nat, Hd, V, VP, false};
+        EpiStore e{};
+        e.out = dOut + r0 * Hd; e.ld = Hd; e.alpha = 1.f; e.atomic = 1;
+        const int tiles = ((rc + kBM - 1) / kBM) * ((Hd + 255) / 256);
+        ProfTag ptag("logits_dgrad");
+        VC_TRY(gemm_store(s, A, nullptr, 0, Bw, rc, Hd, V, e, Hd % 256 == 0 ? 256 : 64, std::max(1, num_sms() / tiles)));
+      }
+    }
+    vocab_bwd_done = true;
+  } else {
+    {
+      Operand A{Out, rows_all, Hd, Hd, false}, Bw{wo_t, V, Hd, Hd, false};
+      ProfTag ptag("logits_fwd");
+      VC_TRY(gemm_tma_rows(s, A, Bw, T * N, V, Hd, logits, VP, pp(pidx("decoder/rnn_logits/bias")), 0, 256));
+    }
+    VC_TRY(ce_rows(s, logits, VP, in.cap_lbl, N, T, V, scal, ce_row, scal + 2, loss_scale, write_grad ? 1 : 0));
+  }
   last_ann = annealing_coeff(cfg, in.global_step);
   have_forward = true;
   logits_intact = !write_grad;
@@ -732,14 +772,14 @@ int Model::backward(const StepInputs& in, cudaStream_t s) {
   const int B = in.B, T = in.T, C = cfg.num_captions, N = B * C;
   const int E = cfg.embed_size, Hd = cfg.decoder_hidden, Z = cfg.latent_size, S = cfg.gen_z_samples, V = cfg.vocab_size,
             F = cfg.cnn_feature_size, K = cfg.num_clusters;
-  VC_CUDA(cudaMemsetAsync(Gf, 0, (size_t)(n_adam + 64) * sizeof(float), s));
+  if (!vocab_bwd_done) VC_CUDA(cudaMemsetAsync(Gf, 0, (size_t)(n_adam + 64) * sizeof(float), s));
   const long long rows = (long long)T * N;
   // logits layer: dOut = dlogits x W_o^T ; dW_o = Out^T x dlogits ; db_o = colsum(dlogits)
   {
     Operand A{logits, rows, V, VP, false}, Bw{wo_nat, Hd, V, VP, false};
     EpiStore e{};
     e.out = dOut; e.ld = Hd; e.alpha = 1.f;
-    {
+    if (!vocab_bwd_done) {  // (the row-chunked forward has done the input gradient and the bias column sum already)
       ProfTag ptag("logits_dgrad");
       VC_TRY(gemm_store(s, A, nullptr, 0, Bw, (int)rows, Hd, V, e, Hd % 256 == 0 ? 256 : 64, 1));
     }
@@ -769,7 +809,7 @@ int Model::backward(const StepInputs& in, cudaStream_t s) {
       e2.atomic = splits > 1 ? 1 : 0;
       VC_TRY(gemm_store(s, A2, nullptr, 0, B2, Hd, V, (int)rows, e2, 256, splits));
     }
-    VC_TRY(colsum_bf16(s, logits, rows, V, VP, gp(pidx("decoder/rnn_logits/bias"))));
+    if (!vocab_bwd_done) VC_TRY(colsum_bf16(s, logits, rows, V, VP, gp(pidx("decoder/rnn_logits/bias"))));
     // data parallel: each group of gradients is summed over the ranks as soon as its last producer is enqueued
     // (comm.cu); the vocabulary projection's 23 MB travel under the decoder's BPTT
     VC_TRY(grad_ready_params({pidx("decoder/rnn_logits/kernel"), pidx("decoder/rnn_logits/bias")}, s));

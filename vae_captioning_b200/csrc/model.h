@@ -79,6 +79,7 @@ class Model {
   int64_t adam_t = 0;       // TF global_step of the optimiser (1-based after the first update)
   bool shadows_dirty = true, decode_shadows_dirty = true;
   bool have_forward = false, logits_intact = false;
+  bool vocab_bwd_done = false;  // the row-chunked forward already produced dOut and the vocabulary bias gradient
   int lastN = 0, lastT = 0;
   float last_ann = 1.f;
 

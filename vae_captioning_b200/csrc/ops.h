@@ -146,8 +146,9 @@ int sample_z(cudaStream_t s, const float* mu, const float* sd, const float* eps,
 int dz_reduce(cudaStream_t s, const float* dz, const float* eps, unsigned long long seed, unsigned long long offset,
               const float* sd, const float* dkl_dmu, const float* dkl_dsd, float kl_scale, void* dheads, long long ld,
               int zp, float* dmu_out, float* dsd_out, int S, int N, int Z);
+// rows [row0, row0 + n_rows) of the time-major logits matrix (n_rows < 0: all rows from row0)
 int ce_rows(cudaStream_t s, void* logits, long long ld, const int* lbl, int N, int T, int V, float* sums, float* ce_out,
-            const float* count, float loss_scale, int write_grad);
+            const float* count, float loss_scale, int write_grad, int row0 = 0, int n_rows = -1);
 int count_mask(cudaStream_t s, const int* lbl, long long n, float* count);
 int colsum_bf16(cudaStream_t s, const void* x, long long rows, int cols, long long ld, float* out);
 int sumsq(cudaStream_t s, const float* g, long long n, float* out);
