@@ -521,11 +521,15 @@ def read_bundle(prefix, names=None, verify=True):
 
 def update_checkpoint_state(directory, prefix, keep=()):
     """The text-format CheckpointState file `checkpoint` that Saver.save maintains next to the bundles."""
+    # Saver writes paths RELATIVE to the state file's directory when the bundle lives there (so a checkpoint directory
+    # can be moved); tf.train.latest_checkpoint joins them back
+    def rel(p):
+        return os.path.basename(p) if os.path.abspath(os.path.dirname(p) or ".") == os.path.abspath(directory) else p
     paths = [p for p in keep if p != prefix] + [prefix]
     with open(os.path.join(directory, "checkpoint"), "w") as f:
-        f.write('model_checkpoint_path: "%s"\n' % prefix)
+        f.write('model_checkpoint_path: "%s"\n' % rel(prefix))
         for p in paths:
-            f.write('all_model_checkpoint_paths: "%s"\n' % p)
+            f.write('all_model_checkpoint_paths: "%s"\n' % rel(p))
 
 
 def latest_checkpoint(directory):
@@ -537,5 +541,5 @@ def latest_checkpoint(directory):
         for line in f:
             if line.startswith("model_checkpoint_path:"):
                 v = line.split(":", 1)[1].strip().strip('"')
-                return v if os.path.isabs(v) or os.path.exists(v + ".index") else os.path.join(directory, v)
+                return v if os.path.isabs(v) else os.path.join(directory, v)
     return None
