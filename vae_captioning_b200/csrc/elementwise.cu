@@ -133,6 +133,19 @@ __global__ void __launch_bounds__(256) k_refresh_multi(const RefreshJobs jobs) {
     }
     return;
   }
+  if (J.kind == 2) {
+    const unsigned int total = (unsigned int)J.rows * (unsigned int)J.cols;
+    const unsigned int i0 = b * 2048u + threadIdx.x;
+    const unsigned int cin = (unsigned int)J.gate_h, cout = (unsigned int)J.cols;
+#pragma unroll
+    for (unsigned int k = 0; k < 8; ++k) {
+      const unsigned int i = i0 + k * 256u;
+      if (i >= total) break;
+      const unsigned int co = i % cout, r = i / cout, ci = r % cin, tap = r / cin;
+      dst[(size_t)ci * 9 * cout + (8 - tap) * cout + co] = __float2bfloat16(src[i]);
+    }
+    return;
+  }
   const int tiles_c = (J.cols + 31) / 32;
   const int c0 = (int)(b % tiles_c) * 32, r0 = (int)(b / tiles_c) * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -159,7 +172,9 @@ int refresh_multi(cudaStream_t s, RefreshJobs& jobs) {
   for (int i = 0; i < jobs.n; ++i) {
     RefreshJob& J = jobs.j[i];
     J.blk0 = blocks;
-    if (J.kind == 0) {
+    if (J.kind == 2) {
+      blocks += (int)(((long long)J.rows * J.cols + 2047) / 2048);
+    } else if (J.kind == 0) {
       J.vec4 = (J.cols % 4 == 0 && J.ld_src % 4 == 0 && J.ld_dst % 4 == 0 && (reinterpret_cast<uintptr_t>(J.src) & 15) == 0 &&
                 (reinterpret_cast<uintptr_t>(J.dst) & 7) == 0) ? 1 : 0;
       const long long total = (long long)J.rows * J.cols;

@@ -111,12 +111,12 @@ struct RefreshJob {
   __nv_bfloat16* dst;
   int rows, cols;       // of src
   int ld_src, ld_dst;
-  int kind;             // 0: cast, 1: transpose (+ LSTM gate interleave when gate_h > 0)
+  int kind;             // 0: cast, 1: transpose (+ LSTM gate interleave when gate_h > 0), 2: conv dgrad filter (tap-reversed, rows = 9*Cin taps x channels, cols = Cout; gate_h = Cin)
   int gate_h, upt;
   int vec4, blk0;       // filled by refresh_multi
 };
 struct RefreshJobs {
-  RefreshJob j[16];
+  RefreshJob j[32];
   int n = 0;
   void cast(const float* src, void* dst, int rows, int cols, int ld_src, int ld_dst) {
     j[n++] = RefreshJob{src, (__nv_bfloat16*)dst, rows, cols, ld_src, ld_dst, 0, 0, 0, 0, 0};
@@ -124,6 +124,11 @@ struct RefreshJobs {
   void transpose(const float* src, void* dst, int rows, int cols, int ld_src, int ld_dst, int gate_h, int upt) {
     j[n++] = RefreshJob{src, (__nv_bfloat16*)dst, rows, cols, ld_src, ld_dst, 1, gate_h, upt, 0, 0};
   }
+  // dst[ci, (8 - tap) * Cout + co] = bf16(W[tap, ci, co]): the tap-reversed [Cin, 9*Cout] filter of the input-gradient convolution
+  void dgrad_filter(const float* w_hwio, void* dst, int cin, int cout) {
+    j[n++] = RefreshJob{w_hwio, (__nv_bfloat16*)dst, 9 * cin, cout, cout, 9 * cout, 2, cin, 0, 0, 0};
+  }
+  bool full() const { return n >= 32; }
 };
 int refresh_multi(cudaStream_t s, RefreshJobs& jobs);
 int keep_mask(cudaStream_t s, float* mask, long long n, float keep_prob, unsigned long long seed, unsigned long long offset);

