@@ -51,3 +51,46 @@ def test_train_checkpoint_inference_roundtrip(tmp_path, monkeypatch, kw):
         caps = json.load(open(name))
         assert len(caps) == 3 * p.batch_size and set(caps[0]) == {"image_id", "caption"}
         assert isinstance(caps[0]["caption"], str)
+
+
+def test_ag_inference_uses_the_cluster_means_file(tmp_path, monkeypatch):
+    """with --prior AG the generation prior's mean is built from c_means (decoder.py:45-71), which the
+    reference creates in both modes and keeps in ./pickles/cluster_means.pickle. The inference driver must load them:
+    captions decoded with two different cluster-means files differ, and run() leaves the file behind when it made it."""
+    import pickle
+    monkeypatch.chdir(tmp_path)
+    p = small_params(prior="AG", use_c_v=True, latent_size=8, std=0.0001)
+    feeder = M.SyntheticFeeder(p, p.vocab_size, batches=2, T=6)
+    M.run(p, feeder=feeder, out=lambda *_: None, max_len=8).close()
+    assert os.path.exists(M.CLUSTER_MEANS_FILE)
+    outs = []
+    for scale in (1.0, -40.0):
+        means = np.asarray(pickle.load(open(M.CLUSTER_MEANS_FILE, "rb")), dtype=np.float32)
+        with open(M.CLUSTER_MEANS_FILE, "wb") as f:
+            pickle.dump(means * scale, f)
+        M.run(small_params(mode="inference", sample_gen="greedy", prior="AG", use_c_v=True, latent_size=8, std=0.0001),
+              feeder=feeder, out=lambda *_: None, max_len=8).close()
+        outs.append(json.load(open("val_unit.json")))
+    assert [c["caption"] for c in outs[0]] != [c["caption"] for c in outs[1]]
+
+
+def test_images_through_the_decoder_after_fine_tune():
+    """generation after --fine_tune feeds raw images; the decoder runs them through the engine's VGG16
+    first and gives the same captions as decoding the fc2 features directly."""
+    from test_decode_gpu import FakeDict
+    from vae_captioning_b200 import synthetic
+    from vae_captioning_b200.decode import Decoder
+    from vae_captioning_b200.engine import Engine
+    p = small_params(fine_tune=True, mode="inference")
+    eng = Engine(p, vocab_size=p.vocab_size, max_batch=2, max_len=8)
+    eng.load_state(synthetic.init_weights(eng.variables(), seed=4))
+    dec = Decoder(eng, p, FakeDict(p.vocab_size))
+    g = np.random.Generator(np.random.PCG64(5))
+    images = g.integers(0, 256, size=(3, 224, 224, 3), dtype=np.uint8)  # more images than max_batch: chunked VGG forward
+    feats = np.concatenate([eng.vgg_forward(images[i:i + 2]) for i in range(0, 3, 2)])
+    t_img, l_img = dec.greedy_tokens(images, None, "greedy", {"seed": 3})
+    t_ft, l_ft = dec.greedy_tokens(feats, None, "greedy", {"seed": 3})
+    assert np.array_equal(t_img, t_ft) and np.array_equal(l_img, l_ft)
+    with pytest.raises(ValueError):
+        dec.greedy_tokens(images[:, :100], None, "greedy")
+    eng.close()
