@@ -880,6 +880,9 @@ int Model::backward(const StepInputs& in, cudaStream_t s) {
     VC_TRY(lstm_backward(enc, N, T, in.len, nullptr, nullptr, s));
     VC_TRY(embed_scatter(s, enc.dX + (size_t)enc.pre * N * E, in.cap_lbl, gp(pidx("encoder/enc_embeddings")), nullptr, 1.f,
                          g_tail + 0, N, T, E, V));
+    // both embedding-slice norms are final now: the encoder table and the tail leave here, so that only the two small
+    // projections (4 MB) are left for the last, fully exposed bucket
+    VC_TRY(grad_ready_params({pidx("encoder/enc_embeddings"), -2}, s));
   }
   // imf_emb: gradient of the tiled projection sums over the C captions of an image (Q7)
   VC_TRY(tile_reduce(s, dec.dX, cfg.no_encoder ? nullptr : enc.dX, nullptr, dimf_h, B, C, E));
@@ -912,11 +915,11 @@ int Model::backward(const StepInputs& in, cudaStream_t s) {
     VC_TRY(vgg_backward(dfeats_f, B, s));
   }
   if (comm != nullptr) {
-    // last bucket: encoder LSTM + table, the two small projections, and the 64-float tail whose first two entries are
-    // the per-token embedding-slice squared norms of this rank (Q4: the norm is over every tower's slices)
+    // last bucket: the two small projections (and, without an encoder, the 64-float tail whose first two entries are
+    // the per-token embedding-slice squared norms of this rank; Q4: the norm is over every tower's slices)
     // one NCCL group (one launch) for all of it; params are listed in buffer order so neighbours merge into one range
     VC_TRY(grad_ready_params({pidx("imf_emb/kernel"), pidx("imf_emb/bias"), cfg.use_c_v ? pidx("cv_emb/kernel") : -1,
-                              cfg.use_c_v ? pidx("cv_emb/bias") : -1, cfg.no_encoder ? -1 : pidx("encoder/enc_embeddings"), -2}, s));
+                              cfg.use_c_v ? pidx("cv_emb/bias") : -1, cfg.no_encoder ? -2 : -1}, s));
   }
   VC_TRY(side_join(s));  // the optimiser (or the caller's own all-reduce) follows on `s`
   // squared norm of the dense (non-embedding) gradients -> tail[2] (apply); embedding slices are in tail[0..1] (Q4)
