@@ -20,6 +20,10 @@ int vc_gemm_bf16(const void* A, int a_mn, long long lda, const void* B, int b_mn
                  const float* bias, int M, int N, int K, int bn, int splits, int relu, int out_bf16, int atomic,
                  void* stream);
 
+/* CTA-pair policy of the tcgen05 mainloop (cluster of 2, cta_group::2): -1 = automatic (default; VC_PAIR in the
+ * environment), 0 = never, 1 = wherever the tile shape allows it. Lets the parity tests run the same GEMM both ways. */
+void vc_test_pair_mode(int mode);
+
 /* Gradients of one 3x3 SAME convolution (tf.nn.conv2d in utils/image_embeddings.py:40-205, differentiated by
  * ops/optimizers.py:49-82): x, dy bf16 NHWC; w fp32 HWIO; dw fp32 [9*Cin, Cout] (zeroed by the call); dx bf16 NHWC. */
 int vc_conv3x3_bwd(const void* x, const void* dy, const float* w, float* dw, void* dx, int B, int hw, int cin, int cout,

@@ -103,3 +103,59 @@ def test_gemm_splitk_ragged_atomic():
     run_gemm(70, 45, 4096, 1, 1, 64, splits=8, bias=False, ldo=45)
     run_gemm(512, 1000, 1536, 1, 1, 256, splits=3, ldo=1001)
     run_gemm(97, 130, 256, 0, 0, 128, force_atomic=True)
+
+
+@pytest.fixture
+def pair_forced():
+    """Run the mainloop as CTA pairs (cluster of 2, tcgen05 cta_group::2) wherever the tile shape allows it."""
+    lib = L.load()
+    lib.vc_test_pair_mode(1)
+    yield
+    lib.vc_test_pair_mode(-1)
+
+
+@pytest.mark.parametrize("a_mn", [0, 1])
+@pytest.mark.parametrize("b_mn", [0, 1])
+@pytest.mark.parametrize("bn", [64, 128, 256])
+def test_gemm_pair_major_modes(pair_forced, a_mn, b_mn, bn):
+    # bn = 64 with an MN-major B is not pairable (a CTA would stage 32 columns): falls back to single CTAs, same result
+    run_gemm(384, 512, 256, a_mn, b_mn, bn)
+    run_gemm(512, 768, 320, a_mn, b_mn, bn, seed=3)
+
+
+def test_gemm_pair_odd_tiles_and_ragged(pair_forced):
+    # odd m-tile counts (the surplus tile of the last pair reads zero fill and stores nothing), ragged M / N / K
+    run_gemm(130, 300, 520, 0, 0, 64)
+    run_gemm(257, 11313 // 8, 72, 0, 0, 128)
+    run_gemm(300, 200, 1500, 1, 1, 128)
+    run_gemm(641, 333, 192, 0, 1, 256, ldo=333)
+    run_gemm(200, 100, 192, 0, 0, 32)
+
+
+def test_gemm_pair_persistent_and_splitk(pair_forced):
+    # more pair tiles than clusters: ring wrap, TMEM double buffer, remote tempty arrivals over many tiles
+    run_gemm(8192, 2048, 192, 0, 0, 64)
+    run_gemm(4096, 4096, 1024, 0, 0, 256)
+    run_gemm(4096, 1024, 512, 1, 1, 256, out_bf16=1)
+    run_gemm(512, 512, 4096, 0, 0, 128, splits=7)
+    run_gemm(512, 1000, 1536, 1, 1, 256, splits=3, ldo=1001)
+
+
+def test_gemm_pair_matches_single_bitwise():
+    # same k order per tile, same fp32 accumulation: pairing changes which SM computes a tile, not the result
+    lib = L.load()
+    outs = []
+    for mode in (0, 1):
+        lib.vc_test_pair_mode(mode)
+        try:
+            g = torch.Generator(device="cpu").manual_seed(5)
+            A = torch.randn(1024, 512, generator=g).to(torch.bfloat16).cuda()
+            B = torch.randn(768, 512, generator=g).to(torch.bfloat16).cuda()
+            out = torch.zeros(1024, 768, device="cuda")
+            L.check(lib.vc_gemm_bf16(L.ptr(A), 0, ctypes.c_longlong(512), L.ptr(B), 0, ctypes.c_longlong(512), L.ptr(out),
+                                     ctypes.c_longlong(768), None, 1024, 768, 512, 256, 1, 0, 0, 0, L.stream_ptr()))
+            torch.cuda.synchronize()
+            outs.append(out.clone())
+        finally:
+            lib.vc_test_pair_mode(-1)
+    assert torch.equal(outs[0], outs[1])

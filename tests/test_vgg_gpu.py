@@ -79,3 +79,31 @@ def test_vgg_requires_cnn_handle():
     with pytest.raises(Exception):
         eng.vgg_forward(images.numpy())
     eng.close()
+
+
+def test_vgg_conv_layers_cta_pairs_match_single_ctas_bitwise():
+    """Every convolution kernel has a CTA-pair form (cluster of 2, tcgen05 cta_group::2: the generic implicit GEMM and both
+    halo kernels). Pairing changes which SM holds which operand half, not the order of the fp32 accumulation, so each
+    layer's activation must be bit-identical to the single-CTA form -- B = 3 gives odd m-tile counts (a surplus tile in
+    the last pair)."""
+    from vae_captioning_b200 import lib as L
+    lib = L.load()
+    B = 3
+    cfg, params, images = make_vgg_case(B, seed=7)
+    names = ["conv1_2", "conv2_1", "conv2_2", "conv3_1", "conv3_3", "conv4_2", "conv5_3", "pool5"]
+    acts = {}
+    try:
+        for mode in (0, 1):
+            lib.vc_test_pair_mode(mode)
+            eng = engine_for(cfg, params, B, 5, with_cnn=True)
+            eng.vgg_keep_activations(True)
+            eng.vgg_forward(images.numpy())
+            acts[mode] = {n: eng.vgg_activation(n, B).copy() for n in names}
+            eng.vgg_keep_activations(False)
+            eng.vgg_forward(images.numpy())
+            acts[mode]["pool5_fused"] = eng.vgg_activation("pool5", B).copy()
+            eng.close()
+    finally:
+        lib.vc_test_pair_mode(-1)
+    for n in acts[0]:
+        np.testing.assert_array_equal(acts[0][n], acts[1][n], err_msg=n)

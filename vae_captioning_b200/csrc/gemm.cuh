@@ -51,6 +51,8 @@ struct GemmCore {
   // (OOB zero fill = SAME padding); B is the same un-shifted patch of the output gradient.
   int pw, ph, pn, tw, th, tiles_w, tiles_h, cpk;  // cpk = Cin / 64 chunks per filter tap
   int n_img;                                      // A_WGRAD3x3: image count (an image index >= n_img zero-fills)
+  int pair;      // 1: run as CTA pairs (gemm_tc_kernel<Epi, 1>: cluster of 2, tcgen05 cta_group::2). m_tiles is then even
+                 // (rounded up; the surplus tile reads zero fill and its stores are clipped) and tmB's box holds bn / 2 rows
   int tap_rows;  // A_CONV3x3 over a window map (conv1_1): k-block kb is filter ROW kb; the three taps of the row and their
                  // channels are one contiguous run of the zero-padded input, so the box moves by (0, kb) instead of (s-1, r-1)
 };
@@ -107,19 +109,29 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmCore& g, int tile) {
 
 // Epi must provide:
 //   static constexpr int kSmemBytes;   // epilogue staging (multiple of 2048), split evenly over the 2 groups
+//   static constexpr bool kPairOk;     // may run under gemm_tc_kernel<Epi, 1> (CTA pairs)
 //   __device__ void operator()(uint32_t tmem_row_addr, const GemmCore& g, const TileCoord& t, int row,
 //                              uint8_t* grp_smem, int grp, int& phase) const
 // called by each of the 128 threads of epilogue group `grp` (row = 0..127 = TMEM lane = tile row) once the
 // accumulator is complete. tmem_row_addr addresses column 0 of this thread's warp lane quarter;
 // grp_smem is the group's half of the staging area; phase is per-thread state carried across tiles.
 //   __device__ void finish() const     // called once per epilogue thread after the last tile
-template <class Epi>
+//
+// kPair = 1 (launched as clusters of 2): the two CTAs of a pair own m-tiles 2p and 2p + 1 of the same n-tile. Each stages
+// its own A tile and HALF of the B tile (rows / columns [rank * bn/2, +bn/2) of it); every TMA load signals the LEADER's
+// `full` barrier (cluster rank 0), whose MMA warp issues one 256-row tcgen05.mma.cta_group::2 per k-step and releases the
+// ring stage / publishes the accumulator in BOTH CTAs with a multicast commit. Each CTA drains its own 128 TMEM lanes with
+// the unchanged epilogue and arrives on the leader's `tempty` barrier. Per SM and k-step the tensor core then reads
+// 4 KB + bn/2 rows of operands from shared memory instead of 4 KB + bn rows (the 128 x 256 tile of cta_group::1 is below
+// the shared-memory ridge), and a stage is 32 KB instead of 48 KB of L2 -> SM traffic.
+template <class Epi, int kPair>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                const __grid_constant__ CUtensorMap tmB, const GemmCore g, const __grid_constant__ Epi epi) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int stage_bytes = gemm_stage_bytes(g.bn);
+  const int b_rows = kPair ? g.bn / 2 : g.bn;  // rows (K-major) / columns (MN-major) of B this CTA stages
+  const int stage_bytes = gemm_stage_bytes(b_rows);
   uint8_t* epi_smem = smem + g.stages * stage_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(epi_smem + Epi::kSmemBytes);
   uint64_t* full = bars;
@@ -132,7 +144,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int total_tiles = g.m_tiles * g.n_tiles * g.splits;
+  // pair mode: the schedule runs over PAIR tiles (m_tiles / 2 of them per n-tile), one cluster per pair tile
+  const uint32_t rank = kPair ? cluster_ctarank() : 0u;
+  const int total_tiles = (kPair ? g.m_tiles / 2 : g.m_tiles) * g.n_tiles * g.splits;
+  const int tile0 = kPair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int tile_step = kPair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  GemmCore gs = g;  // what decode_tile sees
+  if (kPair) gs.m_tiles = g.m_tiles / 2;
+  auto tile_of = [&](int tile) {
+    TileCoord t = decode_tile(gs, tile);
+    if (kPair) t.m_blk = t.m_blk * 2 + (int)rank;
+    return t;
+  };
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -146,13 +169,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int i = 0; i < kMaxAcc; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], 4);
+      mbar_init(&tempty[i], kPair ? 8 : 4);  // pair: the four epilogue warps of both CTAs arrive on the leader's
     }
     fence_mbar_init();
   }
-  if (warp == 2) tmem_alloc<512>(tmem_slot);
+  if (warp == 2) {
+    if (kPair) tmem_alloc_pair<512>(tmem_slot);
+    else tmem_alloc<512>(tmem_slot);
+  }
   tc_fence_before();
-  __syncthreads();
+  if (kPair) cluster_sync_all();  // the peer's barriers must be initialised before anything arrives on them
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -162,8 +189,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const TileCoord t = decode_tile(g, tile);
+      for (int tile = tile0; tile < total_tiles; tile += tile_step) {
+        const TileCoord t = tile_of(tile);
         PatchOrigin po[4];
         if (g.a_mode == A_CONV3x3) {
 #pragma unroll
@@ -173,7 +200,38 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* sa = smem + stage * stage_bytes;
           uint8_t* sb = sa + kABytes;
-          if (elect_one()) {
+          if (kPair) {
+            // both CTAs load; the bytes of both land on the leader's barrier
+            if (elect_one()) {
+              if (rank == 0) mbar_expect_tx(&full[stage], 2 * stage_bytes);
+              const uint32_t fb = mapa_u32(&full[stage], 0);
+              if (g.a_mode == A_KMAJOR) {
+                if (g.a_switch >= 0 && kb >= g.a_switch)
+                  tma_load_2d_pair(sa, &tmA2, fb, (kb - g.a_switch) * kBK, t.m_blk * kBM);
+                else
+                  tma_load_2d_pair(sa, &tmA, fb, kb * kBK, t.m_blk * kBM);
+              } else if (g.a_mode == A_MNMAJOR) {
+                const bool second = g.a_switch >= 0 && t.m_blk >= g.a_switch;
+                const CUtensorMap* tm = second ? &tmA2 : &tmA;
+                const int m0 = (second ? t.m_blk - g.a_switch : t.m_blk) * kBM;
+                tma_load_2d_pair(sa, tm, fb, m0, kb * kBK);
+                tma_load_2d_pair(sa + 8192, tm, fb, m0 + 64, kb * kBK);
+              } else {  // A_CONV3x3 (the planners never pair A_WGRAD3x3)
+                const int tap = kb / g.cpk;
+                const int c0 = (kb - tap * g.cpk) * kBK;
+                const int fr = g.tap_rows ? tap + 1 : tap / 3, fs = g.tap_rows ? 1 : tap - (tap / 3) * 3;
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                  tma_load_4d_pair(sa + q * 4096, &tmA, fb, c0, po[q].w + fs - 1, po[q].h + fr - 1, po[q].n);
+              }
+              const int nb = t.n_blk * g.bn + (int)rank * b_rows;
+              if (g.b_mn == 1) {
+                for (int j = 0; j < b_rows; j += 64) tma_load_2d_pair(sb + j * 128, &tmB, fb, nb + j, kb * kBK);
+              } else {
+                tma_load_2d_pair(sb, &tmB, fb, kb * kBK, nb);
+              }
+            }
+          } else if (elect_one()) {
           mbar_expect_tx(&full[stage], stage_bytes);
           if (g.a_mode == A_KMAJOR) {
             if (g.a_switch >= 0 && kb >= g.a_switch)
@@ -229,10 +287,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
     // the whole warp walks the schedule (uniform control flow, descriptors in uniform registers); one elected lane
-    // issues the tcgen05 instructions
-    {
+    // issues the tcgen05 instructions. In pair mode only the leader CTA issues (for both SMs).
+    if (rank == 0) {
       const bool a_mn = g.a_mode == A_MNMAJOR || g.a_mode == A_WGRAD3x3;
-      const uint32_t idesc = make_idesc_bf16(kBM, g.bn, a_mn, g.b_mn != 0);
+      const uint32_t idesc = make_idesc_bf16(kPair ? 2 * kBM : kBM, g.bn, a_mn, g.b_mn != 0);
       const uint32_t a_lbo = a_mn ? 8192u : 16u;
       const uint32_t b_lbo = g.b_mn ? 8192u : 16u;
       const uint32_t a_kstep = a_mn ? (2048u >> 4) : (32u >> 4);
@@ -241,8 +299,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const TileCoord t = decode_tile(g, tile);
+      for (int tile = tile0; tile < total_tiles; tile += tile_step) {
+        const TileCoord t = tile_of(tile);
         mbar_wait(&tempty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * acc_stride;
@@ -255,10 +313,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (elect_one()) {
 #pragma unroll
             for (int k = 0; k < kBK / 16; ++k) {
-              umma_bf16(d_tmem, adesc + uint64_t(k * a_kstep), bdesc + uint64_t(k * b_kstep), idesc,
-                        (kb > t.kb_begin || k > 0) ? 1u : 0u);
+              if (kPair)
+                umma_bf16_pair(d_tmem, adesc + uint64_t(k * a_kstep), bdesc + uint64_t(k * b_kstep), idesc,
+                               (kb > t.kb_begin || k > 0) ? 1u : 0u);
+              else
+                umma_bf16(d_tmem, adesc + uint64_t(k * a_kstep), bdesc + uint64_t(k * b_kstep), idesc,
+                          (kb > t.kb_begin || k > 0) ? 1u : 0u);
             }
-            umma_commit(&empty[stage]);
+            if (kPair) umma_commit_pair(&empty[stage]);
+            else umma_commit(&empty[stage]);
           }
           __syncwarp();
           if (++stage == g.stages) {
@@ -266,7 +329,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             phase ^= 1;
           }
         }
-        if (elect_one()) umma_commit(&tfull[acc]);
+        if (elect_one()) {
+          if (kPair) umma_commit_pair(&tfull[acc]);
+          else umma_commit(&tfull[acc]);
+        }
         __syncwarp();
         if (++acc == nacc) {
           acc = 0;
@@ -283,11 +349,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     int epi_phase = 0;
     uint8_t* grp_smem = epi_smem + grp * (Epi::kSmemBytes / 2);
     int ord = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ord) {
+    const uint32_t tempty_leader = kPair ? mapa_u32(tempty, 0) : 0u;
+    for (int tile = tile0; tile < total_tiles; tile += tile_step, ++ord) {
       if ((ord & 1) != grp) continue;
       const int acc = ord % nacc;
       const uint32_t acc_phase = (ord / nacc) & 1;
-      const TileCoord t = decode_tile(g, tile);
+      const TileCoord t = tile_of(tile);
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
       if (t.kb_end > t.kb_begin) {
@@ -296,13 +363,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[acc]);
+      if (lane == 0) {
+        if (kPair) mbar_arrive_cluster(tempty_leader + acc * 8);
+        else mbar_arrive(&tempty[acc]);
+      }
     }
     epi.finish();
   }
   tc_fence_before();
-  __syncthreads();
-  if (warp == 2) tmem_dealloc<512>(tmem_base);
+  if (kPair) cluster_sync_all();  // neither CTA may leave while the other can still touch its barriers / shared memory
+  else __syncthreads();
+  if (warp == 2) {
+    if (kPair) tmem_dealloc_pair<512>(tmem_base);
+    else tmem_dealloc<512>(tmem_base);
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -319,6 +393,7 @@ struct EpiStore {
   float alpha;
   // staging for the atomic path: one 32 x 32 fp32 block per epilogue warp (2 groups x 4 warps x 4 KB)
   static constexpr int kSmemBytes = 32 * 1024;
+  static constexpr bool kPairOk = true;  // tile-local epilogue: runs unchanged in either CTA of a pair
   __device__ __forceinline__ void finish() const {}
 
   __device__ __forceinline__ void operator()(uint32_t taddr, const GemmCore&, const TileCoord& t, int row,
@@ -413,6 +488,7 @@ struct EpiTma {
   int N, bn, relu, mode;
   float alpha;
   static constexpr int kSmemBytes = 32 * 1024;  // 2 groups x (128 rows x 128 B)
+  static constexpr bool kPairOk = true;
 
   __device__ __forceinline__ void finish() const {
     if ((threadIdx.x & 127) == 0) bulk_wait_all();  // the issuing thread of each group
@@ -513,6 +589,7 @@ struct EpiTmaF32 {
   int N, bn;
   float alpha;
   static constexpr int kSmemBytes = 32 * 1024;  // 2 groups x (128 rows x 128 B)
+  static constexpr bool kPairOk = true;
 
   __device__ __forceinline__ void finish() const {
     if ((threadIdx.x & 127) == 0) bulk_wait_all();
@@ -572,7 +649,11 @@ __host__ inline int conv_halo_smem_bytes(int epi_bytes) {
   return kHaloWBytes + kHaloStages * kHaloBytes + epi_bytes + 1024 + 512;
 }
 
-template <class Epi>
+// kPair = 1: CTA pairs as in gemm_tc_kernel<Epi, 1>. The pair owns m-tiles 2p and 2p + 1 (each CTA stages its own halo)
+// and ONE n-tile of bn = 64 or 128 output channels, of whose resident filter slice each CTA holds bn / 2 rows per tap;
+// the leader issues 256-row MMAs. At Cout = 128 an SM then reads 4 KB + 2 KB of operands per 128 x 128 x 16 MMA half
+// (64 tensor cycles) instead of 4 KB + 2 KB per 128 x 64 x 16 (32 cycles).
+template <class Epi, int kPair>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmCore g,
                  const __grid_constant__ Epi epi) {
@@ -588,14 +669,23 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* tempty = bars + 2 * kHaloStages + kMaxAcc;
   uint64_t* wfull = bars + 2 * kHaloStages + 2 * kMaxAcc;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kHaloStages + 2 * kMaxAcc + 1);
-  constexpr int nacc = kMaxAcc, acc_stride = 64;  // bn = 64
+  const int bn = kPair ? g.bn : 64;
+  const int wtap = (kPair ? bn / 2 : 64) * 128;  // bytes per filter tap held by this CTA
+  const int acc_stride = bn > 64 ? 128 : 64;
+  const int nacc = 512 / acc_stride;
+  const uint32_t rank = kPair ? cluster_ctarank() : 0u;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   // static schedule: a CTA keeps one n-tile (its resident filter slice) and strides over the m-tiles
-  const int n_blk = blockIdx.x % g.n_tiles;
-  const int m_first = blockIdx.x / g.n_tiles;
-  const int m_step = gridDim.x / g.n_tiles;
+  // (pair mode: the same over pair tiles and clusters; m_first / m_step / m_end then count PAIRS, see m_of)
+  const int sched_id = kPair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int sched_n = kPair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int n_blk = sched_id % g.n_tiles;
+  const int m_first = sched_id / g.n_tiles;
+  const int m_step = sched_n / g.n_tiles;
+  const int m_end = kPair ? (g.m_tiles + 1) / 2 : g.m_tiles;
+  auto m_of = [&](int i) { return kPair ? 2 * i + (int)rank : i; };  // a surplus tile of the last pair is all zero fill
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -608,32 +698,48 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     for (int i = 0; i < kMaxAcc; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], 4);
+      mbar_init(&tempty[i], kPair ? 8 : 4);
     }
     mbar_init(wfull, 1);
     fence_mbar_init();
   }
-  if (warp == 2) tmem_alloc<512>(tmem_slot);
+  if (warp == 2) {
+    if (kPair) tmem_alloc_pair<512>(tmem_slot);
+    else tmem_alloc<512>(tmem_slot);
+  }
   tc_fence_before();
-  __syncthreads();
+  if (kPair) cluster_sync_all();
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
     {  // whole warp, one elected lane issues (see elect_one)
       if (elect_one()) {
-        mbar_expect_tx(wfull, kHaloWBytes);
-        for (int tap = 0; tap < 9; ++tap) tma_load_2d(wres + tap * 8192, &tmB, wfull, tap * 64, n_blk * 64);
+        if (kPair) {
+          if (rank == 0) mbar_expect_tx(wfull, 2 * 9 * wtap);
+          const uint32_t wb = mapa_u32(wfull, 0);
+          for (int tap = 0; tap < 9; ++tap)
+            tma_load_2d_pair(wres + tap * wtap, &tmB, wb, tap * 64, n_blk * bn + (int)rank * (bn / 2));
+        } else {
+          mbar_expect_tx(wfull, kHaloWBytes);
+          for (int tap = 0; tap < 9; ++tap) tma_load_2d(wres + tap * 8192, &tmB, wfull, tap * 64, n_blk * 64);
+        }
       }
       __syncwarp();
       int stage = 0;
       uint32_t phase = 0;
-      for (int m_blk = m_first; m_blk < g.m_tiles; m_blk += m_step) {
-        const PatchOrigin po = conv_patch_origin(g, m_blk, 0);
+      for (int mi = m_first; mi < m_end; mi += m_step) {
+        const PatchOrigin po = conv_patch_origin(g, m_of(mi), 0);
         mbar_wait(&hempty[stage], phase ^ 1);
         if (elect_one()) {
-          mbar_expect_tx(&hfull[stage], kHaloBytes);
-          tma_load_4d(halo + stage * kHaloBytes, &tmA, &hfull[stage], 0, po.w - 1, po.h - 1, po.n);
+          if (kPair) {
+            if (rank == 0) mbar_expect_tx(&hfull[stage], 2 * kHaloBytes);
+            tma_load_4d_pair(halo + stage * kHaloBytes, &tmA, mapa_u32(&hfull[stage], 0), 0, po.w - 1, po.h - 1, po.n);
+          } else {
+            mbar_expect_tx(&hfull[stage], kHaloBytes);
+            tma_load_4d(halo + stage * kHaloBytes, &tmA, &hfull[stage], 0, po.w - 1, po.h - 1, po.n);
+          }
         }
         __syncwarp();
         if (++stage == kHaloStages) {
@@ -644,8 +750,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else if (warp == 1) {
     // MMA issuer: the whole warp walks the schedule (uniform control flow), one elected lane issues
-    {
-      const uint32_t idesc = make_idesc_bf16(kBM, 64, false, false);
+    if (rank == 0) {
+      const uint32_t idesc = make_idesc_bf16(kPair ? 2 * kBM : kBM, bn, false, false);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -653,7 +759,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_wait(wfull, 0);
       tc_fence_after();
       const uint32_t wbase = smem_u32(wres);
-      for (int m_blk = m_first; m_blk < g.m_tiles; m_blk += m_step) {
+      for (int mi = m_first; mi < m_end; mi += m_step) {
         mbar_wait(&tempty[acc], acc_phase ^ 1);
         mbar_wait(&hfull[stage], phase);
         tc_fence_after();
@@ -664,13 +770,22 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           for (int tap = 0; tap < 9; ++tap) {
             const int fr = tap / 3, fs = tap - fr * 3;
             const uint64_t adesc = make_smem_desc(hbase + (fr * kHaloLineRows + fs) * 128, 16u, kHaloLineRows * 128);
-            const uint64_t bdesc = make_smem_desc(wbase + tap * 8192, 16u, 1024);
+            const uint64_t bdesc = make_smem_desc(wbase + tap * wtap, 16u, 1024);
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              umma_bf16(d_tmem, adesc + uint64_t(k * 2), bdesc + uint64_t(k * 2), idesc, (tap > 0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < 4; ++k) {
+              if (kPair)
+                umma_bf16_pair(d_tmem, adesc + uint64_t(k * 2), bdesc + uint64_t(k * 2), idesc, (tap > 0 || k > 0) ? 1u : 0u);
+              else
+                umma_bf16(d_tmem, adesc + uint64_t(k * 2), bdesc + uint64_t(k * 2), idesc, (tap > 0 || k > 0) ? 1u : 0u);
+            }
           }
-          umma_commit(&hempty[stage]);
-          umma_commit(&tfull[acc]);
+          if (kPair) {
+            umma_commit_pair(&hempty[stage]);
+            umma_commit_pair(&tfull[acc]);
+          } else {
+            umma_commit(&hempty[stage]);
+            umma_commit(&tfull[acc]);
+          }
         }
         __syncwarp();
         if (++stage == kHaloStages) {
@@ -689,25 +804,33 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     int epi_phase = 0;
     uint8_t* grp_smem = epi_smem + grp * (Epi::kSmemBytes / 2);
     int ord = 0;
-    for (int m_blk = m_first; m_blk < g.m_tiles; m_blk += m_step, ++ord) {
+    const uint32_t tempty_leader = kPair ? mapa_u32(tempty, 0) : 0u;
+    for (int mi = m_first; mi < m_end; mi += m_step, ++ord) {
       if ((ord & 1) != grp) continue;
       const int acc = ord % nacc;
       const uint32_t acc_phase = (ord / nacc) & 1;
       TileCoord t;
-      t.m_blk = m_blk; t.n_blk = n_blk; t.split = 0; t.kb_begin = 0; t.kb_end = 9;
+      t.m_blk = m_of(mi); t.n_blk = n_blk; t.split = 0; t.kb_begin = 0; t.kb_end = 9;
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + acc * acc_stride + (uint32_t(q * 32) << 16);
       epi(taddr, g, t, q * 32 + lane, grp_smem, grp, epi_phase);
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[acc]);
+      if (lane == 0) {
+        if (kPair) mbar_arrive_cluster(tempty_leader + acc * 8);
+        else mbar_arrive(&tempty[acc]);
+      }
     }
     epi.finish();
   }
   tc_fence_before();
-  __syncthreads();
-  if (warp == 2) tmem_dealloc<512>(tmem_base);
+  if (kPair) cluster_sync_all();
+  else __syncthreads();
+  if (warp == 2) {
+    if (kPair) tmem_dealloc_pair<512>(tmem_base);
+    else tmem_dealloc<512>(tmem_base);
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -736,15 +859,18 @@ __host__ inline int conv_halo_stream_smem_bytes(int bn, int epi_bytes) {
   return kHaloSStages * kHaloBytes + conv_halo_stream_b_stages(bn, epi_bytes) * bn * 128 + epi_bytes + 1024 + 512;
 }
 
-template <class Epi>
+// kPair = 1: CTA pairs (see gemm_tc_kernel<Epi, 1>): pair tile = m-tiles 2p, 2p + 1; each CTA stages its own halos and
+// bn / 2 rows of every filter block, so the filter ring holds twice as many blocks.
+template <class Epi, int kPair>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 conv_halo_stream_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmCore g,
                         const __grid_constant__ Epi epi) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int b_bytes = g.bn * 128;
+  const int b_rows = kPair ? g.bn / 2 : g.bn;
+  const int b_bytes = b_rows * 128;
   uint8_t* halo = smem;
-  const int b_stages = conv_halo_stream_b_stages(g.bn, Epi::kSmemBytes);
+  const int b_stages = conv_halo_stream_b_stages(b_rows, Epi::kSmemBytes);
   uint8_t* bring = smem + kHaloSStages * kHaloBytes;
   uint8_t* epi_smem = bring + b_stages * b_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(epi_smem + Epi::kSmemBytes);
@@ -760,7 +886,12 @@ conv_halo_stream_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int total_tiles = g.m_tiles * g.n_tiles;
+  // pair mode: the schedule runs over pair tiles and clusters; a surplus tile of the last pair is all zero fill
+  const uint32_t rank = kPair ? cluster_ctarank() : 0u;
+  const int total_tiles = (kPair ? (g.m_tiles + 1) / 2 : g.m_tiles) * g.n_tiles;
+  const int tile0 = kPair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int tile_step = kPair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  auto m_of = [&](int tile) { return kPair ? 2 * (tile / g.n_tiles) + (int)rank : tile / g.n_tiles; };
   const int cin = g.cpk * 64;
 
   if (warp == 0 && lane == 0) {
@@ -778,13 +909,17 @@ conv_halo_stream_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
     }
     for (int i = 0; i < kMaxAcc; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], 4);
+      mbar_init(&tempty[i], kPair ? 8 : 4);
     }
     fence_mbar_init();
   }
-  if (warp == 2) tmem_alloc<512>(tmem_slot);
+  if (warp == 2) {
+    if (kPair) tmem_alloc_pair<512>(tmem_slot);
+    else tmem_alloc<512>(tmem_slot);
+  }
   tc_fence_before();
-  __syncthreads();
+  if (kPair) cluster_sync_all();
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -793,13 +928,18 @@ conv_halo_stream_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
     {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const PatchOrigin po = conv_patch_origin(g, tile / g.n_tiles, 0);
+      for (int tile = tile0; tile < total_tiles; tile += tile_step) {
+        const PatchOrigin po = conv_patch_origin(g, m_of(tile), 0);
         for (int c = 0; c < g.cpk; ++c) {
           mbar_wait(&hempty[stage], phase ^ 1);
           if (elect_one()) {
-            mbar_expect_tx(&hfull[stage], kHaloBytes);
-            tma_load_4d(halo + stage * kHaloBytes, &tmA, &hfull[stage], c * 64, po.w - 1, po.h - 1, po.n);
+            if (kPair) {
+              if (rank == 0) mbar_expect_tx(&hfull[stage], 2 * kHaloBytes);
+              tma_load_4d_pair(halo + stage * kHaloBytes, &tmA, mapa_u32(&hfull[stage], 0), c * 64, po.w - 1, po.h - 1, po.n);
+            } else {
+              mbar_expect_tx(&hfull[stage], kHaloBytes);
+              tma_load_4d(halo + stage * kHaloBytes, &tmA, &hfull[stage], c * 64, po.w - 1, po.h - 1, po.n);
+            }
           }
           __syncwarp();
           if (++stage == kHaloSStages) {
@@ -814,14 +954,20 @@ conv_halo_stream_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
     {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = tile0; tile < total_tiles; tile += tile_step) {
         const int n0 = (tile % g.n_tiles) * g.bn;
         for (int c = 0; c < g.cpk; ++c) {
           for (int tap = 0; tap < 9; ++tap) {
             mbar_wait(&bempty[stage], phase ^ 1);
             if (elect_one()) {
-              mbar_expect_tx(&bfull[stage], b_bytes);
-              tma_load_2d(bring + stage * b_bytes, &tmB, &bfull[stage], tap * cin + c * 64, n0);
+              if (kPair) {
+                if (rank == 0) mbar_expect_tx(&bfull[stage], 2 * b_bytes);
+                tma_load_2d_pair(bring + stage * b_bytes, &tmB, mapa_u32(&bfull[stage], 0), tap * cin + c * 64,
+                                 n0 + (int)rank * b_rows);
+              } else {
+                mbar_expect_tx(&bfull[stage], b_bytes);
+                tma_load_2d(bring + stage * b_bytes, &tmB, &bfull[stage], tap * cin + c * 64, n0);
+              }
             }
             __syncwarp();
             if (++stage == b_stages) {
@@ -834,11 +980,11 @@ conv_halo_stream_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer (whole warp, one elected lane issues)
-    {
-      const uint32_t idesc = make_idesc_bf16(kBM, g.bn, false, false);
+    if (rank == 0) {
+      const uint32_t idesc = make_idesc_bf16(kPair ? 2 * kBM : kBM, g.bn, false, false);
       int hs = 0, bs = 0, acc = 0;
       uint32_t hphase = 0, bphase = 0, acc_phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = tile0; tile < total_tiles; tile += tile_step) {
         mbar_wait(&tempty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * acc_stride;
@@ -854,9 +1000,14 @@ conv_halo_stream_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
             const uint64_t bdesc = make_smem_desc(smem_u32(bring + bs * b_bytes), 16u, 1024);
             if (elect_one()) {
 #pragma unroll
-              for (int k = 0; k < 4; ++k)
-                umma_bf16(d_tmem, adesc + uint64_t(k * 2), bdesc + uint64_t(k * 2), idesc, (c > 0 || tap > 0 || k > 0) ? 1u : 0u);
-              umma_commit(&bempty[bs]);
+              for (int k = 0; k < 4; ++k) {
+                if (kPair)
+                  umma_bf16_pair(d_tmem, adesc + uint64_t(k * 2), bdesc + uint64_t(k * 2), idesc, (c > 0 || tap > 0 || k > 0) ? 1u : 0u);
+                else
+                  umma_bf16(d_tmem, adesc + uint64_t(k * 2), bdesc + uint64_t(k * 2), idesc, (c > 0 || tap > 0 || k > 0) ? 1u : 0u);
+              }
+              if (kPair) umma_commit_pair(&bempty[bs]);
+              else umma_commit(&bempty[bs]);
             }
             __syncwarp();
             if (++bs == b_stages) {
@@ -864,14 +1015,20 @@ conv_halo_stream_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
               bphase ^= 1;
             }
           }
-          if (elect_one()) umma_commit(&hempty[hs]);
+          if (elect_one()) {
+            if (kPair) umma_commit_pair(&hempty[hs]);
+            else umma_commit(&hempty[hs]);
+          }
           __syncwarp();
           if (++hs == kHaloSStages) {
             hs = 0;
             hphase ^= 1;
           }
         }
-        if (elect_one()) umma_commit(&tfull[acc]);
+        if (elect_one()) {
+          if (kPair) umma_commit_pair(&tfull[acc]);
+          else umma_commit(&tfull[acc]);
+        }
         __syncwarp();
         if (++acc == nacc) {
           acc = 0;
@@ -885,25 +1042,33 @@ conv_halo_stream_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
     int epi_phase = 0;
     uint8_t* grp_smem = epi_smem + grp * (Epi::kSmemBytes / 2);
     int ord = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ord) {
+    const uint32_t tempty_leader = kPair ? mapa_u32(tempty, 0) : 0u;
+    for (int tile = tile0; tile < total_tiles; tile += tile_step, ++ord) {
       if ((ord & 1) != grp) continue;
       const int acc = ord % nacc;
       const uint32_t acc_phase = (ord / nacc) & 1;
       TileCoord t;
-      t.m_blk = tile / g.n_tiles; t.n_blk = tile % g.n_tiles; t.split = 0; t.kb_begin = 0; t.kb_end = 9 * g.cpk;
+      t.m_blk = m_of(tile); t.n_blk = tile % g.n_tiles; t.split = 0; t.kb_begin = 0; t.kb_end = 9 * g.cpk;
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + acc * acc_stride + (uint32_t(q * 32) << 16);
       epi(taddr, g, t, q * 32 + lane, grp_smem, grp, epi_phase);
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[acc]);
+      if (lane == 0) {
+        if (kPair) mbar_arrive_cluster(tempty_leader + acc * 8);
+        else mbar_arrive(&tempty[acc]);
+      }
     }
     epi.finish();
   }
   tc_fence_before();
-  __syncthreads();
-  if (warp == 2) tmem_dealloc<512>(tmem_base);
+  if (kPair) cluster_sync_all();
+  else __syncthreads();
+  if (warp == 2) {
+    if (kPair) tmem_dealloc_pair<512>(tmem_base);
+    else tmem_dealloc<512>(tmem_base);
+  }
 }
 
 // ------------------------------------------------------------------------------------------

@@ -71,6 +71,8 @@ extern "C" int vc_gemm_bf16(const void* A, int a_mn, long long lda, const void* 
   return gemm_store(static_cast<cudaStream_t>(stream), a, nullptr, 0, b, M, N, K, epi, bn, splits);
 }
 
+extern "C" void vc_test_pair_mode(int mode) { vc::set_pair_mode(mode); }
+
 // Test entries for the convolution backward kernels (parity against torch conv2d gradients on the same bf16 inputs):
 // x, dy bf16 NHWC; w fp32 HWIO; dw fp32 [9*Cin, Cout] (zeroed here); dx bf16 NHWC. All device pointers.
 extern "C" int vc_conv3x3_bwd(const void* x, const void* dy, const float* w, float* dw, void* dx, int B, int hw, int cin,

@@ -214,8 +214,33 @@ static int operand_tmap(CUtensorMap* out, const Operand& o, int box_rows_kmajor)
   return make_tmap_2d(out, o.ptr, o.cols, o.rows, o.ld, 64, box_rows_kmajor);
 }
 
+// ------------------------------------------------------------------------------------------
+static int g_pair_mode = -2;  // -2: read VC_PAIR on first use
+void set_pair_mode(int mode) { g_pair_mode = mode < -1 || mode > 1 ? -1 : mode; }
+bool gemm_pair_wanted(int m_tiles, int bn, int b_mn, int k_blocks) {
+  if (g_pair_mode == -2) {
+    const char* e = getenv("VC_PAIR");
+    g_pair_mode = (e && e[0] == '0') ? 0 : (e && e[0] == '1') ? 1 : -1;
+  }
+  if (g_pair_mode == 0) return false;
+  // M = 256 needs N % 16 == 0; each CTA stages bn / 2 rows (8-row swizzle groups) or bn / 2 columns in 64-wide MN blocks
+  const bool legal = m_tiles >= 2 && bn >= 32 && bn % 32 == 0 && (b_mn == 0 || bn % 128 == 0);
+  if (!legal) return false;
+  if (g_pair_mode == 1) return true;
+  // short contractions are bound by their epilogue (conv1_1 as a K = 64 GEMM, the K = 512 vocabulary projection: measured
+  // 0.52 -> 0.67 ms and 0.295 -> 0.31 ms as pairs), where coupling two SMs only costs
+  return bn >= 128 && k_blocks >= 12 && (m_tiles % 2 == 0 || m_tiles >= 9);
+}
+
+bool halo_pair_wanted(int bn) {
+  gemm_pair_wanted(2, 128, 0, 16);  // reads the environment once
+  // a 256 x 64 pair MMA is no faster than two 128 x 64 ones (conv1_2 as pairs: 0.98 -> 1.22 ms), 256 x 128 is
+  // (conv2_2: 0.94 -> 0.80 ms, conv2_1: 0.48 -> 0.45 ms)
+  return g_pair_mode == 1 || (g_pair_mode != 0 && bn >= 128);
+}
+
 int plan_gemm(GemmPlan* p, const Operand& A, const Operand* A2, long long a2_at, const Operand& B, int M, int N, int K,
-              int bn, int splits) {
+              int bn, int splits, bool pair_ok) {
   if (bn < 16 || bn > 256 || (bn % 16) != 0 || (B.mn_major && (bn % 64) != 0))
     return set_error(VC_E_ARG, "plan_gemm: unsupported tile width bn=%d", bn);
   if (M <= 0 || N <= 0 || K <= 0) return set_error(VC_E_SHAPE, "plan_gemm: empty problem %dx%dx%d", M, N, K);
@@ -230,6 +255,8 @@ int plan_gemm(GemmPlan* p, const Operand& A, const Operand* A2, long long a2_at,
   g.a_mode = A.mn_major ? A_MNMAJOR : A_KMAJOR;
   g.b_mn = B.mn_major ? 1 : 0;
   g.a_switch = -1;
+  g.pair = pair_ok && gemm_pair_wanted(g.m_tiles, bn, g.b_mn, (g.k_blocks + g.splits - 1) / g.splits) ? 1 : 0;
+  if (g.pair) g.m_tiles = (g.m_tiles + 1) / 2 * 2;
   VC_TRY(operand_tmap(&p->tmA, A, kBM));
   p->tmA2 = p->tmA;
   if (A2 != nullptr && A2->ptr != nullptr) {
@@ -239,7 +266,7 @@ int plan_gemm(GemmPlan* p, const Operand& A, const Operand* A2, long long a2_at,
     g.a_switch = (int)(a2_at / (A.mn_major ? kBM : kBK));
     VC_TRY(operand_tmap(&p->tmA2, *A2, kBM));
   }
-  VC_TRY(operand_tmap(&p->tmB, B, bn));
+  VC_TRY(operand_tmap(&p->tmB, B, g.pair ? bn / 2 : bn));
   return VC_OK;
 }
 
@@ -272,17 +299,18 @@ int plan_conv_halo(GemmPlan* p, const void* in, const void* wt, const ConvGeom& 
   g.tiles_w = cg.W / 8;
   g.tiles_h = cg.H / 16;
   g.m_tiles = g.tiles_w * g.tiles_h * cg.Nimg;
-  g.n_tiles = cg.Cout / 64;
+  g.pair = halo_pair_wanted(cg.Cout % 128 == 0 ? 128 : 64) && g.m_tiles >= 2 ? 1 : 0;
+  g.bn = g.pair && cg.Cout % 128 == 0 ? 128 : 64;  // a pair covers 128 output channels with the filter bytes of 64 per CTA
+  g.n_tiles = cg.Cout / g.bn;
   g.cpk = 1;
   g.k_blocks = 9;
   g.splits = 1;
-  g.bn = 64;
   g.stages = kHaloStages;
   g.a_mode = A_CONV3x3;
   g.a_switch = -1;
   VC_TRY(make_tmap_nhwc(&p->tmA, in, cg.Cin, cg.W, cg.H, cg.Nimg, kHaloLineRows, kHaloLines, 1));
   p->tmA2 = p->tmA;
-  VC_TRY(make_tmap_2d(&p->tmB, wt, 9ull * cg.Cin, cg.Cout, 9ull * cg.Cin, 64, 64));
+  VC_TRY(make_tmap_2d(&p->tmB, wt, 9ull * cg.Cin, cg.Cout, 9ull * cg.Cin, 64, g.pair ? g.bn / 2 : 64));
   return VC_OK;
 }
 
@@ -356,12 +384,13 @@ int plan_conv_halo_stream(GemmPlan* p, const void* in, const void* wt, const Con
   g.k_blocks = 9 * g.cpk;
   g.splits = 1;
   g.bn = cg.Cout;
+  g.pair = halo_pair_wanted(g.bn) && g.m_tiles >= 2 ? 1 : 0;
   g.stages = kHaloStages;
   g.a_mode = A_CONV3x3;
   g.a_switch = -1;
   VC_TRY(make_tmap_nhwc(&p->tmA, in, cg.Cin, cg.W, cg.H, cg.Nimg, kHaloLineRows, kHaloLines, 1));
   p->tmA2 = p->tmA;
-  VC_TRY(make_tmap_2d(&p->tmB, wt, 9ull * cg.Cin, cg.Cout, 9ull * cg.Cin, 64, cg.Cout));
+  VC_TRY(make_tmap_2d(&p->tmB, wt, 9ull * cg.Cin, cg.Cout, 9ull * cg.Cin, 64, g.pair ? cg.Cout / 2 : cg.Cout));
   return VC_OK;
 }
 
@@ -385,9 +414,11 @@ int plan_conv(GemmPlan* p, const void* in, const void* wt, const ConvGeom& cg, i
   g.a_mode = A_CONV3x3;
   g.b_mn = 0;
   g.a_switch = -1;
+  g.pair = gemm_pair_wanted(g.m_tiles, bn, 0, g.k_blocks) ? 1 : 0;
+  if (g.pair) g.m_tiles = (g.m_tiles + 1) / 2 * 2;  // a surplus tile lies past the last image: zero fill in, clipped out
   VC_TRY(make_tmap_nhwc(&p->tmA, in, cg.Cin, cg.W, cg.H, cg.Nimg, cg.pw, cg.ph, cg.pn));
   p->tmA2 = p->tmA;
-  VC_TRY(make_tmap_2d(&p->tmB, wt, 9ull * cg.Cin, cg.Cout, 9ull * cg.Cin, 64, bn));
+  VC_TRY(make_tmap_2d(&p->tmB, wt, 9ull * cg.Cin, cg.Cout, 9ull * cg.Cin, 64, g.pair ? bn / 2 : bn));
   return VC_OK;
 }
 

@@ -3,6 +3,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
+#include <algorithm>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -97,8 +98,9 @@ struct GemmPlan {
 // Builds tensor maps + tile schedule for D[M,N] = A * B (contraction K). A2 optional (ptr == nullptr):
 //   A K-major:  A covers k in [0, a2_at), A2 covers the rest (a2_at multiple of 64).
 //   A MN-major: A covers m in [0, a2_at), A2 the rest (a2_at multiple of 128).
+// pair_ok = false: never plan a CTA-pair launch (epilogues that are not tile-local)
 int plan_gemm(GemmPlan* p, const Operand& A, const Operand* A2, long long a2_at, const Operand& B, int M, int N, int K,
-              int bn, int splits);
+              int bn, int splits, bool pair_ok = true);
 
 // D = conv3x3_same(in NHWC bf16 [Nimg,H,W,Cin], Wt bf16 [Cout, 9*Cin] (tap-major, then cin)); Cin % 64 == 0.
 int plan_conv(GemmPlan* p, const void* in, const void* wt, const ConvGeom& g, int bn);
@@ -132,11 +134,60 @@ int launch_conv_wgrad_halo(cudaStream_t stream, const void* x, const void* dy, f
 bool conv_halo_stream_applicable(int W, int H, int Cin, int Cout);
 int plan_conv_halo_stream(GemmPlan* p, const void* in, const void* wt, const ConvGeom& g);
 
+// CTA-pair policy (gemm_tc_kernel<Epi, 1>): VC_PAIR=0 never, VC_PAIR=1 wherever the tile shape allows it, unset = where it
+// pays (wide tiles, enough m-tiles that rounding their count up to even costs little). set_pair_mode overrides the
+// environment (tests): -1 automatic, 0 off, 1 forced.
+void set_pair_mode(int mode);
+bool gemm_pair_wanted(int m_tiles, int bn, int b_mn, int k_blocks);
+bool halo_pair_wanted(int bn);
+
+// Launch of a kernel written for CTA pairs: clusters of 2, at most `pairs` of them and never more than can be co-resident.
+template <class Kernel, class... Args>
+int launch_pair_kernel(Kernel kernel, int* max_clusters, int pairs, int sm_cap, int smem, cudaStream_t stream, const char* tag,
+                       const Args&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  if (*max_clusters == 0) {
+    VC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    cfg.gridDim = dim3(num_sms() / 2 * 2);
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, kernel, &cfg) != cudaSuccess || n <= 0) {
+      cudaGetLastError();
+      n = num_sms() / 2;
+    }
+    *max_clusters = n;
+  }
+  if (pairs <= 0) return VC_OK;
+  const int cap = std::max(1, std::min(*max_clusters, sm_cap / 2));
+  cfg.gridDim = dim3(2 * (pairs < cap ? pairs : cap));
+  {
+    ProfScope ps(stream, tag);
+    VC_CUDA(cudaLaunchKernelEx(&cfg, kernel, args...));
+  }
+  VC_CUDA(cudaGetLastError());
+  return VC_OK;
+}
+
 template <class Epi>
 int launch_conv_halo_stream(const GemmPlan& p, const Epi& epi, cudaStream_t stream) {
+  if (p.core.pair) {
+    static int max_clusters = 0;
+    return launch_pair_kernel(conv_halo_stream_kernel<Epi, 1>, &max_clusters, (p.core.m_tiles + 1) / 2 * p.core.n_tiles, num_sms(),
+                              conv_halo_stream_smem_bytes(p.core.bn / 2, Epi::kSmemBytes), stream, "conv_halo_stream", p.tmA,
+                              p.tmB, p.core, epi);
+  }
   static bool configured = false;
   if (!configured) {
-    VC_CUDA(cudaFuncSetAttribute(conv_halo_stream_kernel<Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    VC_CUDA(cudaFuncSetAttribute(conv_halo_stream_kernel<Epi, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured = true;
   }
   const int total = p.core.m_tiles * p.core.n_tiles;
@@ -145,7 +196,7 @@ int launch_conv_halo_stream(const GemmPlan& p, const Epi& epi, cudaStream_t stre
   const int smem = conv_halo_stream_smem_bytes(p.core.bn, Epi::kSmemBytes);
   {
     ProfScope ps(stream, "conv_halo_stream");
-    conv_halo_stream_kernel<Epi><<<grid, kGemmThreads, smem, stream>>>(p.tmA, p.tmB, p.core, epi);
+    conv_halo_stream_kernel<Epi, 0><<<grid, kGemmThreads, smem, stream>>>(p.tmA, p.tmB, p.core, epi);
   }
   VC_CUDA(cudaGetLastError());
   return VC_OK;
@@ -153,29 +204,55 @@ int launch_conv_halo_stream(const GemmPlan& p, const Epi& epi, cudaStream_t stre
 
 template <class Epi>
 int launch_conv_halo(const GemmPlan& p, const Epi& epi, cudaStream_t stream) {
+  const int nt = p.core.n_tiles;
+  if (p.core.pair) {
+    // a cluster keeps one n-tile: the cluster count is a multiple of the n-tile count (see the kernel's schedule)
+    static int max_clusters = 0;
+    if (max_clusters == 0) VC_TRY(launch_pair_kernel(conv_halo_kernel<Epi, 1>, &max_clusters, 0, num_sms(), conv_halo_smem_bytes(Epi::kSmemBytes), stream, "conv_halo", p.tmA, p.tmB, p.core, epi));
+    const int pairs = (p.core.m_tiles + 1) / 2;
+    int clusters = std::min(max_clusters, num_sms() / 2) / nt * nt;
+    if (clusters > pairs * nt) clusters = pairs * nt;
+    return launch_pair_kernel(conv_halo_kernel<Epi, 1>, &max_clusters, clusters, 2 * clusters, conv_halo_smem_bytes(Epi::kSmemBytes), stream,
+                              "conv_halo", p.tmA, p.tmB, p.core, epi);
+  }
   static bool configured = false;
   if (!configured) {
-    VC_CUDA(cudaFuncSetAttribute(conv_halo_kernel<Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    VC_CUDA(cudaFuncSetAttribute(conv_halo_kernel<Epi, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured = true;
   }
-  const int nt = p.core.n_tiles;
   int grid = num_sms() / nt * nt;
   if (grid > p.core.m_tiles * nt) grid = p.core.m_tiles * nt;
   if (grid <= 0) return VC_OK;
   const int smem = conv_halo_smem_bytes(Epi::kSmemBytes);
   {
     ProfScope ps(stream, "conv_halo");
-    conv_halo_kernel<Epi><<<grid, kGemmThreads, smem, stream>>>(p.tmA, p.tmB, p.core, epi);
+    conv_halo_kernel<Epi, 0><<<grid, kGemmThreads, smem, stream>>>(p.tmA, p.tmB, p.core, epi);
   }
   VC_CUDA(cudaGetLastError());
   return VC_OK;
 }
 
+
+template <class Epi>
+int launch_gemm_pair(const GemmPlan& p, const Epi& epi, cudaStream_t stream) {
+  static int max_clusters = 0;
+  GemmCore core = p.core;
+  const int b_rows = core.bn / 2;
+  core.stages = gemm_pick_stages(b_rows, Epi::kSmemBytes);
+  if (core.stages < 2) return set_error(VC_E_ARG, "launch_gemm: tile too large for shared memory (bn=%d)", core.bn);
+  return launch_pair_kernel(gemm_tc_kernel<Epi, 1>, &max_clusters, core.m_tiles / 2 * core.n_tiles * core.splits, sm_budget(),
+                            gemm_smem_bytes(b_rows, core.stages, Epi::kSmemBytes), stream, "gemm", p.tmA, p.tmA2, p.tmB, core, epi);
+}
+
 template <class Epi>
 int launch_gemm(const GemmPlan& p, const Epi& epi, cudaStream_t stream) {
+  if (p.core.pair) {
+    if constexpr (Epi::kPairOk) return launch_gemm_pair(p, epi, stream);
+    else return set_error(VC_E_ARG, "launch_gemm: this epilogue does not run as a CTA pair");
+  }
   static bool configured = false;
   if (!configured) {
-    VC_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    VC_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<Epi, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured = true;
   }
   const int total = p.core.m_tiles * p.core.n_tiles * p.core.splits;
@@ -187,7 +264,7 @@ int launch_gemm(const GemmPlan& p, const Epi& epi, cudaStream_t stream) {
   const int smem = gemm_smem_bytes(core.bn, core.stages, Epi::kSmemBytes);
   {
     ProfScope ps(stream, "gemm");
-    gemm_tc_kernel<Epi><<<grid, kGemmThreads, smem, stream>>>(p.tmA, p.tmA2, p.tmB, core, epi);
+    gemm_tc_kernel<Epi, 0><<<grid, kGemmThreads, smem, stream>>>(p.tmA, p.tmA2, p.tmB, core, epi);
   }
   VC_CUDA(cudaGetLastError());
   return VC_OK;

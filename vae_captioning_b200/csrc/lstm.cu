@@ -21,7 +21,7 @@ int lstm_fwd_step(cudaStream_t stream, const LstmFwdArgs& a) {
   Operand Hp{a.h_prev, a.N, a.H, a.H, false};
   Operand W{a.w_t_perm, 4LL * a.H, (long long)a.E + a.H, (long long)a.E + a.H, false};
   GemmPlan plan;
-  VC_TRY(plan_gemm(&plan, X, &Hp, a.E, W, a.N, 4 * a.H, a.E + a.H, 4 * kUPT, 1));
+  VC_TRY(plan_gemm(&plan, X, &Hp, a.E, W, a.N, 4 * a.H, a.E + a.H, 4 * kUPT, 1, false));
   EpiLstmFwd epi;
   epi.bias = a.bias;
   epi.c_prev = a.c_prev;
@@ -47,6 +47,7 @@ constexpr int kBwdBN = 64;
 struct EpiLstmBwd {
   LstmBwdCommon c;
   static constexpr int kSmemBytes = 0;
+  static constexpr bool kPairOk = false;
   __device__ __forceinline__ void finish() const {}
   __device__ __forceinline__ void operator()(uint32_t taddr, const GemmCore&, const TileCoord& tc, int row, uint8_t*,
                                              int, int&) const {
@@ -105,7 +106,7 @@ int lstm_bwd_step(cudaStream_t stream, const LstmBwdArgs& a) {
   Operand A{a.d_gates_next, a.N, 4LL * a.H, 4LL * a.H, false};
   Operand B{(const __nv_bfloat16*)a.w_nat + (long long)a.E * 4 * a.H, a.H, 4LL * a.H, 4LL * a.H, false};
   GemmPlan plan;
-  VC_TRY(plan_gemm(&plan, A, nullptr, 0, B, a.N, a.H, 4 * a.H, kBwdBN, 1));
+  VC_TRY(plan_gemm(&plan, A, nullptr, 0, B, a.N, a.H, 4 * a.H, kBwdBN, 1, false));
   EpiLstmBwd epi{c};
   ProfTag tag("lstm_bwd_step");
   return launch_gemm(plan, epi, stream);

@@ -252,7 +252,7 @@ int Model::vgg_conv_layer(int l, const void* in, int B, bool fuse_pool, cudaStre
   if (halo) {
     VC_TRY(conv_halo_geometry(&g, L.hw, L.hw, B, L.cin, L.cout));
     VC_TRY(plan_conv_halo(&plan, in, L.wt, g));
-    epi.bn = 64;
+    epi.bn = plan.core.bn;
   } else if (halo2) {
     VC_TRY(conv_halo_geometry(&g, L.hw, L.hw, B, L.cin, L.cout));
     VC_TRY(plan_conv_halo_stream(&plan, in, L.wt, g));

@@ -158,7 +158,7 @@ int conv3x3_dgrad(cudaStream_t s, const void* dy, const void* wt_d, void* dx, in
   if (halo) {
     VC_TRY(conv_halo_geometry(&g, hw, hw, B, cout, cin));
     VC_TRY(plan_conv_halo(&plan, dy, wt_d, g));
-    epi.bn = 64;
+    epi.bn = plan.core.bn;
   } else if (halo2) {
     VC_TRY(conv_halo_geometry(&g, hw, hw, B, cout, cin));
     VC_TRY(plan_conv_halo_stream(&plan, dy, wt_d, g));
