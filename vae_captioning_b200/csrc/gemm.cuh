@@ -216,7 +216,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const int m0 = (second ? t.m_blk - g.a_switch : t.m_blk) * kBM;
                 tma_load_2d_pair(sa, tm, fb, m0, kb * kBK);
                 tma_load_2d_pair(sa + 8192, tm, fb, m0 + 64, kb * kBK);
-              } else {  // A_CONV3x3 (the planners never pair A_WGRAD3x3)
+              } else if (g.a_mode == A_WGRAD3x3) {
+                const int tiw = kb % g.tiles_w;
+                const int r = kb / g.tiles_w;
+                const int w0 = tiw * g.pw, h0 = (r % g.tiles_h) * g.ph, n0 = (r / g.tiles_h) * g.pn;
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                  const int chunk = t.m_blk * 2 + half;
+                  const int tap = chunk / g.cpk;
+                  const int c0 = (chunk - tap * g.cpk) * 64;
+                  const int fr = tap / 3, fs = tap - fr * 3;
+                  if (tap < 9)
+                    tma_load_4d_pair(sa + half * 8192, &tmA, fb, c0, w0 + fs - 1, h0 + fr - 1, n0);
+                  else
+                    tma_load_4d_pair(sa + half * 8192, &tmA, fb, 0, 0, 0, g.n_img);  // past the last tap: zeros
+                }
+                for (int j = 0; j < b_rows; j += 64)
+                  tma_load_4d_pair(sb + j * 128, &tmB, fb, t.n_blk * g.bn + (int)rank * b_rows + j, w0, h0, n0);
+              } else {  // A_CONV3x3
                 const int tap = kb / g.cpk;
                 const int c0 = (kb - tap * g.cpk) * kBK;
                 const int fr = g.tap_rows ? tap + 1 : tap / 3, fs = g.tap_rows ? 1 : tap - (tap / 3) * 3;
@@ -227,7 +244,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               const int nb = t.n_blk * g.bn + (int)rank * b_rows;
               if (g.b_mn == 1) {
                 for (int j = 0; j < b_rows; j += 64) tma_load_2d_pair(sb + j * 128, &tmB, fb, nb + j, kb * kBK);
-              } else {
+              } else if (g.b_mn == 0) {
                 tma_load_2d_pair(sb, &tmB, fb, kb * kBK, nb);
               }
             }

@@ -483,6 +483,9 @@ int plan_conv_wgrad(GemmPlan* p, const void* in, const void* dy, int W, int H, i
   g.b_mn = 2;
   g.a_switch = -1;
   g.n_img = Nimg;
+  // pairs: each CTA gathers its own (tap, channel chunk) rows and half of the dy patch columns
+  g.pair = gemm_pair_wanted(g.m_tiles, bn, 1, (g.k_blocks + g.splits - 1) / g.splits) ? 1 : 0;
+  if (g.pair) g.m_tiles = (g.m_tiles + 1) / 2 * 2;
   VC_TRY(make_tmap_nhwc(&p->tmA, in, Cin, W, H, Nimg, g.pw, g.ph, g.pn));
   p->tmA2 = p->tmA;
   VC_TRY(make_tmap_nhwc(&p->tmB, dy, Cout, W, H, Nimg, g.pw, g.ph, g.pn));
