@@ -709,10 +709,12 @@ k_ce(__nv_bfloat16* __restrict__ logits, long long ld, const int* __restrict__ l
   }
   __syncthreads();
   mx = bcast;
+  constexpr float kLog2e = 1.4426950408889634f;
+  const float mxl = -mx * kLog2e;
   float sum = 0.f;
 #pragma unroll
   for (int j = 0; j < kCeVecs * 8; ++j) {
-    v[j] = __expf(v[j] - mx);
+    v[j] = exp2f(fmaf(v[j], kLog2e, mxl));  // one FFMA + EX2; the -inf padding becomes 0
     sum += v[j];
   }
   __syncthreads();
@@ -727,9 +729,10 @@ k_ce(__nv_bfloat16* __restrict__ logits, long long ld, const int* __restrict__ l
   __syncthreads();
   sum = bcast;
   const float mask = label != 0 ? 1.f : 0.f;  // tf.sign(tf.to_float(labels)), labels >= 0
+  float ll = 0.f;
   if (threadIdx.x == 0) {
     const int lc = label < 0 ? 0 : (label >= V ? V - 1 : label);
-    const float ll = __bfloat162float(logits[(long long)row * ld + lc]);
+    ll = __bfloat162float(logits[(long long)row * ld + lc]);
     const float ce = logf(sum) + mx - ll;
     if (ce_rows) ce_rows[(long long)n * T + t] = ce;
     if (mask != 0.f) {
@@ -741,19 +744,22 @@ k_ce(__nv_bfloat16* __restrict__ logits, long long ld, const int* __restrict__ l
     __syncthreads();  // the label logit was read above before anyone overwrites it
     const float gm = mask * loss_scale / fmaxf(count[0], 1.f);
     const float g = gm / sum;
+    // softmax * g for every column (padding columns hold exp(-inf) = 0); the one-hot term is patched into the label
+    // column by one thread afterwards instead of a compare + select per element
 #pragma unroll
     for (int c = 0; c < kCeVecs; ++c) {
       const int i = threadIdx.x + c * kCeThreads;
       if (i < vecs) {
         float a[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const int col = 8 * i + k;
-          a[k] = v[c * 8 + k] * g - (col == label ? gm : 0.f);
-          if (col >= V) a[k] = 0.f;
-        }
+        for (int k = 0; k < 8; ++k) a[k] = v[c * 8 + k] * g;
         p[i] = make_uint4(pack_bf16(a[0], a[1]), pack_bf16(a[2], a[3]), pack_bf16(a[4], a[5]), pack_bf16(a[6], a[7]));
       }
+    }
+    if (gm != 0.f && label >= 0 && label < V) {  // block-uniform
+      __syncthreads();
+      if (threadIdx.x == 0)
+        logits[(long long)row * ld + label] = __float2bfloat16(exp2f(fmaf(ll, kLog2e, mxl)) * g - gm);
     }
   }
 }
