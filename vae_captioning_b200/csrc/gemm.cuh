@@ -1106,6 +1106,11 @@ constexpr int kWgHaloBytes = kHaloLineRows * 10 * 128;  // 20,480: x box 16 w x 
 constexpr int kWgDyBytes = 64 * 128;                    // 8,192: dy box 8 x 8 pixels x 64 channels
 constexpr int kWgStageBytes = kWgHaloBytes + kWgDyBytes;
 constexpr int kWgStages = 7;
+// kWide (Cout % 128 == 0): the CTA owns 128 output channels (two dy boxes, N = 128 MMAs: 8 KB of operands read from shared
+// memory per 64 tensor cycles instead of 6 KB per 32) and HALF of the taps, because 5 accumulators of 128 columns exceed
+// the 512 TMEM columns: half 0 = taps 0..5 (three pairs), half 1 = taps 6, 7, 8 (pair (6, 7) and 8 paired with itself).
+constexpr int kWgWideStageBytes = kWgHaloBytes + 2 * kWgDyBytes;
+constexpr int kWgWideStages = 6;
 
 struct WgradHaloArgs {
   float* dw;          // [9 * Cin, Cout] fp32, accumulated with atomics
@@ -1113,25 +1118,35 @@ struct WgradHaloArgs {
   int tiles_w, tiles_h, n_img;  // 8 x 8 patches per image row / column (ragged edges: TMA zero fill)
   int k_total, splits;
 };
+__host__ __device__ constexpr int wg_stage_bytes(bool wide) { return wide ? kWgWideStageBytes : kWgStageBytes; }
+__host__ __device__ constexpr int wg_stages(bool wide) { return wide ? kWgWideStages : kWgStages; }
 
+template <bool kWide>
 static __global__ void __launch_bounds__(256, 1)
 conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDy,
                        const WgradHaloArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kWgStages * kWgStageBytes);
+  constexpr int kStages = wg_stages(kWide), kStageBytes = wg_stage_bytes(kWide);
+  constexpr int kBN = kWide ? 128 : 64;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
   uint64_t* full = bars;
-  uint64_t* empty = bars + kWgStages;
-  uint64_t* tfull = bars + 2 * kWgStages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kWgStages + 1);
+  uint64_t* empty = bars + kStages;
+  uint64_t* tfull = bars + 2 * kStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int unit = blockIdx.x / a.splits;
-  const int split = blockIdx.x - unit * a.splits;
-  const int n_chunks = a.Cout / 64;
+  const int unit0 = blockIdx.x / a.splits;
+  const int split = blockIdx.x - unit0 * a.splits;
+  const int tap_half = kWide ? (unit0 & 1) : 0;
+  const int unit = kWide ? (unit0 >> 1) : unit0;
+  const int n_chunks = a.Cout / kBN;
   const int c_chunk = unit / n_chunks;
   const int n_chunk = unit - c_chunk * n_chunks;
+  // tap pairs of this CTA: pair p covers taps (tap0 + 2p, tap0 + 2p + 1); the last pair of the last group is (8, 8)
+  const int tap0 = kWide ? tap_half * 6 : 0;
+  const int n_pairs = kWide ? (tap_half == 0 ? 3 : 2) : 5;
   const int kps = (a.k_total + a.splits - 1) / a.splits;
   const int kb_begin = split * kps;
   const int kb_end = min(a.k_total, kb_begin + kps);
@@ -1141,7 +1156,7 @@ conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
     tma_prefetch_desc(&tmDy);
   }
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < kWgStages; ++i) {
+    for (int i = 0; i < kStages; ++i) {
       mbar_init(&full[i], 1);
       mbar_init(&empty[i], 1);
     }
@@ -1163,14 +1178,15 @@ conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
         const int r = kb / a.tiles_w;
         const int w0 = tiw * 8, h0 = (r % a.tiles_h) * 8, n0 = r / a.tiles_h;
         mbar_wait(&empty[stage], phase ^ 1);
-        uint8_t* sx = smem + stage * kWgStageBytes;
+        uint8_t* sx = smem + stage * kStageBytes;
         if (elect_one()) {
-          mbar_expect_tx(&full[stage], kWgStageBytes);
+          mbar_expect_tx(&full[stage], kStageBytes);
           tma_load_4d(sx, &tmX, &full[stage], c_chunk * 64, w0 - 1, h0 - 1, n0);
-          tma_load_4d(sx + kWgHaloBytes, &tmDy, &full[stage], n_chunk * 64, w0, h0, n0);
+          tma_load_4d(sx + kWgHaloBytes, &tmDy, &full[stage], n_chunk * kBN, w0, h0, n0);
+          if (kWide) tma_load_4d(sx + kWgHaloBytes + kWgDyBytes, &tmDy, &full[stage], n_chunk * kBN + 64, w0, h0, n0);
         }
         __syncwarp();
-        if (++stage == kWgStages) {
+        if (++stage == kStages) {
           stage = 0;
           phase ^= 1;
         }
@@ -1178,29 +1194,30 @@ conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
     }
   } else if (warp == 1) {
     {  // whole warp walks the k-range, one elected lane issues
-      const uint32_t idesc = make_idesc_bf16(kBM, 64, true, true);
+      const uint32_t idesc = make_idesc_bf16(kBM, kBN, true, true);
       int stage = 0;
       uint32_t phase = 0;
       for (int kb = kb_begin; kb < kb_end; ++kb) {
         mbar_wait(&full[stage], phase);
         tc_fence_after();
-        const uint32_t sx = smem_u32(smem + stage * kWgStageBytes);
+        const uint32_t sx = smem_u32(smem + stage * kStageBytes);
         const uint64_t bdesc = make_smem_desc(sx + kWgHaloBytes, 8192u, 1024);
         if (elect_one()) {
 #pragma unroll
           for (int p = 0; p < 5; ++p) {
-            const int ta = 2 * p, tb = p < 4 ? 2 * p + 1 : 8;
+            if (p >= n_pairs) break;
+            const int ta = tap0 + 2 * p, tb = ta < 8 ? ta + 1 : 8;
             const int ra = (ta / 3) * kHaloLineRows + ta % 3, rb = (tb / 3) * kHaloLineRows + tb % 3;
             const uint64_t adesc = make_smem_desc(sx + ra * 128, uint32_t(rb - ra) * 128u, kHaloLineRows * 128);
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-              umma_bf16(tmem_base + p * 64, adesc + uint64_t(k * ((2 * kHaloLineRows * 128) >> 4)), bdesc + uint64_t(k * (2048 >> 4)),
+              umma_bf16(tmem_base + p * kBN, adesc + uint64_t(k * ((2 * kHaloLineRows * 128) >> 4)), bdesc + uint64_t(k * (2048 >> 4)),
                         idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
           }
           umma_commit(&empty[stage]);
         }
         __syncwarp();
-        if (++stage == kWgStages) {
+        if (++stage == kStages) {
           stage = 0;
           phase ^= 1;
         }
@@ -1219,15 +1236,15 @@ conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
       // instruction adds 32 consecutive floats of one dW row instead of one float in each of 32 rows.
       float* stage = reinterpret_cast<float*>(smem) + q * 1024;
 #pragma unroll 1
-      for (int p = 0; p < 5; ++p) {
-        const int tap = 2 * p + (q >> 1);
-        const bool keep = p < 4 || q < 2;  // the second half of the last pair is a copy of tap 8 (warp-uniform)
-        float* o = a.dw + ((long long)tap * a.Cin + c_chunk * 64 + (q & 1) * 32) * a.Cout + n_chunk * 64 + lane;
+      for (int p = 0; p < n_pairs; ++p) {
+        const int tap = tap0 + 2 * p + (q >> 1);
+        const bool keep = tap <= 8;  // the second half of the pair (8, 8) is a copy of tap 8 (warp-uniform)
+        float* o = a.dw + ((long long)tap * a.Cin + c_chunk * 64 + (q & 1) * 32) * a.Cout + n_chunk * kBN + lane;
 #pragma unroll 1
-        for (int c = 0; c < 64; c += 32) {
+        for (int c = 0; c < kBN; c += 32) {
           float v[32];
           __syncwarp();
-          tmem_ld32(tmem_base + (uint32_t(q * 32) << 16) + p * 64 + c, v);
+          tmem_ld32(tmem_base + (uint32_t(q * 32) << 16) + p * kBN + c, v);
           tmem_ld_wait();
           if (keep) {
 #pragma unroll

@@ -227,16 +227,15 @@ bool gemm_pair_wanted(int m_tiles, int bn, int b_mn, int k_blocks) {
   const bool legal = m_tiles >= 2 && bn >= 32 && bn % 32 == 0 && (b_mn == 0 || bn % 128 == 0);
   if (!legal) return false;
   if (g_pair_mode == 1) return true;
-  // short contractions are bound by their epilogue (conv1_1 as a K = 64 GEMM, the K = 512 vocabulary projection: measured
-  // 0.52 -> 0.67 ms and 0.295 -> 0.31 ms as pairs), where coupling two SMs only costs
-  return bn >= 128 && k_blocks >= 12 && (m_tiles % 2 == 0 || m_tiles >= 9);
+  // automatic: everywhere except where rounding an odd m-tile count up to even wastes more than a tenth of the work
+  (void)k_blocks;
+  return m_tiles % 2 == 0 || m_tiles >= 9;
 }
 
 bool halo_pair_wanted(int bn) {
   gemm_pair_wanted(2, 128, 0, 16);  // reads the environment once
-  // a 256 x 64 pair MMA is no faster than two 128 x 64 ones (conv1_2 as pairs: 0.98 -> 1.22 ms), 256 x 128 is
-  // (conv2_2: 0.94 -> 0.80 ms, conv2_1: 0.48 -> 0.45 ms)
-  return g_pair_mode == 1 || (g_pair_mode != 0 && bn >= 128);
+  (void)bn;  // 64-wide pair tiles pay as well (conv1_2: 1.02 -> 0.85 ms)
+  return g_pair_mode != 0;
 }
 
 int plan_gemm(GemmPlan* p, const Operand& A, const Operand* A2, long long a2_at, const Operand& B, int M, int N, int K,
@@ -333,12 +332,13 @@ bool conv_wgrad_halo_applicable(int W, int H, int Cin, int Cout) {
   return enabled && Cin % 64 == 0 && Cout % 64 == 0 && Cin <= wg_max_ch() && Cout <= wg_max_ch() && W >= 56 && H >= 56;
 }
 
-int launch_conv_wgrad_halo(cudaStream_t stream, const void* x, const void* dy, float* dw, int W, int H, int Nimg, int Cin,
-                           int Cout) {
+template <bool kWide>
+static int launch_conv_wgrad_halo_t(cudaStream_t stream, const void* x, const void* dy, float* dw, int W, int H, int Nimg,
+                                    int Cin, int Cout) {
   static bool configured = false;
-  const int smem = kWgStages * kWgStageBytes + 1024 + 256;
+  const int smem = wg_stages(kWide) * wg_stage_bytes(kWide) + 1024 + 256;
   if (!configured) {
-    VC_CUDA(cudaFuncSetAttribute(conv_wgrad_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    VC_CUDA(cudaFuncSetAttribute(conv_wgrad_halo_kernel<kWide>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
   WgradHaloArgs a{};
@@ -349,17 +349,28 @@ int launch_conv_wgrad_halo(cudaStream_t stream, const void* x, const void* dy, f
   a.tiles_h = (H + 7) / 8;
   a.n_img = Nimg;
   a.k_total = a.tiles_w * a.tiles_h * Nimg;
-  const int units = (Cin / 64) * (Cout / 64);
+  // wide: (64 input channels) x (128 output channels) x (tap half); narrow: (64) x (64), all nine taps
+  const int units = kWide ? (Cin / 64) * (Cout / 128) * 2 : (Cin / 64) * (Cout / 64);
   a.splits = std::max(1, std::min(num_sms() / units, a.k_total));
   CUtensorMap tmX, tmDy;
   VC_TRY(make_tmap_nhwc(&tmX, x, Cin, W, H, Nimg, kHaloLineRows, 10, 1));
   VC_TRY(make_tmap_nhwc(&tmDy, dy, Cout, W, H, Nimg, 8, 8, 1));
   {
     ProfScope ps(stream, "conv_wgrad_halo");
-    conv_wgrad_halo_kernel<<<units * a.splits, 256, smem, stream>>>(tmX, tmDy, a);
+    conv_wgrad_halo_kernel<kWide><<<units * a.splits, 256, smem, stream>>>(tmX, tmDy, a);
   }
   VC_CUDA(cudaGetLastError());
   return VC_OK;
+}
+
+int launch_conv_wgrad_halo(cudaStream_t stream, const void* x, const void* dy, float* dw, int W, int H, int Nimg, int Cin,
+                           int Cout) {
+  static const bool wide_ok = [] {
+    const char* e = getenv("VC_WGRAD_WIDE");
+    return !(e && e[0] == '0');
+  }();
+  if (wide_ok && Cout % 128 == 0) return launch_conv_wgrad_halo_t<true>(stream, x, dy, dw, W, H, Nimg, Cin, Cout);
+  return launch_conv_wgrad_halo_t<false>(stream, x, dy, dw, W, H, Nimg, Cin, Cout);
 }
 
 bool conv_halo_stream_applicable(int W, int H, int Cin, int Cout) {

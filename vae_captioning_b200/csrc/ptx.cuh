@@ -202,8 +202,11 @@ __device__ __forceinline__ uint32_t mapa_u32(const void* p, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(p)), "r"(rank));
   return r;
 }
+// (default qualifiers, i.e. CTA-scope release: what this arrival orders is the thread's TMEM reads, which
+// tcgen05.wait::ld + tcgen05.fence::before_thread_sync have already completed; `.release.cluster` costs a MEMBAR.ALL +
+// ERRBAR per arrival that waits for every global store in flight -- 14 % of the samples of the first pair kernels)
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA loads of a CTA pair: data lands in THIS CTA's shared memory, the bytes are signalled on the mbarrier at the
 // shared::cluster address `bar_cluster` (the leader's `full` barrier)
