@@ -17,6 +17,7 @@
 // need no transposes. A may also come from a 4-D NHWC tensor map (3x3 SAME convolution taps with
 // TMA out-of-bounds zero fill doing the padding) or be split across two tensor maps.
 #pragma once
+#include <type_traits>
 #include "ptx.cuh"
 
 namespace vc {
@@ -107,6 +108,22 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmCore& g, int tile) {
   return t;
 }
 
+// An epilogue may declare `static constexpr bool kPrefetch = true`, a `struct Pre` and
+//   __device__ void prefetch(const GemmCore& g, const TileCoord& t, int row, Pre& pre) const
+// which the epilogue threads call BEFORE they wait for the tile's accumulator (global loads whose latency then hides behind
+// the tile's MMAs); operator() receives `const Pre*` as a last argument.
+struct EpiNoPre {};
+template <class E, class = void>
+struct epi_prefetches {
+  static constexpr bool value = false;
+  using type = EpiNoPre;
+};
+template <class E>
+struct epi_prefetches<E, std::enable_if_t<E::kPrefetch>> {
+  static constexpr bool value = true;
+  using type = typename E::Pre;
+};
+
 // Epi must provide:
 //   static constexpr int kSmemBytes;   // epilogue staging (multiple of 2048), split evenly over the 2 groups
 //   static constexpr bool kPairOk;     // may run under gemm_tc_kernel<Epi, 1> (CTA pairs)
@@ -115,7 +132,7 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmCore& g, int tile) {
 // called by each of the 128 threads of epilogue group `grp` (row = 0..127 = TMEM lane = tile row) once the
 // accumulator is complete. tmem_row_addr addresses column 0 of this thread's warp lane quarter;
 // grp_smem is the group's half of the staging area; phase is per-thread state carried across tiles.
-//   __device__ void finish() const     // called once per epilogue thread after the last tile
+//   __device__ void finish(uint8_t* grp_smem, int phase) const   // called once per epilogue thread after the last tile
 //
 // kPair = 1 (launched as clusters of 2): the two CTAs of a pair own m-tiles 2p and 2p + 1 of the same n-tile. Each stages
 // its own A tile and HALF of the B tile (rows / columns [rank * bn/2, +bn/2) of it); every TMA load signals the LEADER's
@@ -372,11 +389,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int acc = ord % nacc;
       const uint32_t acc_phase = (ord / nacc) & 1;
       const TileCoord t = tile_of(tile);
+      [[maybe_unused]] typename epi_prefetches<Epi>::type pre;
+      if constexpr (epi_prefetches<Epi>::value) epi.prefetch(g, t, q * 32 + lane, pre);
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
       if (t.kb_end > t.kb_begin) {
         const uint32_t taddr = tmem_base + acc * acc_stride + (uint32_t(q * 32) << 16);
-        epi(taddr, g, t, q * 32 + lane, grp_smem, grp, epi_phase);
+        if constexpr (epi_prefetches<Epi>::value) epi(taddr, g, t, q * 32 + lane, grp_smem, grp, epi_phase, &pre);
+        else epi(taddr, g, t, q * 32 + lane, grp_smem, grp, epi_phase);
       }
       tc_fence_before();
       __syncwarp();
@@ -385,7 +405,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         else mbar_arrive(&tempty[acc]);
       }
     }
-    epi.finish();
+    epi.finish(grp_smem, epi_phase);
   }
   tc_fence_before();
   if (kPair) cluster_sync_all();  // neither CTA may leave while the other can still touch its barriers / shared memory
@@ -411,7 +431,7 @@ struct EpiStore {
   // staging for the atomic path: one 32 x 32 fp32 block per epilogue warp (2 groups x 4 warps x 4 KB)
   static constexpr int kSmemBytes = 32 * 1024;
   static constexpr bool kPairOk = true;  // tile-local epilogue: runs unchanged in either CTA of a pair
-  __device__ __forceinline__ void finish() const {}
+  __device__ __forceinline__ void finish(uint8_t*, int) const {}
 
   __device__ __forceinline__ void operator()(uint32_t taddr, const GemmCore&, const TileCoord& t, int row,
                                              uint8_t* grp_smem, int, int&) const {
@@ -499,27 +519,72 @@ struct EpiStore {
 //   kConvPool: same with a fused 2x2/2 max-pool (partners are lanes of a warp), box {64, pw/2, ph*th/2, pn*tn}
 enum TmaOutMode : int { kRows = 0, kConv = 1, kConvPool = 2 };
 
-struct EpiTma {
+// kRelu = true (EpiTmaRelu, kConv mode only; the input gradients of the fine-tune pass): the tile is the gradient with
+// respect to a ReLU output, `relu_src` holds that forward activation (same NHWC geometry as the output): the epilogue zeroes
+// the gradient where the activation is not positive -- what k_relu_bwd did in a separate pass over three feature maps --
+// and accumulates the per-channel sums of the masked (bf16-rounded) gradient, i.e. the bias gradient, in a 2 KB
+// shared-memory table per epilogue group that is flushed to `dbias` with one atomic per channel at the end of the CTA.
+template <bool kRelu>
+struct EpiTmaT {
   CUtensorMap tm;
   const float* bias;  // nullable, indexed by n (16-byte aligned)
   int N, bn, relu, mode;
   float alpha;
-  static constexpr int kSmemBytes = 32 * 1024;  // 2 groups x (128 rows x 128 B)
+  const __nv_bfloat16* relu_src;  // kRelu: forward activation [n_img, H, W, N] bf16
+  float* dbias;                   // kRelu: [N] fp32, accumulated
+  int W, H, n_img;                // kRelu: extent of the output feature map
+  // 2 groups x (128 rows x 128 B staging [+ 512 fp32 channel sums + 4 x 64 partial sums of the current chunk])
+  static constexpr int kStageBytes = 16 * 1024;
+  static constexpr int kSmemBytes = kRelu ? 38 * 1024 : 32 * 1024;
   static constexpr bool kPairOk = true;
+  static constexpr bool kPrefetch = kRelu;
+  struct Pre {
+    const __nv_bfloat16* row;  // this thread's pixel of relu_src (nullptr: outside the feature map)
+    uint4 a[8];                // its first 64 channels of the tile
+  };
+  __device__ __forceinline__ void prefetch(const GemmCore& g, const TileCoord& t, int row, Pre& pre) const {
+    const int lane = row & 31, q = row >> 5;
+    const PatchOrigin pq = conv_patch_origin(g, t.m_blk, q);
+    const int w = pq.w + lane % g.pw, h = pq.h + (lane / g.pw) % g.ph, n = pq.n + lane / (g.pw * g.ph);
+    pre.row = nullptr;
+    if (w < W && h < H && n < n_img) {
+      pre.row = relu_src + (((long long)n * H + h) * W + w) * N;
+      const uint4* a4 = reinterpret_cast<const uint4*>(pre.row + t.n_blk * bn);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) pre.a[j] = __ldg(a4 + j);
+    }
+  }
 
-  __device__ __forceinline__ void finish() const {
+  __device__ __forceinline__ void finish(uint8_t* buf, int phase) const {
     if ((threadIdx.x & 127) == 0) bulk_wait_all();  // the issuing thread of each group
+    if constexpr (kRelu) {
+      if (!(phase & 2)) return;  // this group never saw a tile (group-uniform): its table was never cleared
+      named_bar_sync(1 + (((threadIdx.x >> 5) - 4) >> 2), 128);  // every warp's shared-memory atomics are in
+      const float* sums = reinterpret_cast<const float*>(buf + kStageBytes);
+      for (int c = threadIdx.x & 127; c < N && c < 512; c += 128)
+        if (sums[c] != 0.f) atomicAdd(dbias + c, sums[c]);
+    }
   }
 
   // The accumulator row is rounded to packed bf16 pairs right after the bias add; ReLU and the 2x2 max-pool then run
   // on the pairs (max commutes with the monotone rounding, so the result equals pooling / clamping in fp32 first)
   // with half the instructions and half the shuffles.
   __device__ __forceinline__ void operator()(uint32_t taddr, const GemmCore& g, const TileCoord& t, int row,
-                                             uint8_t* buf, int grp, int& phase) const {
+                                             uint8_t* buf, int grp, int& phase, const Pre* pre = nullptr) const {
     const int lane = row & 31, q = row >> 5;
     const int n_base = t.n_blk * bn;
     PatchOrigin po{0, 0, 0};
     if (mode != kRows) po = conv_patch_origin(g, t.m_blk, 0);
+    [[maybe_unused]] const __nv_bfloat16* relu_row = nullptr;  // this thread's pixel of the forward activation
+    [[maybe_unused]] float* sums = reinterpret_cast<float*>(buf + kStageBytes);
+    if constexpr (kRelu) {
+      if (!(phase & 2)) {  // first tile of this group: clear the channel sums (bit 1 of the carried state marks it done)
+        for (int c = row; c < 512; c += 128) sums[c] = 0.f;
+        named_bar_sync(1 + grp, 128);
+        phase |= 2;
+      }
+      relu_row = pre->row;
+    }
 #pragma unroll 1
     for (int c = 0; c < bn; c += 64) {
       const int n0 = n_base + c;
@@ -554,6 +619,27 @@ struct EpiTma {
           p[j] = *reinterpret_cast<const uint32_t*>(&x);
         }
       }
+      if constexpr (kRelu) {
+        // gradient of ReLU: keep where the forward activation is positive; pixels outside the map contribute nothing
+        if (relu_row != nullptr && n0 + 64 <= N) {
+          const uint4* a4 = reinterpret_cast<const uint4*>(relu_row + n0);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const uint4 a = c == 0 ? pre->a[j] : __ldg(a4 + j);  // the first chunk was fetched ahead of the accumulator
+            const uint32_t aw[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              // bf16 > 0  <=>  sign bit clear and not zero (activations are ReLU outputs: never negative, never NaN)
+              const uint32_t lo = (aw[k] & 0x7fffu) != 0 && (aw[k] & 0x8000u) == 0 ? 0x0000ffffu : 0u;
+              const uint32_t hi = (aw[k] & 0x7fff0000u) != 0 && (aw[k] & 0x80000000u) == 0 ? 0xffff0000u : 0u;
+              p[4 * j + k] &= (lo | hi);
+            }
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) p[j] = 0u;
+        }
+      }
       int srow = row;
       bool writer = true;
       if (mode == kConvPool) {
@@ -581,6 +667,27 @@ struct EpiTma {
       }
       fence_proxy_async();
       named_bar_sync(1 + grp, 128);
+      if constexpr (kRelu) {
+        // channel sums of the staged chunk: thread (rg, cp) adds channel pair cp over rows [32 rg, 32 rg + 32)
+        const int cp = row & 31, rg = row >> 5;
+        float sx = 0.f, sy = 0.f;
+#pragma unroll 8
+        for (int r = rg * 32; r < rg * 32 + 32; ++r) {
+          const uint32_t u = *reinterpret_cast<const uint32_t*>(buf + r * 128 + (((cp >> 2) ^ (r & 7)) << 4) + (cp & 3) * 4);
+          sx += __uint_as_float(u << 16);
+          sy += __uint_as_float(u & 0xffff0000u);
+        }
+        // (no shared-memory float atomics: they are compare-and-swap loops, and four warps meeting on 64 addresses doubled
+        // the time of the 64-channel layer) the four row groups park their partial sums, row group 0 owns the table
+        float* part = sums + 512;
+        part[rg * 64 + 2 * cp] = sx;
+        part[rg * 64 + 2 * cp + 1] = sy;
+        named_bar_sync(1 + grp, 128);
+        if (rg == 0 && n0 + 2 * cp + 1 < 512) {
+          sums[n0 + 2 * cp] += part[2 * cp] + part[64 + 2 * cp] + part[128 + 2 * cp] + part[192 + 2 * cp];
+          sums[n0 + 2 * cp + 1] += part[2 * cp + 1] + part[64 + 2 * cp + 1] + part[128 + 2 * cp + 1] + part[192 + 2 * cp + 1];
+        }
+      }
       if (row == 0) {
         if (mode == kRows)
           tma_store_2d(&tm, buf, n0, t.m_blk * kBM);
@@ -595,6 +702,9 @@ struct EpiTma {
   }
 };
 
+using EpiTma = EpiTmaT<false>;
+using EpiTmaRelu = EpiTmaT<true>;
+
 // ------------------------------------------------------------------------------------------
 // fp32 row-matrix tile store through shared memory + TMA: out[m, n] = acc * alpha + bias[n], 32 columns (128 bytes) at
 // a time. Same reason as EpiTma: a TMEM lane is a tile row, so EpiStore's per-thread 16-byte stores touch 32 cache lines
@@ -608,7 +718,7 @@ struct EpiTmaF32 {
   static constexpr int kSmemBytes = 32 * 1024;  // 2 groups x (128 rows x 128 B)
   static constexpr bool kPairOk = true;
 
-  __device__ __forceinline__ void finish() const {
+  __device__ __forceinline__ void finish(uint8_t*, int) const {
     if ((threadIdx.x & 127) == 0) bulk_wait_all();
   }
   __device__ __forceinline__ void operator()(uint32_t taddr, const GemmCore&, const TileCoord& t, int row, uint8_t* buf, int grp,
@@ -828,10 +938,13 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const uint32_t acc_phase = (ord / nacc) & 1;
       TileCoord t;
       t.m_blk = m_of(mi); t.n_blk = n_blk; t.split = 0; t.kb_begin = 0; t.kb_end = 9;
+      [[maybe_unused]] typename epi_prefetches<Epi>::type pre;
+      if constexpr (epi_prefetches<Epi>::value) epi.prefetch(g, t, q * 32 + lane, pre);
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + acc * acc_stride + (uint32_t(q * 32) << 16);
-      epi(taddr, g, t, q * 32 + lane, grp_smem, grp, epi_phase);
+      if constexpr (epi_prefetches<Epi>::value) epi(taddr, g, t, q * 32 + lane, grp_smem, grp, epi_phase, &pre);
+      else epi(taddr, g, t, q * 32 + lane, grp_smem, grp, epi_phase);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
@@ -839,7 +952,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         else mbar_arrive(&tempty[acc]);
       }
     }
-    epi.finish();
+    epi.finish(grp_smem, epi_phase);
   }
   tc_fence_before();
   if (kPair) cluster_sync_all();
@@ -1066,10 +1179,13 @@ conv_halo_stream_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
       const uint32_t acc_phase = (ord / nacc) & 1;
       TileCoord t;
       t.m_blk = m_of(tile); t.n_blk = tile % g.n_tiles; t.split = 0; t.kb_begin = 0; t.kb_end = 9 * g.cpk;
+      [[maybe_unused]] typename epi_prefetches<Epi>::type pre;
+      if constexpr (epi_prefetches<Epi>::value) epi.prefetch(g, t, q * 32 + lane, pre);
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + acc * acc_stride + (uint32_t(q * 32) << 16);
-      epi(taddr, g, t, q * 32 + lane, grp_smem, grp, epi_phase);
+      if constexpr (epi_prefetches<Epi>::value) epi(taddr, g, t, q * 32 + lane, grp_smem, grp, epi_phase, &pre);
+      else epi(taddr, g, t, q * 32 + lane, grp_smem, grp, epi_phase);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
@@ -1077,7 +1193,7 @@ conv_halo_stream_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
         else mbar_arrive(&tempty[acc]);
       }
     }
-    epi.finish();
+    epi.finish(grp_smem, epi_phase);
   }
   tc_fence_before();
   if (kPair) cluster_sync_all();

@@ -48,7 +48,7 @@ struct EpiLstmBwd {
   LstmBwdCommon c;
   static constexpr int kSmemBytes = 0;
   static constexpr bool kPairOk = false;
-  __device__ __forceinline__ void finish() const {}
+  __device__ __forceinline__ void finish(uint8_t*, int) const {}
   __device__ __forceinline__ void operator()(uint32_t taddr, const GemmCore&, const TileCoord& tc, int row, uint8_t*,
                                              int, int&) const {
     const int m = tc.m_blk * kBM + row;

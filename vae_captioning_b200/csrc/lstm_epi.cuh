@@ -24,7 +24,7 @@ struct EpiLstmFwd {
   int precise;  // 1: expf / tanhf (generation: token ties are decided at the 1e-4 level); 0: MUFU tanh.approx (training)
   static constexpr int kSmemBytes = 0;
   static constexpr bool kPairOk = false;
-  __device__ __forceinline__ void finish() const {}
+  __device__ __forceinline__ void finish(uint8_t*, int) const {}
 
   __device__ __forceinline__ void operator()(uint32_t taddr, const GemmCore&, const TileCoord& tc, int row, uint8_t*,
                                              int, int&) const {

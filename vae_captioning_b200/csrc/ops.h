@@ -92,8 +92,10 @@ int lstm_bwd_seq2(cudaStream_t stream, const LstmSeqBwdArgs& a);
 // vgg_bwd.cu -------------------------------------------------------------------------------
 int conv3x3_wgrad(cudaStream_t s, const void* x, const void* dy, float* dw, int B, int hw, int cin, int cout,
                   const char* tag = "conv_wgrad");
+// relu_src (nullable): the forward activation whose gradient dx is ([B, hw, hw, cin] bf16, a ReLU output): dx is then
+// masked where relu_src <= 0 and dbias[cin] += per-channel sums of the masked dx, all inside the GEMM epilogue
 int conv3x3_dgrad(cudaStream_t s, const void* dy, const void* wt_d, void* dx, int B, int hw, int cin, int cout,
-                  const char* tag = "conv_dgrad");
+                  const char* tag = "conv_dgrad", const void* relu_src = nullptr, float* dbias = nullptr);
 int dgrad_shadow(cudaStream_t s, const float* w_hwio, void* wt_d, int cin, int cout);
 int relu_pool_bwd(cudaStream_t s, const void* dA, const void* out, void* dY, int B, int hw, int C, bool pooled, float* db);
 
