@@ -29,6 +29,13 @@ void vc_test_pair_mode(int mode);
 int vc_conv3x3_bwd(const void* x, const void* dy, const float* w, float* dw, void* dx, int B, int hw, int cin, int cout,
                    void* stream);
 
+/* Input gradient of one 3x3 SAME convolution with the ReLU derivative of the layer below taken in the GEMM epilogue
+ * (the fine-tune backward pass between un-pooled layers, ops/optimizers.py:49-82 through image_embeddings.py:46-205):
+ * dx = conv3x3_same(dy, rot180(w)^T) where act > 0, else 0; dbias[cin] += per-channel sums of dx. act: bf16 NHWC
+ * [B, hw, hw, cin] (a ReLU output); dbias must be zeroed by the caller. cin a multiple of 64, <= 512. */
+int vc_conv3x3_dgrad_relu(const void* dy, const float* w, const void* act, void* dx, float* dbias, int B, int hw, int cin,
+                          int cout, void* stream);
+
 /* Derivative of ReLU (+ 2x2/2 max-pool when pooled) with the bias gradient fused: dY = dA routed to the first maximum
  * of each window where the stored post-ReLU activation `out` is positive; db[C] += per-channel sum of dY.
  * (tf.nn.relu / tf.nn.max_pool gradients, image_embeddings.py:46-211.) */

@@ -8,5 +8,5 @@ mkdir -p gpurun_out
 CS=/usr/local/cuda/bin/compute-sanitizer
 for TOOL in memcheck racecheck; do
   timeout 1500 $CS --tool $TOOL --error-exitcode 9 --print-limit 20 python scripts/sanitize_case.py > gpurun_out/sanitize_$TOOL.log 2>&1
-  echo "$TOOL rc=$?"; grep -E "ERROR SUMMARY|RACECHECK SUMMARY|train step ok|decode ok|Error|error" gpurun_out/sanitize_$TOOL.log | head -12
+  echo "$TOOL rc=$?"; grep -E "ERROR SUMMARY|RACECHECK SUMMARY|train step ok|kernel level ok|decode ok|Error|error" gpurun_out/sanitize_$TOOL.log | head -12
 done

@@ -74,3 +74,31 @@ def test_relu_pool_backward_bit_exact(B, hw, C, pooled):
     # fused bias gradient: per-channel sum of dY (fp32 accumulation of the bf16 values)
     want = ref.float().sum(dim=(0, 1, 2))
     assert (db.cpu() - want).abs().max().item() <= 1e-3 * max(1.0, want.abs().max().item())
+
+
+@pytest.mark.parametrize("B,hw,cin,cout", [(2, 16, 128, 128), (3, 56, 128, 256), (3, 28, 256, 512), (5, 14, 512, 512),
+                                           (2, 112, 128, 128), (1, 24, 128, 256), (3, 40, 64, 256), (1, 32, 64, 64)])
+def test_conv3x3_dgrad_with_fused_relu_derivative(B, hw, cin, cout):
+    """The fine-tune pass takes the ReLU derivative and the bias gradient of an un-pooled layer in the epilogue of the
+    input-gradient GEMM above it (EpiTmaRelu). Against the unfused entry on the same inputs the masked gradient must be
+    BIT-IDENTICAL (same accumulator, same bf16 rounding, then a mask) and the bias gradient must equal the column sums of
+    that bf16 tensor to fp32 summation-order noise. Covers the generic implicit GEMM, both halo kernels, CTA pairs, odd
+    tile counts and ragged tiles."""
+    lib = L.load()
+    g = torch.Generator().manual_seed(hw * 77 + cin + B)
+    x = torch.zeros(B, hw, hw, cin, dtype=torch.bfloat16)
+    dy = torch.randn(B, hw, hw, cout, generator=g).to(torch.bfloat16)
+    w = (torch.randn(3, 3, cin, cout, generator=g) / np.sqrt(9 * cin)).float()
+    act = torch.relu(torch.randn(B, hw, hw, cin, generator=g)).to(torch.bfloat16)  # half of it exactly zero
+    xd, dyd, wd, actd = x.cuda(), dy.cuda(), w.cuda(), act.cuda()
+    dw = torch.zeros(9 * cin, cout, device="cuda")
+    dx_plain = torch.zeros(B, hw, hw, cin, dtype=torch.bfloat16, device="cuda")
+    L.check(lib.vc_conv3x3_bwd(L.ptr(xd), L.ptr(dyd), L.ptr(wd), L.ptr(dw), L.ptr(dx_plain), B, hw, cin, cout, L.stream_ptr()))
+    dx = torch.full((B, hw, hw, cin), 3.0, dtype=torch.bfloat16, device="cuda")
+    db = torch.zeros(cin, device="cuda")
+    L.check(lib.vc_conv3x3_dgrad_relu(L.ptr(dyd), L.ptr(wd), L.ptr(actd), L.ptr(dx), L.ptr(db), B, hw, cin, cout, L.stream_ptr()))
+    torch.cuda.synchronize()
+    want = torch.where(actd > 0, dx_plain, torch.zeros_like(dx_plain))
+    assert torch.equal(dx.view(torch.int16), want.view(torch.int16))
+    ref_db = want.float().sum(dim=(0, 1, 2))
+    assert (db - ref_db).abs().max().item() <= 1e-4 * max(1.0, ref_db.abs().max().item())

@@ -195,8 +195,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     else tmem_alloc<512>(tmem_slot);
   }
   tc_fence_before();
+  __syncthreads();                // the TMEM address written by tcgen05.alloc is read by every thread below
   if (kPair) cluster_sync_all();  // the peer's barriers must be initialised before anything arrives on them
-  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -835,8 +835,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     else tmem_alloc<512>(tmem_slot);
   }
   tc_fence_before();
+  __syncthreads();
   if (kPair) cluster_sync_all();
-  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -1048,8 +1048,8 @@ conv_halo_stream_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
     else tmem_alloc<512>(tmem_slot);
   }
   tc_fence_before();
+  __syncthreads();
   if (kPair) cluster_sync_all();
-  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 

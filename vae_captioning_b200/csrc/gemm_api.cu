@@ -91,6 +91,19 @@ extern "C" int vc_conv3x3_bwd(const void* x, const void* dy, const float* w, flo
   return st;
 }
 
+extern "C" int vc_conv3x3_dgrad_relu(const void* dy, const float* w, const void* act, void* dx, float* dbias, int B, int hw,
+                                     int cin, int cout, void* stream) {
+  using namespace vc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  void* wt_d = nullptr;
+  VC_CUDA(cudaMalloc(&wt_d, (size_t)9 * cin * cout * 2));
+  int st = dgrad_shadow(s, w, wt_d, cin, cout);
+  if (st == VC_OK) st = conv3x3_dgrad(s, dy, wt_d, dx, B, hw, cin, cout, "conv_dgrad", act, dbias);
+  cudaStreamSynchronize(s);
+  cudaFree(wt_d);
+  return st;
+}
+
 // db: fp32 [C] device, accumulated into (the bias gradient = per-channel sum of dY)
 extern "C" int vc_relu_pool_bwd(const void* dA, const void* out, void* dY, float* db, int B, int hw, int C, int pooled,
                                 void* stream) {
