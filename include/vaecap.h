@@ -146,6 +146,13 @@ int vc_train_step_images_u8(vc_handle* h, const uint8_t* images_host, const int3
 int vc_stage_batch(vc_handle* h, int slot, const void* feats_or_images_host, int kind, const int32_t* cap_lbl_host,
                    const int32_t* cap_in_host, const int32_t* len_host, const float* c_v_host, int B, int T, void* copy_stream);
 int vc_train_step_staged(vc_handle* h, int slot, int64_t global_step, const vc_rng* rng, vc_step_out* out, void* stream);
+/* Deferred read-back of a step's scalars (the reference's sess.run returns them synchronously, main.py:229-244; waiting
+ * for step i before enqueueing step i+1 leaves the GPU idle for the host's launch time). After a train step called with
+ * out == NULL, vc_step_result_queue enqueues the 64-byte device-to-host copy of ITS scalars on `stream` and returns at
+ * once; vc_step_result waits for the OLDEST queued copy and fills `out`. At most two results may be outstanding
+ * (VC_E_STATE beyond that, and when nothing is queued). */
+int vc_step_result_queue(vc_handle* h, void* stream);
+int vc_step_result(vc_handle* h, vc_step_out* out);
 /* Data-parallel form of the staged step: forward + backward from the slot, gradients left in vc_grad_buffer for the
  * caller's all-reduce; finish with vc_apply_gradients(1/world). */
 int vc_forward_backward_staged(vc_handle* h, int slot, int64_t global_step, const vc_rng* rng, void* stream);

@@ -304,3 +304,42 @@ def test_double_buffered_feed_equals_plain_steps(kw):
         staged.stage_batch(2, **pinned[0])
     plain.close()
     staged.close()
+
+
+def test_deferred_step_results_equal_synchronous_ones():
+    """vc_step_result_queue / vc_step_result: the host enqueues step i + 1 before it reads the scalars of step i. Every
+    step's result must be the one the synchronous call returns, in order; at most two may be outstanding; popping with
+    nothing queued is an error, not a hang."""
+    B, T = 4, 6
+    cfg, params, _ = make_case(SMALL, B, T, seed=13, prior="GMM", use_c_v=True)
+    batches = [O.synthetic_batch(cfg, B, T, seed=40 + i, dtype=torch.float64, ragged=True) for i in range(5)]
+    feeds = [feed_of(b) for b in batches]
+    sync = engine_for(cfg, params, B, T)
+    want = [sync.train_step(anneal=i, rng={"seed": 9 + i}, **feeds[i]) for i in range(5)]
+    lazy = engine_for(cfg, params, B, T)
+    with pytest.raises(Exception):
+        lazy.pop_result()  # nothing queued (and no step has run)
+    pinned = [{k: (lazy.pinned(v) if v is not None else None) for k, v in f.items()} for f in feeds]
+    got = []
+    lazy.stage_batch(0, **pinned[0])
+    for i in range(5):
+        if i + 1 < 5:
+            lazy.stage_batch((i + 1) & 1, **pinned[i + 1])
+        assert lazy.train_step_staged(i & 1, anneal=i, rng={"seed": 9 + i}, fetch=False) is None
+        lazy.queue_result()
+        if i >= 1:
+            got.append(lazy.pop_result())  # the result of step i - 1, while step i is in flight
+    # two outstanding are allowed, a third is refused
+    lazy.queue_result()
+    with pytest.raises(Exception):
+        lazy.queue_result()
+    got.append(lazy.pop_result())
+    dup = lazy.pop_result()  # the second queued copy of the last step
+    with pytest.raises(Exception):
+        lazy.pop_result()
+    assert len(got) == 5
+    for a, b in zip(got + [dup], want + [want[-1]]):
+        for k in ("rec_loss", "kld", "lower_bound", "global_norm", "n_tokens", "annealing"):
+            assert abs(a[k] - b[k]) <= 1e-4 * max(1.0, abs(b[k])), (k, a[k], b[k])
+    sync.close()
+    lazy.close()

@@ -253,6 +253,22 @@ int vc_train_step_staged(vc_handle* h, int slot, int64_t gs, const vc_rng* rng, 
   VC_GUARD_END
 }
 
+int vc_step_result_queue(vc_handle* h, void* stream) {
+  VC_GUARD_BEGIN
+  if (!h) return set_error(VC_E_ARG, "null handle");
+  cudaSetDevice(h->m.device);
+  return h->m.result_queue((cudaStream_t)stream);
+  VC_GUARD_END
+}
+
+int vc_step_result(vc_handle* h, vc_step_out* out) {
+  VC_GUARD_BEGIN
+  if (!h) return set_error(VC_E_ARG, "null handle");
+  cudaSetDevice(h->m.device);
+  return h->m.result_pop(out);
+  VC_GUARD_END
+}
+
 int vc_forward_backward_staged(vc_handle* h, int slot, int64_t gs, const vc_rng* rng, void* stream) {
   VC_GUARD_BEGIN
   if (!h) return set_error(VC_E_ARG, "null handle");

@@ -108,6 +108,16 @@ class Model {
   float *st_feats = nullptr, *st_cv = nullptr;
   int32_t *st_lbl = nullptr, *st_in = nullptr, *st_len = nullptr;
   float* host_scal = nullptr;  // pinned
+  // deferred results (vc_step_result_queue / vc_step_result): ring of two pinned 16-float slots + what fetch() needs besides
+  struct PendingResult {
+    cudaEvent_t ev = nullptr;
+    int n = 0;
+    float ann = 0.f;
+  } pending[2];
+  int pending_head = 0, pending_count = 0;
+  int result_queue(cudaStream_t s);
+  int result_pop(vc_step_out* out);
+  void fill_out(vc_step_out* out, const float* h, int n, float ann) const;
   float *emb_keep_buf = nullptr, *out_keep_buf = nullptr;  // Philox keep masks of the decoder dropouts (allocated on first use)
   // Double-buffered feed (vc_stage_batch / vc_train_step_staged): the next step's host buffers are copied into one slot
   // on a copy stream while the current step computes from the other. Slots are allocated on first use.
@@ -117,10 +127,12 @@ class Model {
     float* cv = nullptr;
     int32_t *lbl = nullptr, *in = nullptr, *len = nullptr;
     cudaEvent_t ready = nullptr, consumed = nullptr;
+    cudaEvent_t img_ready = nullptr, px_free = nullptr;  // frozen extractor: image copy done / VGG16 forward has read px
     int B = 0, T = 0, kind = -1;
-    bool has_cv = false, filled = false, in_use = false;
+    bool has_cv = false, filled = false, in_use = false, px_used = false;
   };
   StageSlot slots[2];
+  cudaStream_t h2d_stream = nullptr;  // image copies of the frozen-extractor feed (so that they overlap the previous forward)
   int stage_slot(int slot, const void* px_host, int kind, const int32_t* lbl, const int32_t* inp, const int32_t* len,
                  const float* cv, int B, int T, cudaStream_t copy_stream);
   int step_from_slot(int slot, int64_t gs, const vc_rng* rng, cudaStream_t s, bool apply_update = true);

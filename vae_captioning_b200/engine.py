@@ -318,6 +318,17 @@ class Engine(object):
                                               ctypes.byref(out) if fetch else None, self._stream()))
         return out.as_dict() if fetch else None
 
+    def queue_result(self):
+        """Queue the read-back of the last step's scalars (a step called with fetch=False) without waiting for it."""
+        L.check(self.lib.vc_step_result_queue(self._h, self._stream()))
+
+    def pop_result(self):
+        """Wait for the OLDEST queued read-back; same dict as train_step returns. Lets the host enqueue step i + 1 before
+        it reads the loss of step i (at most two results outstanding)."""
+        out = VcStepOut()
+        L.check(self.lib.vc_step_result(self._h, ctypes.byref(out)))
+        return out.as_dict()
+
     def forward_backward_staged(self, slot, anneal, rng=None):
         """Data-parallel half of train_step_staged: gradients stay in grad_buffer() for the all-reduce; finish with
         apply_gradients(1 / world)."""
