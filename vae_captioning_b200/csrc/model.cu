@@ -541,8 +541,10 @@ int Model::side_join(cudaStream_t s) {
   return VC_OK;
 }
 
+// defer_weight_grads: only the recurrence and the input gradient run here; the caller runs lstm_weight_grads later (data
+// parallel: the decoder's weight / bias gradients wait until the big posterior-head bucket is on the wire, see backward()).
 int Model::lstm_backward(LstmNet& L, int N, int T, const int32_t* len, const float* d_out, const float* out_keep,
-                         cudaStream_t s) {
+                         cudaStream_t s, bool defer_weight_grads) {
   const int steps = L.pre + T;
   uint16_t* Gt = (uint16_t*)L.G;
   uint16_t* dGt = (uint16_t*)L.dG;
@@ -577,6 +579,24 @@ int Model::lstm_backward(LstmNet& L, int N, int T, const int32_t* len, const flo
     a.pre = L.pre; a.T = T; a.steps = steps; a.N = N; a.E = L.E; a.H = L.H;
     VC_TRY(lstm_bwd_seq(s, a));
   }
+  if (!defer_weight_grads) VC_TRY(lstm_weight_grads(L, N, T, s));
+  // input gradient: dX[steps*N, E] = dG x W_x^T  (B = rows 0..E of the natural shadow)
+  const long long rows = (long long)steps * N;
+  Operand AG{L.dG, rows, 4LL * L.H, 4LL * L.H, false};
+  Operand BW{L.w_nat, L.E, 4LL * L.H, 4LL * L.H, false};
+  EpiStore ex{};
+  ex.out = L.dX;
+  ex.ld = L.E;
+  ex.alpha = 1.f;
+  {
+    ProfTag ptag("lstm_dx");
+    VC_TRY(gemm_store(s, AG, nullptr, 0, BW, (int)rows, L.E, 4 * L.H, ex, L.E % 256 == 0 ? 256 : 64, 1));
+  }
+  return VC_OK;
+}
+
+int Model::lstm_weight_grads(LstmNet& L, int N, int T, cudaStream_t s) {
+  const int steps = L.pre + T;
   // weight gradient: dW[E+H, 4H] = [X ; H_prev]^T x dG over all steps (one GEMM, split-K, fp32 atomics). Nothing in the
   // backward pass waits for it (nor for the bias gradient): with the side stream on, both run there, beside whatever
   // the main stream does next -- for the decoder that is the encoder's BPTT, which leaves 68 of 148 SMs idle.
@@ -610,19 +630,7 @@ int Model::lstm_backward(LstmNet& L, int N, int T, const int32_t* len, const flo
   }
   VC_TRY(colsum_bf16(s, L.dG, rows, 4 * L.H, 4 * L.H, gp(L.p_bias)));
   VC_TRY(grad_ready_params({L.p_kernel, L.p_bias}, s));  // data parallel: this bucket leaves from the stream that made it
-  s = main_s;
-  GridCap uncap(0);
-  // input gradient: dX[steps*N, E] = dG x W_x^T  (B = rows 0..E of the natural shadow)
-  Operand AG{L.dG, rows, 4LL * L.H, 4LL * L.H, false};
-  Operand BW{L.w_nat, L.E, 4LL * L.H, 4LL * L.H, false};
-  EpiStore ex{};
-  ex.out = L.dX;
-  ex.ld = L.E;
-  ex.alpha = 1.f;
-  {
-    ProfTag ptag("lstm_dx");
-    VC_TRY(gemm_store(s, AG, nullptr, 0, BW, (int)rows, L.E, 4 * L.H, ex, L.E % 256 == 0 ? 256 : 64, 1));
-  }
+  (void)main_s;
   return VC_OK;
 }
 
@@ -841,11 +849,19 @@ int Model::backward(const StepInputs& in, cudaStream_t s) {
   // decoder BPTT
   VC_CUDA(cudaMemsetAsync(dec.dh_carry, 0, (size_t)N * Hd * sizeof(float), s));
   VC_CUDA(cudaMemsetAsync(dec.dc_carry, 0, (size_t)N * Hd * sizeof(float), s));
-  VC_TRY(lstm_backward(dec, N, T, in.len, dOut, cfg.dec_lstm_drop < 1.f ? in.rng.out_keep_dev : nullptr, s));
-  VC_TRY(embed_scatter(s, dec.dX + (size_t)dec.pre * N * E, in.cap_in, gp(pidx("decoder/net/dec_embeddings")),
-                       cfg.dec_keep_rate < 1.f ? in.rng.emb_keep_dev : nullptr, 1.f / cfg.dec_keep_rate, g_tail + 1, N, T,
-                       E, V));
-  VC_TRY(grad_ready_params({pidx("decoder/net/dec_embeddings")}, s));
+  // Data parallel with an encoder: the posterior heads' gradient (71 MB under GMM / AG) is the biggest bucket and needs
+  // only the decoder's recurrence and input gradient. The decoder's weight / bias gradients and its embedding scatter
+  // (0.15 ms of work nothing waits for) run AFTER that bucket is on the wire, under its all-reduce, instead of before it.
+  const bool dec_late = comm_world() > 1 && !cfg.no_encoder;
+  auto decoder_leaf_grads = [&]() -> int {
+    if (dec_late) VC_TRY(lstm_weight_grads(dec, N, T, s));
+    VC_TRY(embed_scatter(s, dec.dX + (size_t)dec.pre * N * E, in.cap_in, gp(pidx("decoder/net/dec_embeddings")),
+                         cfg.dec_keep_rate < 1.f ? in.rng.emb_keep_dev : nullptr, 1.f / cfg.dec_keep_rate, g_tail + 1, N, T,
+                         E, V));
+    return grad_ready_params({pidx("decoder/net/dec_embeddings")}, s);
+  };
+  VC_TRY(lstm_backward(dec, N, T, in.len, dOut, cfg.dec_lstm_drop < 1.f ? in.rng.out_keep_dev : nullptr, s, dec_late));
+  if (!dec_late) VC_TRY(decoder_leaf_grads());
   if (!cfg.no_encoder) {
     const int He = cfg.encoder_hidden;
     const int SZ = S * Z;
@@ -899,6 +915,7 @@ int Model::backward(const StepInputs& in, cudaStream_t s) {
       VC_TRY(colsum_bf16(s, dheads, N, heads_cols, heads_cols, gp(p_heads_b)));
     }
     VC_TRY(grad_ready_params({p_heads_w, p_heads_b, pidx("decoder/net/z_rnn/kernel"), pidx("decoder/net/z_rnn/bias")}, s));
+    if (dec_late) VC_TRY(decoder_leaf_grads());
     VC_CUDA(cudaMemsetAsync(enc.dc_carry, 0, (size_t)N * He * sizeof(float), s));
     VC_TRY(lstm_backward(enc, N, T, in.len, nullptr, nullptr, s));
     VC_TRY(embed_scatter(s, enc.dX + (size_t)enc.pre * N * E, in.cap_lbl, gp(pidx("encoder/enc_embeddings")), nullptr, 1.f,

@@ -238,7 +238,8 @@ class Model {
   int add_view(const std::string& name, std::vector<int64_t> shape, int parent, int64_t parent_off, int64_t ld);
   int lstm_forward(LstmNet& L, int N, int T, const int32_t* len, void* out, const float* out_keep, cudaStream_t s);
   int lstm_backward(LstmNet& L, int N, int T, const int32_t* len, const float* d_out, const float* out_keep,
-                    cudaStream_t s);
+                    cudaStream_t s, bool defer_weight_grads = false);
+  int lstm_weight_grads(LstmNet& L, int N, int T, cudaStream_t s);
   float* gp(int pi) { return Gf + params[pi].offset; }
   float* pp(int pi) { return Pf + params[pi].offset; }
   int pidx(const std::string& n) const {
