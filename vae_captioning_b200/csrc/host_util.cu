@@ -378,11 +378,19 @@ bool conv_halo_stream_applicable(int W, int H, int Cin, int Cout) {
     const char* e = getenv("VC_CONV_HALO2");
     return !(e && e[0] == '0');
   }();
-  return enabled && (Cin == 128 || Cin == 256) && (Cout == 64 || Cout == 128) && W % 8 == 0 && H % 2 == 0 && H >= 16;
+  // Cout = 256 (conv3_x, 56 x 56): the generic path moves 1152 KB of operands per 128 x 256 tile (125 B/clk per SM at
+  // tensor speed -- it runs at 73 % tensor-pipe utilisation, i.e. at the ~90 B/clk an SM ingests), this one 720 KB; the
+  // price is the ragged last tile row (56 = 3.5 x 16 lines: 12.5 % of the MMAs multiply zero fill)
+  static const bool wide = [] {
+    const char* e = getenv("VC_CONV_HALO2_WIDE");
+    return !(e && e[0] == '0');
+  }();
+  return enabled && (Cin == 128 || Cin == 256) && (Cout == 64 || Cout == 128 || (wide && Cout == 256)) && W % 8 == 0 &&
+         H % 2 == 0 && H >= 16;
 }
 
 int plan_conv_halo_stream(GemmPlan* p, const void* in, const void* wt, const ConvGeom& cg) {
-  if (!(cg.Cin == 128 || cg.Cin == 256) || !(cg.Cout == 64 || cg.Cout == 128) || cg.W % 8 != 0)
+  if (!(cg.Cin == 128 || cg.Cin == 256) || !(cg.Cout == 64 || cg.Cout == 128 || cg.Cout == 256) || cg.W % 8 != 0)
     return set_error(VC_E_SHAPE, "plan_conv_halo_stream: unsupported layer %dx%d Cin=%d Cout=%d", cg.W, cg.H, cg.Cin, cg.Cout);
   memset(p, 0, sizeof(*p));
   GemmCore& g = p->core;
