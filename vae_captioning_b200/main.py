@@ -118,7 +118,8 @@ def run(params, feeder=None, val_feeder=None, test_feeder=None, vocabulary=None,
             out("Restoring from checkpoint")
             checkpoint.restore(eng, ckpt)
         gs = 0
-        lb = rl = float("nan")
+        pending = 0
+        lb = rl = kl = ann = float("nan")
         for e in range(params.num_epochs):
             gs_epoch = 0
             stop = False
@@ -140,17 +141,30 @@ def run(params, feeder=None, val_feeder=None, test_feeder=None, vocabulary=None,
                     if nxt is not None:
                         slot ^= 1
                         eng.stage_batch(slot, **_feed(params, *nxt))
-                    res = eng.train_step_staged(cur_slot, anneal=gs, rng={"seed": gs})
-                    kl, rl, lb, ann = res["kld"], res["rec_loss"], res["lower_bound"], res["annealing"]
+                    # the step's scalars come back one step late (vc_step_result_queue / vc_step_result): the next step is
+                    # enqueued before the host waits for this one's loss; at a report point the queue is drained first, so
+                    # what is printed is the loss of the step named in the line, as in the reference (main.py:240-250)
+                    eng.train_step_staged(cur_slot, anneal=gs, rng={"seed": gs}, fetch=False)
+                    eng.queue_result()
+                    pending += 1
                     gs += 1
                     gs_epoch += 1
-                    if gs % report_every == 0:
+                    report = gs % report_every == 0
+                    while pending > (0 if report else 1):
+                        res = eng.pop_result()
+                        pending -= 1
+                        kl, rl, lb, ann = res["kld"], res["rec_loss"], res["lower_bound"], res["annealing"]
+                    if report:
                         out("Epoch: {} Iteration: {} VLB: {} Rec Loss: {}".format(e, gs, lb, rl))
                         if not params.no_encoder:
                             out("Annealing coefficient:{} KLD: {}".format(ann, kl))
                     if gs_epoch * params.batch_size > params.num_ex_per_epoch:
                         stop = True
                         break
+                while pending:
+                    res = eng.pop_result()
+                    pending -= 1
+                    kl, rl, lb, ann = res["kld"], res["rec_loss"], res["lower_bound"], res["annealing"]
                 if hasattr(batches, "close"):
                     batches.close()
                 if n_batches == 0 or not getattr(feeder, "endless", False):
