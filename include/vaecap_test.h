@@ -23,6 +23,9 @@ int vc_gemm_bf16(const void* A, int a_mn, long long lda, const void* B, int b_mn
 /* CTA-pair policy of the tcgen05 mainloop (cluster of 2, cta_group::2): -1 = automatic (default; VC_PAIR in the
  * environment), 0 = never, 1 = wherever the tile shape allows it. Lets the parity tests run the same GEMM both ways. */
 void vc_test_pair_mode(int mode);
+/* Dual-N tiles of the same mainloop (two adjacent 256-column n-tiles share one A tile, accumulators fill the 512 TMEM
+ * columns): -1 automatic (VC_DUAL in the environment), 0 never, 1 wherever bn = 256 and there are >= 2 n-tiles. */
+void vc_test_dual_mode(int mode);
 
 /* Gradients of one 3x3 SAME convolution (tf.nn.conv2d in utils/image_embeddings.py:40-205, differentiated by
  * ops/optimizers.py:49-82): x, dy bf16 NHWC; w fp32 HWIO; dw fp32 [9*Cin, Cout] (zeroed by the call); dx bf16 NHWC. */

@@ -159,3 +159,42 @@ def test_gemm_pair_matches_single_bitwise():
         finally:
             lib.vc_test_pair_mode(-1)
     assert torch.equal(outs[0], outs[1])
+
+
+@pytest.mark.parametrize("pair", [0, 1])
+def test_gemm_dual_n_tiles_match_single_tiles_bitwise(pair):
+    """Dual-N tiles (two adjacent 256-column n-tiles share one A tile; both accumulators fill the 512 TMEM columns, epilogue
+    group g drains n-tile g) change the schedule, not the arithmetic: every output element sees the same k order. Covers
+    K-major and MN-major operands, an odd n-tile count (the last dual tile's second half is all zero fill), ragged M / N,
+    split-K with atomics, bf16 output, with and without CTA pairs."""
+    lib = L.load()
+    cases = [(1024, 1024, 2048, 0, 0, 1, 0), (768, 1280 + 40, 1024, 0, 1, 1, 0), (640, 512, 4096, 1, 1, 1, 0),
+             (512, 768, 2048, 0, 0, 1, 1), (300, 700, 2048, 0, 0, 3, 0)]
+    for (M, N, K, a_mn, b_mn, splits, out_bf16) in cases:
+        g = torch.Generator(device="cpu").manual_seed(M + N)
+        A = torch.randn(M, K, generator=g).to(torch.bfloat16)
+        B = torch.randn(N, K, generator=g).to(torch.bfloat16)
+        Ad = (A.t().contiguous() if a_mn else A).cuda()
+        Bd = (B.t().contiguous() if b_mn else B).cuda()
+        bias = torch.randn(N, generator=g).cuda()
+        outs = []
+        for dual in (0, 1):
+            lib.vc_test_pair_mode(pair)
+            lib.vc_test_dual_mode(dual)
+            try:
+                out = torch.zeros(M, N, dtype=torch.bfloat16 if out_bf16 else torch.float32, device="cuda")
+                L.check(lib.vc_gemm_bf16(L.ptr(Ad), a_mn, ctypes.c_longlong(M if a_mn else K), L.ptr(Bd), b_mn,
+                                         ctypes.c_longlong(N if b_mn else K), L.ptr(out), ctypes.c_longlong(N), L.ptr(bias), M, N, K,
+                                         256, splits, 0, out_bf16, 1 if splits > 1 else 0, L.stream_ptr()))
+                torch.cuda.synchronize()
+                outs.append(out.float().clone())
+            finally:
+                lib.vc_test_pair_mode(-1)
+                lib.vc_test_dual_mode(-1)
+        ref = A.float().cuda() @ B.float().cuda().t() + bias
+        tol = (2e-2 if out_bf16 else 2e-3) * ref.abs().max().item()
+        assert (outs[1] - ref).abs().max().item() <= tol, (M, N, K, a_mn, b_mn, splits)
+        if splits == 1:
+            assert torch.equal(outs[0], outs[1]), (M, N, K, a_mn, b_mn)
+        else:  # fp32 atomics meet in a different order
+            assert (outs[0] - outs[1]).abs().max().item() <= 1e-3 * ref.abs().max().item()

@@ -52,6 +52,10 @@ struct GemmCore {
   // (OOB zero fill = SAME padding); B is the same un-shifted patch of the output gradient.
   int pw, ph, pn, tw, th, tiles_w, tiles_h, cpk;  // cpk = Cin / 64 chunks per filter tap
   int n_img;                                      // A_WGRAD3x3: image count (an image index >= n_img zero-fills)
+  int dual;      // 1 (bn = 256 only): a tile is TWO adjacent n-tiles sharing one A tile -- both 256-column accumulators fill the
+                 // 512 TMEM columns (no double buffering), a stage holds A + two B blocks, epilogue group g drains n-tile 2j + g.
+                 // The operand bytes an SM ingests per FLOP drop by a quarter (A 16 KB + 2 x 16 KB instead of 2 x (16 + 16) KB
+                 // as a pair): the long-K GEMMs run at the ~90 B/clk an SM ingests, not at the tensor pipe's rate.
   int pair;      // 1: run as CTA pairs (gemm_tc_kernel<Epi, 1>: cluster of 2, tcgen05 cta_group::2). m_tiles is then even
                  // (rounded up; the surplus tile reads zero fill and its stores are clipped) and tmB's box holds bn / 2 rows
   int tap_rows;  // A_CONV3x3 over a window map (conv1_1): k-block kb is filter ROW kb; the three taps of the row and their
@@ -148,7 +152,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int b_rows = kPair ? g.bn / 2 : g.bn;  // rows (K-major) / columns (MN-major) of B this CTA stages
-  const int stage_bytes = gemm_stage_bytes(b_rows);
+  const bool dual = g.dual != 0;
+  const int b_block = b_rows * kBK * 2;        // bytes of one staged B block
+  const int stage_bytes = kABytes + (dual ? 2 : 1) * b_block;
   uint8_t* epi_smem = smem + g.stages * stage_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(epi_smem + Epi::kSmemBytes);
   uint64_t* full = bars;
@@ -156,21 +162,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* tfull = bars + 2 * kMaxStages;
   uint64_t* tempty = bars + 2 * kMaxStages + kMaxAcc;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 2 * kMaxAcc);
-  const int nacc = gemm_acc_buffers(g.bn);
-  const int acc_stride = gemm_acc_stride(g.bn);
+  const int nacc = dual ? 1 : gemm_acc_buffers(g.bn);
+  const int acc_stride = dual ? 512 : gemm_acc_stride(g.bn);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   // pair mode: the schedule runs over PAIR tiles (m_tiles / 2 of them per n-tile), one cluster per pair tile
   const uint32_t rank = kPair ? cluster_ctarank() : 0u;
-  const int total_tiles = (kPair ? g.m_tiles / 2 : g.m_tiles) * g.n_tiles * g.splits;
+  const int n_sched = dual ? (g.n_tiles + 1) / 2 : g.n_tiles;  // dual: the schedule runs over pairs of n-tiles
+  const int total_tiles = (kPair ? g.m_tiles / 2 : g.m_tiles) * n_sched * g.splits;
   const int tile0 = kPair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
   const int tile_step = kPair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   GemmCore gs = g;  // what decode_tile sees
   if (kPair) gs.m_tiles = g.m_tiles / 2;
+  gs.n_tiles = n_sched;
   auto tile_of = [&](int tile) {
     TileCoord t = decode_tile(gs, tile);
     if (kPair) t.m_blk = t.m_blk * 2 + (int)rank;
+    if (dual) t.n_blk *= 2;  // first n-tile of the pair; the second one is t.n_blk + 1 (past N: zero fill in, nothing out)
     return t;
   };
 
@@ -186,7 +195,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int i = 0; i < kMaxAcc; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], kPair ? 8 : 4);  // pair: the four epilogue warps of both CTAs arrive on the leader's
+      // pair: the four epilogue warps of both CTAs arrive on the leader's; dual: both epilogue groups drain every tile
+      mbar_init(&tempty[i], (kPair ? 8 : 4) * (dual ? 2 : 1));
     }
     fence_mbar_init();
   }
@@ -258,11 +268,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 for (int q = 0; q < 4; ++q)
                   tma_load_4d_pair(sa + q * 4096, &tmA, fb, c0, po[q].w + fs - 1, po[q].h + fr - 1, po[q].n);
               }
-              const int nb = t.n_blk * g.bn + (int)rank * b_rows;
-              if (g.b_mn == 1) {
-                for (int j = 0; j < b_rows; j += 64) tma_load_2d_pair(sb + j * 128, &tmB, fb, nb + j, kb * kBK);
-              } else if (g.b_mn == 0) {
-                tma_load_2d_pair(sb, &tmB, fb, kb * kBK, nb);
+              for (int h = 0; h < (dual ? 2 : 1); ++h) {
+                const int nb = (t.n_blk + h) * g.bn + (int)rank * b_rows;
+                uint8_t* sbh = sb + h * b_block;
+                if (g.b_mn == 1) {
+                  for (int j = 0; j < b_rows; j += 64) tma_load_2d_pair(sbh + j * 128, &tmB, fb, nb + j, kb * kBK);
+                } else if (g.b_mn == 0) {
+                  tma_load_2d_pair(sbh, &tmB, fb, kb * kBK, nb);
+                }
               }
             }
           } else if (elect_one()) {
@@ -303,11 +316,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int q = 0; q < 4; ++q)
               tma_load_4d(sa + q * 4096, &tmA, &full[stage], c0, po[q].w + fs - 1, po[q].h + fr - 1, po[q].n);
           }
-          if (g.b_mn == 1) {
-            for (int j = 0; j < g.bn; j += 64)
-              tma_load_2d(sb + j * 128, &tmB, &full[stage], t.n_blk * g.bn + j, kb * kBK);
-          } else if (g.b_mn == 0) {
-            tma_load_2d(sb, &tmB, &full[stage], kb * kBK, t.n_blk * g.bn);
+          for (int h = 0; h < (dual ? 2 : 1); ++h) {
+            uint8_t* sbh = sb + h * b_block;
+            if (g.b_mn == 1) {
+              for (int j = 0; j < g.bn; j += 64)
+                tma_load_2d(sbh + j * 128, &tmB, &full[stage], (t.n_blk + h) * g.bn + j, kb * kBK);
+            } else if (g.b_mn == 0) {
+              tma_load_2d(sbh, &tmB, &full[stage], kb * kBK, (t.n_blk + h) * g.bn);
+            }
           }
           }
           __syncwarp();
@@ -344,6 +360,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const uint32_t sa = smem_u32(smem + stage * stage_bytes);
           const uint64_t adesc = make_smem_desc(sa, a_lbo, 1024);
           const uint64_t bdesc = make_smem_desc(sa + kABytes, b_lbo, 1024);
+          const uint64_t bdesc1 = make_smem_desc(sa + kABytes + b_block, b_lbo, 1024);  // dual: the second n-tile's block
           if (elect_one()) {
 #pragma unroll
             for (int k = 0; k < kBK / 16; ++k) {
@@ -353,6 +370,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               else
                 umma_bf16(d_tmem, adesc + uint64_t(k * a_kstep), bdesc + uint64_t(k * b_kstep), idesc,
                           (kb > t.kb_begin || k > 0) ? 1u : 0u);
+              if (dual) {
+                if (kPair)
+                  umma_bf16_pair(d_tmem + 256, adesc + uint64_t(k * a_kstep), bdesc1 + uint64_t(k * b_kstep), idesc,
+                                 (kb > t.kb_begin || k > 0) ? 1u : 0u);
+                else
+                  umma_bf16(d_tmem + 256, adesc + uint64_t(k * a_kstep), bdesc1 + uint64_t(k * b_kstep), idesc,
+                            (kb > t.kb_begin || k > 0) ? 1u : 0u);
+              }
             }
             if (kPair) umma_commit_pair(&empty[stage]);
             else umma_commit(&empty[stage]);
@@ -385,16 +410,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     int ord = 0;
     const uint32_t tempty_leader = kPair ? mapa_u32(tempty, 0) : 0u;
     for (int tile = tile0; tile < total_tiles; tile += tile_step, ++ord) {
-      if ((ord & 1) != grp) continue;
+      if (!dual && (ord & 1) != grp) continue;
       const int acc = ord % nacc;
       const uint32_t acc_phase = (ord / nacc) & 1;
-      const TileCoord t = tile_of(tile);
+      TileCoord t = tile_of(tile);
+      if (dual) t.n_blk += grp;  // dual: group g drains the tile's n-tile g (TMEM columns [256 g, 256 g + 256))
       [[maybe_unused]] typename epi_prefetches<Epi>::type pre;
       if constexpr (epi_prefetches<Epi>::value) epi.prefetch(g, t, q * 32 + lane, pre);
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
       if (t.kb_end > t.kb_begin) {
-        const uint32_t taddr = tmem_base + acc * acc_stride + (uint32_t(q * 32) << 16);
+        const uint32_t taddr = tmem_base + acc * acc_stride + (dual ? grp * 256 : 0) + (uint32_t(q * 32) << 16);
         if constexpr (epi_prefetches<Epi>::value) epi(taddr, g, t, q * 32 + lane, grp_smem, grp, epi_phase, &pre);
         else epi(taddr, g, t, q * 32 + lane, grp_smem, grp, epi_phase);
       }
@@ -547,7 +573,7 @@ struct EpiTmaT {
     const PatchOrigin pq = conv_patch_origin(g, t.m_blk, q);
     const int w = pq.w + lane % g.pw, h = pq.h + (lane / g.pw) % g.ph, n = pq.n + lane / (g.pw * g.ph);
     pre.row = nullptr;
-    if (w < W && h < H && n < n_img) {
+    if (w < W && h < H && n < n_img && t.n_blk * bn + 64 <= N) {
       pre.row = relu_src + (((long long)n * H + h) * W + w) * N;
       const uint4* a4 = reinterpret_cast<const uint4*>(pre.row + t.n_blk * bn);
 #pragma unroll

@@ -72,6 +72,7 @@ extern "C" int vc_gemm_bf16(const void* A, int a_mn, long long lda, const void* 
 }
 
 extern "C" void vc_test_pair_mode(int mode) { vc::set_pair_mode(mode); }
+extern "C" void vc_test_dual_mode(int mode) { vc::set_dual_mode(mode); }
 
 // Test entries for the convolution backward kernels (parity against torch conv2d gradients on the same bf16 inputs):
 // x, dy bf16 NHWC; w fp32 HWIO; dw fp32 [9*Cin, Cout] (zeroed here); dx bf16 NHWC. All device pointers.

@@ -232,6 +232,27 @@ bool gemm_pair_wanted(int m_tiles, int bn, int b_mn, int k_blocks) {
   return m_tiles % 2 == 0 || m_tiles >= 9;
 }
 
+static int g_dual_mode = -2;
+void set_dual_mode(int mode) { g_dual_mode = mode < -1 || mode > 1 ? -1 : mode; }
+bool gemm_dual_wanted(int n_tiles, int bn, int k_blocks, int tiles_total, int units) {
+  if (g_dual_mode == -2) {
+    const char* e = getenv("VC_DUAL");
+    g_dual_mode = (e && e[0] == '0') ? 0 : (e && e[0] == '1') ? 1 : -1;
+  }
+  if (g_dual_mode == 0 || bn != 256 || n_tiles < 2) return false;
+  if (g_dual_mode == 1) return true;
+  // automatic: the tile's epilogue (two 128 x 256 halves, one per epilogue group) is not overlapped with the next tile's
+  // MMAs, so the contraction must be long; an odd n-tile count wastes half a tile; and the halved tile count must still
+  // fill the machine
+  // (tiles_total counts schedule units -- pair tiles or tiles -- before halving; `units` is what runs side by side)
+  if (!(k_blocks >= 32 && (n_tiles % 2 == 0 || n_tiles >= 9))) return false;
+  const double waves = 0.5 * tiles_total / (double)units;
+  const double eff = waves / (double)(long long)(waves + 0.999999);
+  // the vocabulary input gradient (100 dual tiles on 74 clusters: 1.35 waves) loses more to the second, two-thirds-empty
+  // wave than the tile gains: 0.317 -> 0.323 ms; conv4_x (10.6 waves) 0.80 -> 0.64 ms, conv5_x (2.6 waves) 0.23 -> 0.18
+  return eff >= 0.85;
+}
+
 bool halo_pair_wanted(int bn) {
   gemm_pair_wanted(2, 128, 0, 16);  // reads the environment once
   (void)bn;  // 64-wide pair tiles pay as well (conv1_2: 1.02 -> 0.85 ms)
@@ -256,6 +277,9 @@ int plan_gemm(GemmPlan* p, const Operand& A, const Operand* A2, long long a2_at,
   g.a_switch = -1;
   g.pair = pair_ok && gemm_pair_wanted(g.m_tiles, bn, g.b_mn, (g.k_blocks + g.splits - 1) / g.splits) ? 1 : 0;
   if (g.pair) g.m_tiles = (g.m_tiles + 1) / 2 * 2;
+  g.dual = pair_ok && gemm_dual_wanted(g.n_tiles, bn, (g.k_blocks + g.splits - 1) / g.splits,
+                                       g.m_tiles * g.n_tiles * g.splits / (g.pair ? 2 : 1),
+                                       g.pair ? num_sms() / 2 : num_sms()) ? 1 : 0;
   VC_TRY(operand_tmap(&p->tmA, A, kBM));
   p->tmA2 = p->tmA;
   if (A2 != nullptr && A2->ptr != nullptr) {
@@ -435,6 +459,8 @@ int plan_conv(GemmPlan* p, const void* in, const void* wt, const ConvGeom& cg, i
   g.a_switch = -1;
   g.pair = gemm_pair_wanted(g.m_tiles, bn, 0, g.k_blocks) ? 1 : 0;
   if (g.pair) g.m_tiles = (g.m_tiles + 1) / 2 * 2;  // a surplus tile lies past the last image: zero fill in, clipped out
+  g.dual = gemm_dual_wanted(g.n_tiles, bn, g.k_blocks, g.m_tiles * g.n_tiles / (g.pair ? 2 : 1),
+                            g.pair ? num_sms() / 2 : num_sms()) ? 1 : 0;
   VC_TRY(make_tmap_nhwc(&p->tmA, in, cg.Cin, cg.W, cg.H, cg.Nimg, cg.pw, cg.ph, cg.pn));
   p->tmA2 = p->tmA;
   VC_TRY(make_tmap_2d(&p->tmB, wt, 9ull * cg.Cin, cg.Cout, 9ull * cg.Cin, 64, g.pair ? bn / 2 : bn));

@@ -139,6 +139,10 @@ int plan_conv_halo_stream(GemmPlan* p, const void* in, const void* wt, const Con
 // environment (tests): -1 automatic, 0 off, 1 forced.
 void set_pair_mode(int mode);
 bool gemm_pair_wanted(int m_tiles, int bn, int b_mn, int k_blocks);
+// Dual-N tiles (GemmCore::dual): VC_DUAL=0 never, VC_DUAL=1 wherever legal (bn = 256, >= 2 n-tiles), unset = long contractions
+// only (the accumulators are not double-buffered, so the epilogue of a tile is exposed). set_dual_mode as set_pair_mode.
+void set_dual_mode(int mode);
+bool gemm_dual_wanted(int n_tiles, int bn, int k_blocks, int tiles_total, int units);
 bool halo_pair_wanted(int bn);
 
 // Launch of a kernel written for CTA pairs: clusters of 2, at most `pairs` of them and never more than can be co-resident.
@@ -237,10 +241,11 @@ template <class Epi>
 int launch_gemm_pair(const GemmPlan& p, const Epi& epi, cudaStream_t stream) {
   static int max_clusters = 0;
   GemmCore core = p.core;
-  const int b_rows = core.bn / 2;
+  const int b_rows = (core.dual ? 2 : 1) * core.bn / 2;  // B rows staged per CTA and ring stage
+  const int n_sched = core.dual ? (core.n_tiles + 1) / 2 : core.n_tiles;
   core.stages = gemm_pick_stages(b_rows, Epi::kSmemBytes);
   if (core.stages < 2) return set_error(VC_E_ARG, "launch_gemm: tile too large for shared memory (bn=%d)", core.bn);
-  return launch_pair_kernel(gemm_tc_kernel<Epi, 1>, &max_clusters, core.m_tiles / 2 * core.n_tiles * core.splits, sm_budget(),
+  return launch_pair_kernel(gemm_tc_kernel<Epi, 1>, &max_clusters, core.m_tiles / 2 * n_sched * core.splits, sm_budget(),
                             gemm_smem_bytes(b_rows, core.stages, Epi::kSmemBytes), stream, "gemm", p.tmA, p.tmA2, p.tmB, core, epi);
 }
 
@@ -255,13 +260,14 @@ int launch_gemm(const GemmPlan& p, const Epi& epi, cudaStream_t stream) {
     VC_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<Epi, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured = true;
   }
-  const int total = p.core.m_tiles * p.core.n_tiles * p.core.splits;
+  GemmCore core = p.core;
+  const int b_rows = (core.dual ? 2 : 1) * core.bn;
+  const int total = core.m_tiles * (core.dual ? (core.n_tiles + 1) / 2 : core.n_tiles) * core.splits;
   if (total <= 0) return VC_OK;
   const int grid = total < sm_budget() ? total : sm_budget();
-  GemmCore core = p.core;
-  core.stages = gemm_pick_stages(core.bn, Epi::kSmemBytes);
+  core.stages = gemm_pick_stages(b_rows, Epi::kSmemBytes);
   if (core.stages < 2) return set_error(VC_E_ARG, "launch_gemm: tile too large for shared memory (bn=%d)", core.bn);
-  const int smem = gemm_smem_bytes(core.bn, core.stages, Epi::kSmemBytes);
+  const int smem = gemm_smem_bytes(b_rows, core.stages, Epi::kSmemBytes);
   {
     ProfScope ps(stream, "gemm");
     gemm_tc_kernel<Epi, 0><<<grid, kGemmThreads, smem, stream>>>(p.tmA, p.tmA2, p.tmB, core, epi);
