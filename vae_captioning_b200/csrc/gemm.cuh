@@ -258,8 +258,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                   else
                     tma_load_4d_pair(sa + half * 8192, &tmA, fb, 0, 0, 0, g.n_img);  // past the last tap: zeros
                 }
-                for (int j = 0; j < b_rows; j += 64)
-                  tma_load_4d_pair(sb + j * 128, &tmB, fb, t.n_blk * g.bn + (int)rank * b_rows + j, w0, h0, n0);
+                for (int h = 0; h < (dual ? 2 : 1); ++h)
+                  for (int j = 0; j < b_rows; j += 64)
+                    tma_load_4d_pair(sb + h * b_block + j * 128, &tmB, fb, (t.n_blk + h) * g.bn + (int)rank * b_rows + j, w0, h0, n0);
               } else {  // A_CONV3x3
                 const int tap = kb / g.cpk;
                 const int c0 = (kb - tap * g.cpk) * kBK;
@@ -306,8 +307,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               else
                 tma_load_4d(sa + half * 8192, &tmA, &full[stage], 0, 0, 0, g.n_img);  // past the last tap: zeros
             }
-            for (int j = 0; j < g.bn; j += 64)
-              tma_load_4d(sb + j * 128, &tmB, &full[stage], t.n_blk * g.bn + j, w0, h0, n0);
+            for (int h = 0; h < (dual ? 2 : 1); ++h)
+              for (int j = 0; j < g.bn; j += 64)
+                tma_load_4d(sb + h * b_block + j * 128, &tmB, &full[stage], (t.n_blk + h) * g.bn + j, w0, h0, n0);
           } else {
             const int tap = kb / g.cpk;
             const int c0 = (kb - tap * g.cpk) * kBK;

@@ -531,6 +531,10 @@ int plan_conv_wgrad(GemmPlan* p, const void* in, const void* dy, int W, int H, i
   // pairs: each CTA gathers its own (tap, channel chunk) rows and half of the dy patch columns
   g.pair = gemm_pair_wanted(g.m_tiles, bn, 1, (g.k_blocks + g.splits - 1) / g.splits) ? 1 : 0;
   if (g.pair) g.m_tiles = (g.m_tiles + 1) / 2 * 2;
+  // dual tiles: the gathered x patches (the expensive operand) are fetched once for two 256-column blocks of dy
+  g.dual = Cout % (2 * bn) == 0 && gemm_dual_wanted(g.n_tiles, bn, (g.k_blocks + g.splits - 1) / g.splits,
+                                                     g.m_tiles * g.n_tiles * g.splits / (g.pair ? 2 : 1),
+                                                     g.pair ? num_sms() / 2 : num_sms()) ? 1 : 0;
   VC_TRY(make_tmap_nhwc(&p->tmA, in, Cin, W, H, Nimg, g.pw, g.ph, g.pn));
   p->tmA2 = p->tmA;
   VC_TRY(make_tmap_nhwc(&p->tmB, dy, Cout, W, H, Nimg, g.pw, g.ph, g.pn));

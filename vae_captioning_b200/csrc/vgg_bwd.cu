@@ -139,7 +139,14 @@ int conv3x3_wgrad(cudaStream_t s, const void* x, const void* dy, float* dw, int 
   const int bn = cout >= 256 ? 256 : cout;
   GemmPlan plan;
   const int tiles = ((9 * cin + 127) / 128) * (cout / bn);
-  VC_TRY(plan_conv_wgrad(&plan, x, dy, hw, hw, B, cin, cout, bn, std::max(1, num_sms() / tiles)));
+  int splits = std::max(1, num_sms() / tiles);
+  // dual-N tiles halve the number of schedule units: split the pixel contraction twice as often to keep the SMs busy
+  // (the planner's wave rule then accepts the dual form: 36 m-tiles x 2 n-tiles x 4 splits = 72 dual pair tiles on 74 clusters)
+  if (bn == 256 && cout % 512 == 0) {
+    const long long kb = (long long)B * hw * hw / 64;
+    if (gemm_dual_wanted(cout / bn, bn, (int)(kb / (2 * splits)), tiles * 2 * splits / 2, num_sms() / 2)) splits *= 2;
+  }
+  VC_TRY(plan_conv_wgrad(&plan, x, dy, hw, hw, B, cin, cout, bn, splits));
   EpiStore e{};
   e.out = dw; e.ld = cout; e.alpha = 1.f; e.atomic = 1;
   e.M = 9 * cin; e.N = cout; e.bn = bn;
