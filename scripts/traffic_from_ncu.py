@@ -14,6 +14,8 @@ VGG = ["conv1_1", "conv1_2", "conv2_1", "conv2_2", "conv3_1", "conv3_2", "conv3_
        "conv5_1", "conv5_2", "conv5_3"]
 BY_NAME = {"k_ce(": "ce", "k_adam(": "adam", "k_sumsq(": "sumsq", "k_sample_z(": "sample_z", "k_dz_reduce(": "dz_reduce",
            "lstm_seq_kernel<SeqFwdEpi>": "lstm_fwd_seq", "lstm_seq_kernel<SeqBwdEpi>": "lstm_bwd_seq",
+           "lstm_seq2_kernel<Seq2FwdEpi": "lstm_fwd_seq", "lstm_seq2_kernel<Seq2BwdEpi": "lstm_bwd_seq",
+           "k_sample_z_v4": "sample_z", "k_dz_reduce_v4": "dz_reduce",
            "k_im2col_rgb": "im2col_rgb", "k_embed_gather(": "embed_gather", "k_embed_scatter(": "embed_scatter",
            "k_colsum_bf16(": "colsum_bf16"}
 
